@@ -1,0 +1,615 @@
+// C ABI of basq_b200 (include/basq_b200.h): context, kernel evaluations, staged recombination
+// session and the single-call recombination loop.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+#include <new>
+
+#include "common.cuh"
+
+namespace basq {
+const char* last_error_cstr();
+
+namespace {
+
+__global__ void scale_columns_kernel(double* __restrict__ U, int rows, int cols, int64_t ld,
+                                     const double* __restrict__ s) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)rows * cols) return;
+  const int r = (int)(t / cols), c = (int)(t % cols);
+  U[(int64_t)r * ld + c] *= s[c];
+}
+
+// out = f(C, fx, fy) elementwise for the warped kernels; diag_add on the leading diagonal
+__global__ void warp_gram_kernel(double* __restrict__ C, int64_t a, int64_t b, int mode, const double* __restrict__ fx,
+                                 const double* __restrict__ fy, double diag_add) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a * b) return;
+  const int64_t i = t / b, j = t % b;
+  double c = C[t];
+  if (mode == BASQ_WSABI_L) c = fx[i] * c * fy[j];
+  else if (mode == BASQ_WSABI_M) c = fx[i] * c * fy[j] + 0.5 * c * c;
+  else if (mode == BASQ_MMLT_G) c = fx[i] * fy[j] * expm1(c);
+  if (i == j) c += diag_add;
+  C[t] = c;
+}
+
+// model-space moments of the warped GPs: wsabil_predict / wsabim_predict (BASQ/_wsabi.py:251-277),
+// gspace_predict (SOBER/BASQ/_scale_mmlt.py:211-223)
+__global__ void model_space_kernel(int mode, double offset, int64_t n, double* __restrict__ mean,
+                                   double* __restrict__ var, int write_var) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const double m = mean[p];
+  const double v = var ? var[p] : 0.0;
+  double mo = m, vo = v;
+  if (mode == BASQ_WSABI_L) { mo = offset + 0.5 * m * m; vo = m * v * m; }
+  else if (mode == BASQ_WSABI_M) { mo = offset + 0.5 * (m * m + v); vo = m * v * m + 0.5 * v * v; }
+  else if (mode == BASQ_MMLT_G) { mo = expm1(m + 0.5 * v); vo = mo * mo * expm1(v); }
+  mean[p] = mo;
+  if (write_var) var[p] = vo;
+}
+
+int check_finite_host(const double* v, int64_t n, const char* what) {
+  for (int64_t i = 0; i < n; ++i)
+    BASQ_CHECK(isfinite(v[i]), BASQ_ERR_NUMERIC, "%s contains a non-finite value at %lld", what, (long long)i);
+  return BASQ_OK;
+}
+
+}  // namespace
+}  // namespace basq
+
+using namespace basq;
+
+// =============================================================================================
+// session
+// =============================================================================================
+struct basq_session {
+  basq_ctx* ctx = nullptr;
+  basq_kernel_desc desc;
+  KParams kp;
+  int M = 0, q = 0, n = 0, S = 0, Mtot = 0;
+  int nl = NL_LIN;
+  Landmarks lm;     // Z (+ Xobs appended for the linear posterior-covariance modes)
+  Landmarks lmobs;  // Xobs alone
+  DevBuf Uprime;    // [q, Mtot]
+  DevBuf sz;        // [M] per-landmark factor
+  DevBuf Az;        // [M, n_obs] = K(Z, Xobs) W          (non-linear modes)
+  RecPool pool;
+  DevBuf G;         // [Mtot, ldg]
+  int64_t ldg = 0;
+  DevBuf rank;      // int [S]
+  DevBuf V, corrT;  // chunk buffers of the non-linear modes
+  int64_t chunkP = 0;
+  int64_t idx_base = 0;
+  bool scale_wf = true;
+  std::vector<double> omega_host;
+  std::vector<int> rank_host;
+};
+
+namespace basq {
+namespace {
+
+// G[:, 0..ncols) for local records [p_lo, p_hi), set index = (off + p) mod S
+int session_set_sums(basq_session* s, int64_t off, int S, int64_t p_lo, int64_t p_hi, double* G, int64_t ldg) {
+  basq_ctx* ctx = s->ctx;
+  SetSumArgs a;
+  a.pool = &s->pool;
+  a.lm = s->lm.view();
+  a.off_glob = off;
+  a.S = S;
+  a.nl = s->nl;
+  a.sz = s->sz.as<double>();
+  a.G = G;
+  a.ldg = ldg;
+  if (s->nl == NL_LIN) {
+    a.p_lo = p_lo;
+    a.p_hi = p_hi;
+    a.corrT = nullptr;
+    a.ld_corr = 0;
+    a.accumulate = false;
+    return set_sums(ctx, s->kp, a);
+  }
+  // non-linear kernels need C_h(z_m, x_p) = k(z_m, x_p) - (K_ZX W) k(Xobs, x_p) per pair: build the
+  // correction for a chunk of points with two GEMM-shaped steps, then accumulate.
+  const int n_obs = s->desc.n_obs;
+  BASQ_CUDA(cudaMemsetAsync(G, 0, sizeof(double) * (size_t)s->Mtot * ldg, ctx->stream));
+  for (int64_t c0 = p_lo; c0 < p_hi; c0 += s->chunkP) {
+    const int64_t c1 = std::min(p_hi, c0 + s->chunkP);
+    const int64_t cnt = c1 - c0;
+    BASQ_TRY(base_gram_records(ctx, s->kp, s->lmobs.view(), s->pool, c0, c1, s->V.as<double>(), s->chunkP));
+    // corrT[p, m] = sum_o V[o, p] * Az[m, o]
+    BASQ_TRY(dgemm(ctx, true, true, (int)cnt, s->M, n_obs, 1.0, s->V.as<double>(), s->chunkP, s->Az.as<double>(),
+                   n_obs, 0.0, s->corrT.as<double>(), s->M));
+    a.p_lo = c0;
+    a.p_hi = c1;
+    a.corrT = s->corrT.as<double>();
+    a.ld_corr = s->M;
+    a.accumulate = true;
+    BASQ_TRY(set_sums(ctx, s->kp, a));
+  }
+  return BASQ_OK;
+}
+
+int session_create_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t N_loc, int64_t N_glob,
+                        int64_t idx_base, const void* Z, int64_t M, const double* U, int q, const double* mu,
+                        int S_override, basq_session* s) {
+  PhaseTimer timer(ctx, PH_PREP);
+  BASQ_CHECK(ctx && desc && Z && U, BASQ_ERR_INVALID, "session: NULL argument");
+  BASQ_CHECK(N_loc >= 0 && (X || N_loc == 0), BASQ_ERR_INVALID, "session: bad candidate buffer");
+  BASQ_CHECK(q >= 1 && M >= q, BASQ_ERR_INVALID, "session: need 1 <= q <= M (q=%d, M=%lld)", q, (long long)M);
+  BASQ_CHECK(M <= 1000000, BASQ_ERR_UNSUPPORTED, "session: more than 1e6 landmarks");
+  s->ctx = ctx;
+  s->desc = *desc;
+  BASQ_TRY(make_kparams(desc, &s->kp));
+  BASQ_TRY(compute_center(ctx, desc, Z, M, &s->kp));
+  s->M = (int)M;
+  s->q = q;
+  s->n = q + 1;
+  s->S = S_override > 0 ? S_override : 2 * (q + 1);
+  s->idx_base = idx_base;
+  const int mode = desc->mode;
+  const int n_obs = (mode == BASQ_PLAIN) ? 0 : desc->n_obs;
+  const bool nonlin = (mode == BASQ_WSABI_M || mode == BASQ_MMLT_G);
+  s->nl = mode == BASQ_WSABI_M ? NL_WSABIM : (mode == BASQ_MMLT_G ? NL_MMLT : NL_LIN);
+  s->scale_wf = !nonlin;
+
+  if (mode != BASQ_PLAIN) BASQ_TRY(prep_landmarks(ctx, s->kp, desc->dtype, desc->Xobs, n_obs, nullptr, 0, &s->lmobs));
+  const bool augment = (mode == BASQ_PRED_COV || mode == BASQ_WSABI_L);
+  BASQ_TRY(prep_landmarks(ctx, s->kp, desc->dtype, Z, M, augment ? desc->Xobs : nullptr, augment ? n_obs : 0, &s->lm));
+  s->Mtot = s->lm.count;
+
+  // per-landmark and per-point factors of the warped kernels
+  DevBuf sx;
+  const bool has_factor = (mode == BASQ_WSABI_L || mode == BASQ_WSABI_M || mode == BASQ_MMLT_G);
+  if (has_factor) {
+    BASQ_TRY(s->sz.alloc(sizeof(double) * M));
+    BASQ_TRY(warp_factor(ctx, desc, s->kp, s->lmobs.view(), Z, M, s->sz.as<double>()));
+    BASQ_TRY(sx.alloc(sizeof(double) * std::max<int64_t>(N_loc, 1)));
+    BASQ_TRY(warp_factor(ctx, desc, s->kp, s->lmobs.view(), X, N_loc, sx.as<double>()));
+  }
+
+  // projection matrix U' [q, Mtot]
+  BASQ_TRY(s->Uprime.alloc(sizeof(double) * (size_t)q * s->Mtot));
+  BASQ_CUDA(cudaMemcpy2DAsync(s->Uprime.p, sizeof(double) * s->Mtot, U, sizeof(double) * M, sizeof(double) * M, q,
+                              cudaMemcpyDeviceToDevice, ctx->stream));
+  if (mode == BASQ_WSABI_L) {
+    scale_columns_kernel<<<ceil_div((int64_t)q * M, 256), 256, 0, ctx->stream>>>(s->Uprime.as<double>(), q, (int)M,
+                                                                                s->Mtot, s->sz.as<double>());
+    ctx->launches++;
+  }
+  if (mode != BASQ_PLAIN) {
+    // Az = K(Z, Xobs) W   (BASQ/_gp.py:270-273: KxX @ woodbury_inv)
+    DevBuf KzX;
+    BASQ_TRY(KzX.alloc(sizeof(double) * (size_t)M * n_obs));
+    BASQ_TRY(s->Az.alloc(sizeof(double) * (size_t)M * n_obs));
+    BASQ_TRY(base_gram(ctx, s->kp, s->lm.view(0, (int)M), desc->Xobs, n_obs, KzX.as<double>(), n_obs));
+    BASQ_TRY(dgemm(ctx, false, false, (int)M, n_obs, n_obs, 1.0, KzX.as<double>(), n_obs, desc->W, n_obs, 0.0,
+                   s->Az.as<double>(), n_obs));
+    if (augment) {
+      // U'[:, M:] = -(U diag(sz)) Az : the posterior-covariance correction folded into the projection
+      BASQ_TRY(dgemm(ctx, false, false, q, n_obs, (int)M, -1.0, s->Uprime.as<double>(), s->Mtot, s->Az.as<double>(),
+                     n_obs, 0.0, s->Uprime.as<double>() + M, s->Mtot));
+      s->Az.release();
+    }
+    BASQ_CUDA(cudaStreamSynchronize(ctx->stream));  // KzX goes out of scope
+  }
+
+  // candidate records
+  const double uniform_w = 1.0 / (double)(N_glob > 0 ? N_glob : 1);
+  BASQ_TRY(build_records(ctx, s->kp, desc->dtype, X, N_loc, uniform_w, mu, has_factor ? sx.as<double>() : nullptr,
+                         !nonlin, &s->pool));
+
+  s->ldg = s->S;
+  BASQ_TRY(s->G.alloc(sizeof(double) * (size_t)s->Mtot * s->ldg));
+  BASQ_TRY(s->rank.alloc(sizeof(int) * s->S));
+  if (nonlin) {
+    int64_t P = (int64_t)(96ll << 20) / (8ll * std::max<int64_t>(M, n_obs));
+    P = std::max<int64_t>(1024, std::min<int64_t>(P, 65536));
+    s->chunkP = P;
+    BASQ_TRY(s->V.alloc(sizeof(double) * (size_t)n_obs * P));
+    BASQ_TRY(s->corrT.alloc(sizeof(double) * (size_t)M * P));
+  }
+  s->omega_host.resize(s->S);
+  s->rank_host.resize(s->S);
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));  // sx goes out of scope
+  return BASQ_OK;
+}
+
+int session_partial_impl(basq_session* s, int64_t R_glob, int64_t off, double* A_out) {
+  basq_ctx* ctx = s->ctx;
+  const int S = s->S, n = s->n;
+  const int S_eff = (int)std::min<int64_t>(S, R_glob);
+  BASQ_CHECK(off >= 0 && off + s->pool.count <= R_glob, BASQ_ERR_INVALID,
+             "partial: offset %lld + local %lld exceeds global %lld", (long long)off, (long long)s->pool.count,
+             (long long)R_glob);
+  BASQ_CUDA(cudaMemsetAsync(A_out, 0, sizeof(double) * (size_t)n * S, ctx->stream));
+  {
+    PhaseTimer t(ctx, PH_SETSUM);
+    BASQ_TRY(set_masses(ctx, s->pool, off, S, S_eff, A_out));
+    BASQ_TRY(session_set_sums(s, off, S, 0, s->pool.count, s->G.as<double>(), s->ldg));
+  }
+  {
+    PhaseTimer t(ctx, PH_PROJ);
+    // rows 1..q : U' @ G   (reference: U_svd @ X_for_nys, BASQ/_rchq.py:88)
+    BASQ_TRY(dgemm(ctx, false, false, s->q, S_eff, s->Mtot, 1.0, s->Uprime.as<double>(), s->Mtot, s->G.as<double>(),
+                   s->ldg, 0.0, A_out + S, S));
+  }
+  return BASQ_OK;
+}
+
+int session_apply_impl(basq_session* s, int64_t R_glob, int64_t off, const double* omega, int64_t* R_loc_new) {
+  basq_ctx* ctx = s->ctx;
+  PhaseTimer t(ctx, PH_APPLY);
+  const int S = s->S;
+  const int S_eff = (int)std::min<int64_t>(S, R_glob);
+  BASQ_CUDA(cudaMemcpyAsync(s->omega_host.data(), omega, sizeof(double) * S_eff, cudaMemcpyDeviceToHost, ctx->stream));
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  BASQ_TRY(check_finite_host(s->omega_host.data(), S_eff, "omega"));
+  int K = 0;
+  for (int j = 0; j < S; ++j) {
+    s->rank_host[j] = K;
+    if (j < S_eff && s->omega_host[j] > 0.0) ++K;
+  }
+  BASQ_CHECK(K >= 1, BASQ_ERR_NUMERIC, "apply: the Caratheodory step kept no set");
+  auto D = [&](int64_t g) {  // kept points among global positions < g
+    const int64_t e = g / S;
+    const int j = (int)(g % S);
+    return e * (int64_t)K + s->rank_host[j];
+  };
+  const int64_t dest_base = D(off);
+  const int64_t new_count = D(off + s->pool.count) - dest_base;
+  BASQ_CUDA(cudaMemcpyAsync(s->rank.p, s->rank_host.data(), sizeof(int) * S, cudaMemcpyHostToDevice, ctx->stream));
+  BASQ_TRY(apply_round(ctx, &s->pool, off, S, omega, s->rank.as<int>(), K, s->scale_wf, dest_base, new_count));
+  // rank_host is reused next round: make sure the H2D copy has consumed it
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (R_loc_new) *R_loc_new = new_count;
+  return BASQ_OK;
+}
+
+// Phi[p_lo..p_hi, q] for the session's live records
+int session_features(basq_session* s, double* Phi_out) {
+  basq_ctx* ctx = s->ctx;
+  const int64_t N = s->pool.count;
+  const int64_t P = 16384;
+  DevBuf Gc;
+  BASQ_TRY(Gc.alloc(sizeof(double) * (size_t)s->Mtot * P));
+  for (int64_t p0 = 0; p0 < N; p0 += P) {
+    const int64_t p1 = std::min(N, p0 + P);
+    BASQ_TRY(session_set_sums(s, -p0, (int)P, p0, p1, Gc.as<double>(), P));
+    // Phi[p0 + j, i] = sum_m G[m, j] U'[i, m]
+    BASQ_TRY(dgemm(ctx, true, true, (int)(p1 - p0), s->q, s->Mtot, 1.0, Gc.as<double>(), P, s->Uprime.as<double>(),
+                   s->Mtot, 0.0, Phi_out + p0 * s->q, s->q));
+  }
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BASQ_OK;
+}
+
+int recombine_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t N, const void* Z, int64_t M,
+                   const double* U, int q, const double* mu, int64_t* idx_out, double* w_out, int* n_out_host) {
+  BASQ_CHECK(idx_out && w_out && n_out_host, BASQ_ERR_INVALID, "recombine: NULL output");
+  std::unique_ptr<basq_session> s(new (std::nothrow) basq_session());
+  BASQ_CHECK(s, BASQ_ERR_INVALID, "out of host memory");
+  BASQ_TRY(session_create_impl(ctx, desc, X, N, N, 0, Z, M, U, q, mu, 0, s.get()));
+  const int n = s->n, S = s->S;
+  DevBuf A, omega;
+  BASQ_TRY(A.alloc(sizeof(double) * (size_t)n * S));
+  BASQ_TRY(omega.alloc(sizeof(double) * S));
+  int64_t R = s->pool.count;
+  int rounds = 0;
+  while (R > n) {
+    BASQ_CHECK(++rounds <= 256, BASQ_ERR_NUMERIC, "recombine: no convergence after 256 rounds");
+    BASQ_TRY(session_partial_impl(s.get(), R, 0, A.as<double>()));
+    const int S_eff = (int)std::min<int64_t>(S, R);
+    BASQ_TRY(caratheodory(ctx, A.as<double>(), n, S_eff, S, omega.as<double>()));
+    int64_t Rn = 0;
+    BASQ_TRY(session_apply_impl(s.get(), R, 0, omega.as<double>(), &Rn));
+    BASQ_CHECK(Rn < R, BASQ_ERR_NUMERIC, "recombine: round %d made no progress (%lld points)", rounds, (long long)R);
+    R = Rn;
+  }
+  BASQ_TRY(extract_result(ctx, s->pool, 0, idx_out, w_out));
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  *n_out_host = (int)R;
+  return BASQ_OK;
+}
+
+}  // namespace
+}  // namespace basq
+
+// =============================================================================================
+// extern "C"
+// =============================================================================================
+extern "C" {
+
+int basq_abi_version(void) { return BASQ_ABI_VERSION; }
+const char* basq_last_error(void) { return basq::last_error_cstr(); }
+
+int basq_ctx_create(int device, void* stream, basq_ctx** out) {
+  BASQ_CHECK(out != nullptr, BASQ_ERR_INVALID, "basq_ctx_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device available (%s); basq_b200 has no CPU fallback",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return BASQ_ERR_CUDA;
+  }
+  BASQ_CHECK(device >= 0 && device < ndev, BASQ_ERR_INVALID, "device %d out of range (have %d)", device, ndev);
+  BASQ_CUDA(cudaSetDevice(device));
+  basq_ctx* c = new (std::nothrow) basq_ctx();
+  BASQ_CHECK(c, BASQ_ERR_INVALID, "out of host memory");
+  c->device = device;
+  c->stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    delete c;
+    set_error("cudaGetDeviceProperties failed");
+    return BASQ_ERR_CUDA;
+  }
+  c->num_sms = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  if (prop.major < 10) {
+    delete c;
+    set_error("basq_b200 is built for sm_100a (Blackwell B200); device %d is sm_%d%d", device, prop.major, prop.minor);
+    return BASQ_ERR_CUDA;
+  }
+  cudaEventCreate(&c->ev0);
+  cudaEventCreate(&c->ev1);
+  *out = c;
+  return BASQ_OK;
+}
+
+void basq_ctx_destroy(basq_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  delete ctx;
+}
+
+int64_t basq_ctx_launch_count(const basq_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int basq_ctx_profile(basq_ctx* ctx, int enable) {
+  BASQ_CHECK(ctx, BASQ_ERR_INVALID, "ctx is NULL");
+  ctx->profile = enable != 0;
+  return BASQ_OK;
+}
+
+int basq_ctx_profile_read(basq_ctx* ctx, double* ms_host, int64_t* calls_host, int reset) {
+  BASQ_CHECK(ctx && ms_host, BASQ_ERR_INVALID, "NULL argument");
+  for (int i = 0; i < PH_COUNT; ++i) {
+    ms_host[i] = ctx->phase_ms[i];
+    if (calls_host) calls_host[i] = ctx->phase_calls[i];
+    if (reset) {
+      ctx->phase_ms[i] = 0.0;
+      ctx->phase_calls[i] = 0;
+    }
+  }
+  return BASQ_OK;
+}
+
+int basq_dgemm(basq_ctx* ctx, int transA, int transB, int m, int n, int k, double alpha, const double* A, int lda,
+               const double* B, int ldb, double beta, double* C, int ldc) {
+  BASQ_CHECK(ctx && A && B && C, BASQ_ERR_INVALID, "basq_dgemm: NULL argument");
+  BASQ_CUDA(cudaSetDevice(ctx->device));
+  return dgemm(ctx, transA != 0, transB != 0, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+}
+
+int basq_gram(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t a, const void* Y, int64_t b,
+              double* out) {
+  BASQ_CHECK(ctx && desc && X && Y && out, BASQ_ERR_INVALID, "basq_gram: NULL argument");
+  BASQ_CHECK(a >= 1 && b >= 1, BASQ_ERR_INVALID, "basq_gram: empty operand");
+  BASQ_CUDA(cudaSetDevice(ctx->device));
+  KParams kp;
+  BASQ_TRY(make_kparams(desc, &kp));
+  BASQ_TRY(compute_center(ctx, desc, X, a, &kp));
+  Landmarks lmx;
+  BASQ_TRY(prep_landmarks(ctx, kp, desc->dtype, X, a, nullptr, 0, &lmx));
+  BASQ_TRY(base_gram(ctx, kp, lmx.view(), Y, b, out, b));
+  const int mode = desc->mode;
+  if (mode != BASQ_PLAIN) {
+    const int n_obs = desc->n_obs;
+    Landmarks lmobs;
+    BASQ_TRY(prep_landmarks(ctx, kp, desc->dtype, desc->Xobs, n_obs, nullptr, 0, &lmobs));
+    DevBuf KxX, T, KXy, fx, fy;
+    BASQ_TRY(KxX.alloc(sizeof(double) * (size_t)a * n_obs));
+    BASQ_TRY(T.alloc(sizeof(double) * (size_t)a * n_obs));
+    BASQ_TRY(KXy.alloc(sizeof(double) * (size_t)n_obs * b));
+    BASQ_TRY(base_gram(ctx, kp, lmx.view(), desc->Xobs, n_obs, KxX.as<double>(), n_obs));
+    BASQ_TRY(base_gram(ctx, kp, lmobs.view(), Y, b, KXy.as<double>(), b));
+    BASQ_CHECK(a < (1ll << 31) && b < (1ll << 31), BASQ_ERR_UNSUPPORTED, "basq_gram: operand too large");
+    BASQ_TRY(dgemm(ctx, false, false, (int)a, n_obs, n_obs, 1.0, KxX.as<double>(), n_obs, desc->W, n_obs, 0.0,
+                   T.as<double>(), n_obs));
+    BASQ_TRY(dgemm(ctx, false, false, (int)a, (int)b, n_obs, -1.0, T.as<double>(), n_obs, KXy.as<double>(), b, 1.0,
+                   out, b));
+    const bool warped = (mode == BASQ_WSABI_L || mode == BASQ_WSABI_M || mode == BASQ_MMLT_G);
+    if (warped) {
+      BASQ_TRY(fx.alloc(sizeof(double) * a));
+      BASQ_TRY(fy.alloc(sizeof(double) * b));
+      BASQ_TRY(warp_factor(ctx, desc, kp, lmobs.view(), X, a, fx.as<double>()));
+      BASQ_TRY(warp_factor(ctx, desc, kp, lmobs.view(), Y, b, fy.as<double>()));
+    }
+    if (warped || desc->diag_add != 0.0) {
+      const int64_t tot = a * b;
+      warp_gram_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, ctx->stream>>>(
+          out, a, b, warped ? mode : BASQ_PRED_COV, fx.as<double>(), fy.as<double>(), desc->diag_add);
+      ctx->launches++;
+      BASQ_CUDA(cudaGetLastError());
+    }
+    BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  } else if (desc->diag_add != 0.0) {
+    const int64_t tot = a * b;
+    warp_gram_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, ctx->stream>>>(out, a, b, BASQ_PLAIN, nullptr, nullptr,
+                                                                             desc->diag_add);
+    ctx->launches++;
+    BASQ_CUDA(cudaGetLastError());
+  }
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BASQ_OK;
+}
+
+int basq_gp_predict(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t N, int space, double offset,
+                    double* mean_out, double* var_out) {
+  BASQ_CHECK(ctx && desc && X && mean_out, BASQ_ERR_INVALID, "basq_gp_predict: NULL argument");
+  BASQ_CHECK(desc->n_obs > 0 && desc->Xobs && desc->W && desc->alpha, BASQ_ERR_INVALID,
+             "basq_gp_predict needs the GP caches (n_obs, Xobs, W, alpha)");
+  BASQ_CUDA(cudaSetDevice(ctx->device));
+  KParams kp;
+  basq_kernel_desc d2 = *desc;
+  if (d2.mode == BASQ_PLAIN) d2.mode = BASQ_PRED_COV;
+  BASQ_TRY(make_kparams(&d2, &kp));
+  BASQ_TRY(compute_center(ctx, &d2, d2.Xobs, d2.n_obs, &kp));
+  Landmarks lmobs;
+  BASQ_TRY(prep_landmarks(ctx, kp, d2.dtype, d2.Xobs, d2.n_obs, nullptr, 0, &lmobs));
+  const bool warped = (desc->mode == BASQ_WSABI_L || desc->mode == BASQ_WSABI_M || desc->mode == BASQ_MMLT_G);
+  const bool need_var = var_out != nullptr || (space == 1 && (desc->mode == BASQ_WSABI_M || desc->mode == BASQ_MMLT_G));
+  DevBuf vtmp;
+  double* var = var_out;
+  if (need_var && !var) {
+    BASQ_TRY(vtmp.alloc(sizeof(double) * N));
+    var = vtmp.as<double>();
+  }
+  BASQ_TRY(gp_predict_impl(ctx, &d2, kp, lmobs.view(), X, N, mean_out, need_var ? var : nullptr));
+  if (space == 1 && warped && N > 0) {
+    model_space_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, ctx->stream>>>(desc->mode, offset, N, mean_out,
+                                                                              need_var ? var : nullptr,
+                                                                              var_out != nullptr ? 1 : 0);
+    ctx->launches++;
+    BASQ_CUDA(cudaGetLastError());
+  }
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BASQ_OK;
+}
+
+int basq_nystrom_basis(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, int64_t M, int q,
+                       const double* Omega, int niter, double* U_out, double* S_out) {
+  BASQ_CHECK(ctx && desc && Z && Omega && U_out, BASQ_ERR_INVALID, "basq_nystrom_basis: NULL argument");
+  BASQ_CUDA(cudaSetDevice(ctx->device));
+  return nystrom_basis(ctx, desc, Z, M, q, Omega, niter, U_out, S_out);
+}
+
+int basq_features(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t N, const void* Z, int64_t M,
+                  const double* U, int q, double* Phi_out) {
+  BASQ_CHECK(ctx && desc && X && Z && U && Phi_out, BASQ_ERR_INVALID, "basq_features: NULL argument");
+  BASQ_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<basq_session> s(new (std::nothrow) basq_session());
+  BASQ_CHECK(s, BASQ_ERR_INVALID, "out of host memory");
+  // unit weights: the feature of a point is its set sum with weight 1 (S = 4 keeps the round buffers tiny)
+  DevBuf ones;
+  BASQ_TRY(ones.alloc(sizeof(double) * N));
+  {
+    std::vector<double> h((size_t)N, 1.0);
+    BASQ_CUDA(cudaMemcpyAsync(ones.p, h.data(), sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+    BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  BASQ_TRY(session_create_impl(ctx, desc, X, N, N, 0, Z, M, U, q, ones.as<double>(), 4, s.get()));
+  return session_features(s.get(), Phi_out);
+}
+
+int basq_car(basq_ctx* ctx, double* A, int n, int S, int lda, double* omega_out, int* n_kept_host) {
+  BASQ_CHECK(ctx && A && omega_out, BASQ_ERR_INVALID, "basq_car: NULL argument");
+  BASQ_CUDA(cudaSetDevice(ctx->device));
+  BASQ_TRY(caratheodory(ctx, A, n, S, lda, omega_out));
+  if (n_kept_host) {
+    std::vector<double> h((size_t)S);
+    BASQ_CUDA(cudaMemcpyAsync(h.data(), omega_out, sizeof(double) * S, cudaMemcpyDeviceToHost, ctx->stream));
+    BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    int k = 0;
+    for (double v : h) k += v > 0.0;
+    *n_kept_host = k;
+  }
+  return BASQ_OK;
+}
+
+int basq_recombine(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t N, const void* Z, int64_t M,
+                   const double* U, int q, const double* mu, int64_t* idx_out, double* w_out, int* n_out_host) {
+  BASQ_CHECK(ctx, BASQ_ERR_INVALID, "ctx is NULL");
+  BASQ_CUDA(cudaSetDevice(ctx->device));
+  return recombine_impl(ctx, desc, X, N, Z, M, U, q, mu, idx_out, w_out, n_out_host);
+}
+
+int basq_recombine_host(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X_host, int64_t N,
+                        const void* Z_host, int64_t M, const double* U_host, int q, const double* Omega_host,
+                        int niter, const double* mu_host, int64_t* idx_out_host, double* w_out_host,
+                        int* n_out_host) {
+  BASQ_CHECK(ctx && desc && X_host && Z_host && idx_out_host && w_out_host && n_out_host, BASQ_ERR_INVALID,
+             "basq_recombine_host: NULL argument");
+  BASQ_CHECK(U_host || Omega_host, BASQ_ERR_INVALID, "basq_recombine_host: need U_host or Omega_host");
+  BASQ_CUDA(cudaSetDevice(ctx->device));
+  const size_t esz = desc->dtype == BASQ_F64 ? 8 : 4;
+  DevBuf dX, dZ, dU, dOm, dmu, didx, dw;
+  BASQ_TRY(dX.alloc(esz * (size_t)N * desc->d));
+  BASQ_TRY(dZ.alloc(esz * (size_t)M * desc->d));
+  BASQ_TRY(dU.alloc(sizeof(double) * (size_t)q * M));
+  BASQ_TRY(didx.alloc(sizeof(int64_t) * (q + 1)));
+  BASQ_TRY(dw.alloc(sizeof(double) * (q + 1)));
+  BASQ_CUDA(cudaMemcpyAsync(dX.p, X_host, esz * (size_t)N * desc->d, cudaMemcpyHostToDevice, ctx->stream));
+  BASQ_CUDA(cudaMemcpyAsync(dZ.p, Z_host, esz * (size_t)M * desc->d, cudaMemcpyHostToDevice, ctx->stream));
+  if (mu_host) {
+    BASQ_TRY(dmu.alloc(sizeof(double) * N));
+    BASQ_CUDA(cudaMemcpyAsync(dmu.p, mu_host, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (U_host) {
+    BASQ_CUDA(cudaMemcpyAsync(dU.p, U_host, sizeof(double) * (size_t)q * M, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    BASQ_TRY(dOm.alloc(sizeof(double) * (size_t)M * q));
+    BASQ_CUDA(cudaMemcpyAsync(dOm.p, Omega_host, sizeof(double) * (size_t)M * q, cudaMemcpyHostToDevice, ctx->stream));
+    BASQ_TRY(nystrom_basis(ctx, desc, dZ.p, M, q, dOm.as<double>(), niter, dU.as<double>(), nullptr));
+  }
+  int n_out = 0;
+  BASQ_TRY(recombine_impl(ctx, desc, dX.p, N, dZ.p, M, dU.as<double>(), q, mu_host ? dmu.as<double>() : nullptr,
+                          didx.as<int64_t>(), dw.as<double>(), &n_out));
+  BASQ_CUDA(cudaMemcpyAsync(idx_out_host, didx.p, sizeof(int64_t) * n_out, cudaMemcpyDeviceToHost, ctx->stream));
+  BASQ_CUDA(cudaMemcpyAsync(w_out_host, dw.p, sizeof(double) * n_out, cudaMemcpyDeviceToHost, ctx->stream));
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  *n_out_host = n_out;
+  return BASQ_OK;
+}
+
+int basq_session_create(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t N_loc, int64_t N_glob,
+                        int64_t idx_base, const void* Z, int64_t M, const double* U, int q, const double* mu,
+                        basq_session** out) {
+  BASQ_CHECK(ctx && out, BASQ_ERR_INVALID, "basq_session_create: NULL argument");
+  *out = nullptr;
+  BASQ_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<basq_session> s(new (std::nothrow) basq_session());
+  BASQ_CHECK(s, BASQ_ERR_INVALID, "out of host memory");
+  BASQ_TRY(session_create_impl(ctx, desc, X, N_loc, N_glob, idx_base, Z, M, U, q, mu, 0, s.get()));
+  *out = s.release();
+  return BASQ_OK;
+}
+
+void basq_session_destroy(basq_session* s) { delete s; }
+
+int basq_session_count(const basq_session* s, int64_t* R_loc_host) {
+  BASQ_CHECK(s && R_loc_host, BASQ_ERR_INVALID, "NULL argument");
+  *R_loc_host = s->pool.count;
+  return BASQ_OK;
+}
+
+int basq_session_partial(basq_session* s, int64_t R_glob, int64_t off_glob, double* A_out) {
+  BASQ_CHECK(s && A_out, BASQ_ERR_INVALID, "NULL argument");
+  BASQ_CUDA(cudaSetDevice(s->ctx->device));
+  return session_partial_impl(s, R_glob, off_glob, A_out);
+}
+
+int basq_session_apply(basq_session* s, int64_t R_glob, int64_t off_glob, const double* omega,
+                       int64_t* R_loc_new_host) {
+  BASQ_CHECK(s && omega, BASQ_ERR_INVALID, "NULL argument");
+  BASQ_CUDA(cudaSetDevice(s->ctx->device));
+  return session_apply_impl(s, R_glob, off_glob, omega, R_loc_new_host);
+}
+
+int basq_session_result(basq_session* s, int64_t* idx_out, double* w_out, int cap, int* n_out_host) {
+  BASQ_CHECK(s && idx_out && w_out && n_out_host, BASQ_ERR_INVALID, "NULL argument");
+  BASQ_CHECK(s->pool.count <= cap, BASQ_ERR_INVALID, "result: %lld live points exceed capacity %d",
+             (long long)s->pool.count, cap);
+  BASQ_CUDA(cudaSetDevice(s->ctx->device));
+  BASQ_TRY(extract_result(s->ctx, s->pool, s->idx_base, idx_out, w_out));
+  BASQ_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  *n_out_host = (int)s->pool.count;
+  return BASQ_OK;
+}
+
+}  // extern "C"

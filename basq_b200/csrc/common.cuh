@@ -1,0 +1,349 @@
+// Shared definitions for the basq_b200 CUDA library (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/basq_b200.h"
+
+namespace basq {
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define BASQ_CUDA(expr)                                                                   \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      basq::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,               \
+                      cudaGetErrorString(_e));                                            \
+      return BASQ_ERR_CUDA;                                                               \
+    }                                                                                     \
+  } while (0)
+
+#define BASQ_CHECK(cond, code, ...)                                                       \
+  do {                                                                                    \
+    if (!(cond)) {                                                                        \
+      basq::set_error(__VA_ARGS__);                                                       \
+      return (code);                                                                      \
+    }                                                                                     \
+  } while (0)
+
+#define BASQ_TRY(expr)                                                                    \
+  do {                                                                                    \
+    int _s = (expr);                                                                      \
+    if (_s != BASQ_OK) return _s;                                                         \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+enum Phase { PH_PREP = 0, PH_SETSUM = 1, PH_PROJ = 2, PH_CAR = 3, PH_APPLY = 4, PH_NYS = 5, PH_GP = 6, PH_OTHER = 7, PH_COUNT = 8 };
+
+}  // namespace basq
+
+struct basq_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 0;
+  size_t smem_optin = 0;
+  int64_t launches = 0;
+  bool profile = false;
+  int timer_depth = 0;
+  double phase_ms[basq::PH_COUNT] = {0};
+  int64_t phase_calls[basq::PH_COUNT] = {0};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace basq {
+
+// RAII phase timer (only active when ctx->profile).
+struct PhaseTimer {
+  basq_ctx* ctx;
+  int phase;
+  bool outer;
+  PhaseTimer(basq_ctx* c, int ph) : ctx(c), phase(ph) {
+    outer = (ctx->timer_depth++ == 0);
+    if (ctx->profile && outer) cudaEventRecord(ctx->ev0, ctx->stream);
+  }
+  ~PhaseTimer() {
+    ctx->timer_depth--;
+    if (ctx->profile && outer) {
+      cudaEventRecord(ctx->ev1, ctx->stream);
+      cudaEventSynchronize(ctx->ev1);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+      ctx->phase_ms[phase] += ms;
+      ctx->phase_calls[phase] += 1;
+    }
+  }
+};
+
+// Device buffer with RAII (stream-agnostic cudaMalloc; sessions live across many launches).
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  int alloc(size_t n) {
+    release();
+    if (n == 0) n = 16;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e));
+      p = nullptr;
+      return BASQ_ERR_CUDA;
+    }
+    bytes = n;
+    return BASQ_OK;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// kernel parameters in device-friendly form
+// ---------------------------------------------------------------------------------------------
+// fp32 evaluation uses the expansion  arg = a_x + b_z + sum_i x'_i * zz_i  on centred, scaled
+// coordinates (the same form gpytorch/torch.cdist use):
+//   RBF    : x' = (x-c) * sqrt(log2(e)/2) / l ; a_x = -|x'|^2 ; b_z = -|z'|^2 + log2(os) ; zz = 2 z'
+//            k  = exp2(arg)
+//   Matern : x' = (x-c) / l ; a_x = |x'|^2 ; b_z = |z'|^2 ; zz = -2 z' ; r^2 = max(arg, 0)
+// fp64 evaluation uses direct differences on x' = (x-c)/l.
+struct KParams {
+  int family;
+  int d;
+  int dp;  // padded dimension used by the compiled kernels
+  double outputscale;
+  float log2_os;
+  float os_f;
+  float scale_f[BASQ_MAX_DIM];   // fp32 per-dim multiplier (includes the RBF sqrt(log2e/2))
+  double scale_d[BASQ_MAX_DIM];  // 1 / lengthscale
+  double center[BASQ_MAX_DIM];
+};
+
+// padded dimensions that have compiled instantiations
+static inline int padded_dim(int d) {
+  const int opts[] = {2, 4, 6, 8, 10, 12, 16, 20, 24, 32};
+  for (int o : opts)
+    if (d <= o) return o;
+  return -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// candidate record (array of structs; what each Tchernychova-Lyons round streams)
+//   f32: [ wf:f64 | mu:f64 | idx:i32 | a:f32 | x'[DP]:f32 ]  padded to 16 B   (64 B at DP = 10)
+//   f64: [ wf:f64 | mu:f64 | idx:i64 | x'[DP]:f64 ]          padded to 16 B
+// wf is the weight the feature sums use (mu, or mu * m(x) for WSABI-L; the per-point factor itself
+// for the non-linear modes), mu the plain measure weight (set masses, final answer).
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ static inline int rec_bytes_f32(int dp) { return ((24 + 4 * dp) + 15) / 16 * 16; }
+__host__ __device__ static inline int rec_bytes_f64(int dp) { return ((24 + 8 * dp) + 15) / 16 * 16; }
+
+// non-linearity applied per (landmark, point) pair before accumulation
+enum NlMode { NL_LIN = 0, NL_WSABIM = 1, NL_MMLT = 2 };
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// exact float -> double for non-negative finite floats without touching the conversion pipe
+// (zero maps to 2^-127, which is below anything the sums can resolve).
+__device__ __forceinline__ double f2d_pos(float k) {
+  unsigned u = __float_as_uint(k);
+  return __hiloint2double((int)((u >> 3) + 0x38000000u), (int)(u << 29));
+}
+
+// One kernel evaluation in fp32 from prepared operands.  Every fp32 kernel in the library goes
+// through the same operation sequence (acc = a + b; acc = fma(x_i, zz_i, acc) for i ascending;
+// finish_f32) with the same operand roles, so k(z, x) is bit-identical wherever it is recomputed
+// (set sums of every round, features, Gram matrices).
+__device__ __forceinline__ float finish_f32(int fam, float acc, float os_f) {
+  if (fam == BASQ_RBF) {
+    return ex2_approx(acc);
+  } else {
+    const float r2 = fmaxf(acc, 0.f);
+    const float r = sqrt_approx(r2);
+    if (fam == BASQ_MATERN15) {
+      const float c = 1.7320508075688772f;
+      const float e = ex2_approx(__fmul_rn(-c * 1.4426950408889634f, r));
+      return __fmul_rn(__fmul_rn(os_f, __fmaf_rn(c, r, 1.f)), e);
+    } else {
+      const float c = 2.23606797749979f;
+      const float e = ex2_approx(__fmul_rn(-c * 1.4426950408889634f, r));
+      const float poly = __fmaf_rn(1.6666666666666667f, r2, __fmaf_rn(c, r, 1.f));
+      return __fmul_rn(__fmul_rn(os_f, poly), e);
+    }
+  }
+}
+
+template <int FAM, int DP>
+__device__ __forceinline__ float pair_eval_f32(const float* __restrict__ x, float a, const float* __restrict__ zz,
+                                               float b, float os_f) {
+  float acc = __fadd_rn(a, b);
+#pragma unroll
+  for (int i = 0; i < DP; ++i) acc = __fmaf_rn(x[i], zz[i], acc);
+  return finish_f32(FAM, acc, os_f);
+}
+
+__device__ __forceinline__ double finish_f64(int fam, double r2, double os) {
+  if (fam == BASQ_RBF) {
+    return os * exp(-0.5 * r2);
+  } else {
+    const double r = sqrt(r2);
+    if (fam == BASQ_MATERN15) {
+      const double c = 1.7320508075688772;
+      return os * (1.0 + c * r) * exp(-c * r);
+    } else {
+      const double c = 2.23606797749979;
+      return os * (1.0 + c * r + (5.0 / 3.0) * r2) * exp(-c * r);
+    }
+  }
+}
+
+template <int FAM, int DP>
+__device__ __forceinline__ double pair_eval_f64(const double* __restrict__ x, const double* __restrict__ z, double os) {
+  double r2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < DP; ++i) {
+    const double df = x[i] - z[i];
+    r2 = fma(df, df, r2);
+  }
+  return finish_f64(FAM, r2, os);
+}
+
+__device__ __forceinline__ double nl_apply(int nl, double c, double sz, double sx) {
+  if (nl == NL_WSABIM) return sz * c * sx + 0.5 * c * c;
+  if (nl == NL_MMLT) return sz * sx * expm1(c);
+  return c;
+}
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------------------------------------
+// prepared landmark set (device arrays)
+// ---------------------------------------------------------------------------------------------
+struct LmView {
+  const void* zz = nullptr;  // f32: [count, dp] floats (2z' / -2z') ; f64: [count, dp] doubles (z')
+  const float* b = nullptr;  // f32: [count] floats
+  int count = 0;
+  int dp = 0;
+  int dtype = BASQ_F32;
+};
+
+struct Landmarks {
+  int count = 0;
+  int dp = 0;
+  int dtype = BASQ_F32;
+  DevBuf zz;
+  DevBuf b;
+  LmView view(int first = 0, int cnt = -1) const {
+    LmView v;
+    if (cnt < 0) cnt = count - first;
+    const size_t esz = dtype == BASQ_F32 ? 4 : 8;
+    v.zz = (const unsigned char*)zz.p + (size_t)first * dp * esz;
+    v.b = dtype == BASQ_F32 ? b.as<float>() + first : nullptr;
+    v.count = cnt;
+    v.dp = dp;
+    v.dtype = dtype;
+    return v;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// internal entry points (one per translation unit)
+// ---------------------------------------------------------------------------------------------
+// kparams.cu
+int make_kparams(const basq_kernel_desc* desc, KParams* kp);
+int compute_center(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, int64_t M, KParams* kp);
+int prep_landmarks(basq_ctx* ctx, const KParams& kp, int dtype, const void* Z0, int64_t M0, const void* Z1,
+                   int64_t M1, Landmarks* out);
+
+// gram.cu
+// out[a, b] fp64 row-major (ld = ldo): base kernel between prepared landmarks and raw points P[b, d]
+int base_gram(basq_ctx* ctx, const KParams& kp, const LmView& lm, const void* P, int64_t b, double* out,
+              int64_t ldo);
+// same, the points being live records [p_lo, p_hi) of a pool (already scaled coordinates)
+struct RecPool;
+int base_gram_records(basq_ctx* ctx, const KParams& kp, const LmView& lm, const RecPool& pool, int64_t p_lo,
+                      int64_t p_hi, double* out, int64_t ldo);
+// mean_out[N] = c0 + sum_o coef[o] k(lm_o, x)   (fp64 accumulation)
+int landmark_dot(basq_ctx* ctx, const KParams& kp, const LmView& lm, const double* coef, double c0,
+                 const void* P, int64_t N, double* out);
+int gp_predict_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const KParams& kp, const LmView& lmobs,
+                    const void* X, int64_t N, double* mean_out, double* var_out);
+// per-point / per-landmark factor of the warped kernels (m(x) or mu_g(x)); out == nullptr allowed
+int warp_factor(basq_ctx* ctx, const basq_kernel_desc* desc, const KParams& kp, const LmView& lmobs,
+                const void* X, int64_t N, double* out);
+
+// records.cu
+struct RecPool {
+  int dtype = BASQ_F32;
+  int dp = 0;
+  int rec_bytes = 0;
+  DevBuf buf[2];
+  int cur = 0;
+  int64_t count = 0;
+  int64_t capacity = 0;
+};
+int build_records(basq_ctx* ctx, const KParams& kp, int dtype, const void* X, int64_t N, double uniform_w,
+                  const double* mu, const double* factor, bool factor_in_weight, RecPool* pool);
+int set_masses(basq_ctx* ctx, const RecPool& pool, int64_t off_glob, int S, int S_eff, double* mass_out);
+int apply_round(basq_ctx* ctx, RecPool* pool, int64_t off_glob, int S, const double* omega, const int* rank_excl,
+                int K, bool scale_wf, int64_t dest_base, int64_t new_count);
+int extract_result(basq_ctx* ctx, const RecPool& pool, int64_t idx_base, int64_t* idx_out, double* w_out);
+
+// setsum.cu
+struct SetSumArgs {
+  const RecPool* pool;
+  LmView lm;
+  int64_t off_glob;   // global position of local record 0
+  int S;              // set stride (number of sets)
+  int64_t p_lo, p_hi; // local record range processed by this launch
+  int nl;             // NlMode
+  const double* corrT;  // [p_hi - p_lo, ld_corr] (non-linear modes) : A_z k(Xobs, x_p) per landmark
+  int64_t ld_corr;
+  const double* sz;     // per-landmark factor (non-linear modes)
+  double* G;            // [lm->count, ldg]
+  int64_t ldg;
+  bool accumulate;
+};
+int set_sums(basq_ctx* ctx, const KParams& kp, const SetSumArgs& a);
+
+// dgemm.cu
+int dgemm(basq_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const double* A, int64_t lda,
+          const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
+
+// car.cu
+int caratheodory(basq_ctx* ctx, double* A, int n, int S, int lda, double* omega_out);
+
+// nystrom.cu
+int nystrom_basis(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, int64_t M, int q,
+                  const double* Omega, int niter, double* U_out, double* S_out);
+
+}  // namespace basq

@@ -1,0 +1,237 @@
+// Nystrom eigenbasis of the landmark Gram matrix (reference ker_svd_sparsify, BASQ/_rchq.py:28-31,
+// i.e. torch.svd_lowrank(K, q, niter=2): Halko et al. 2009 alg. 4.4 range finder).
+//
+//   Y = K Omega ; Q = orth(Y) ; niter x { Q = orth(K^T Q) ; Q = orth(K Q) } ; U = Q^T
+//
+// Recombination only depends on span(U) (its test functions are U_i . k(Z, x); any invertible
+// mixing of the rows leaves the set of feasible quadrature rules unchanged, and the Caratheodory
+// kernel is invariant to row scaling), so the final small SVD of the reference - a rotation inside
+// span(Q) - is replaced by Rayleigh quotients reported in S_out.
+//
+// orth() is shifted CholeskyQR3 in fp64: Gram matrix and triangular solve are GEMMs; the q x q
+// Cholesky factor and its inverse come from one persistent cooperative kernel (row-distributed
+// elimination of [G | I], one grid barrier per column).
+#include <math.h>
+
+#include "common.cuh"
+#include "gridsync.cuh"
+
+namespace basq {
+
+namespace {
+constexpr int CH_THREADS = 512;
+
+struct CholDev {
+  double* G;     // [q, ld]  in: SPD matrix (upper part used) ; destroyed
+  double* W;     // [q, ld]  out: L^-1 (lower triangular), G = L L^T
+  int q;
+  int64_t ld;
+  double* prow;  // [2][2q]
+  double floor;  // pivot floor
+  unsigned* bar;
+  int* status;
+};
+
+// Row k owned by CTA k % G.  Step k: owner scales row k of [G | W] by 1/sqrt(g_kk) and publishes it;
+// every CTA eliminates column k from its rows below k.
+__global__ void __launch_bounds__(CH_THREADS, 1) chol_inv_kernel(const CholDev a) {
+  extern __shared__ __align__(16) double rowc[];  // [2q] cached pivot row
+  __shared__ double bcast;
+  __shared__ int abort_sh;
+  const int q = a.q, G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+  unsigned target = 0;
+
+  // W = I on own rows
+  for (int r = b; r < q; r += G)
+    for (int c = tid; c < q; c += NT) a.W[(int64_t)r * a.ld + c] = (r == c) ? 1.0 : 0.0;
+  __syncthreads();
+
+  auto publish = [&](int k) {
+    double* g = a.G + (int64_t)k * a.ld;
+    double* w = a.W + (int64_t)k * a.ld;
+    if (tid == 0) {
+      double piv = g[k];
+      if (!(piv > a.floor)) piv = a.floor;
+      bcast = 1.0 / sqrt(piv);
+    }
+    __syncthreads();
+    const double inv = bcast;
+    double* pub = a.prow + (int64_t)(k & 1) * 2 * q;
+    for (int c = tid; c < 2 * q; c += NT) {
+      double v = 0.0;
+      if (c < q) {
+        if (c >= k) { v = g[c] * inv; g[c] = v; }
+      } else {
+        const int cw = c - q;
+        if (cw <= k) { v = w[cw] * inv; w[cw] = v; }
+      }
+      __stcg(&pub[c], v);
+    }
+    __syncthreads();
+  };
+  auto update = [&](int r, int k) {
+    double* g = a.G + (int64_t)r * a.ld;
+    double* w = a.W + (int64_t)r * a.ld;
+    if (tid == 0) bcast = g[k] / rowc[k];  // l_rk = g_rk / d_k  (rowc[k] = d_k)
+    __syncthreads();
+    const double l = bcast;
+    if (l != 0.0) {
+      for (int c = k + tid; c < q; c += NT) g[c] = (c == k) ? 0.0 : fma(-l, rowc[c], g[c]);
+      for (int c = tid; c <= k; c += NT) w[c] = fma(-l, rowc[q + c], w[c]);
+    }
+    __syncthreads();
+  };
+
+  if (b == 0) publish(0);
+  for (int k = 0; k < q; ++k) {
+    if (grid_barrier(a.bar, target, a.status, &abort_sh)) return;
+    const double* pub = a.prow + (int64_t)(k & 1) * 2 * q;
+    for (int c = tid; c < 2 * q; c += NT) rowc[c] = __ldcg(&pub[c]);
+    __syncthreads();
+    const int kn = k + 1;
+    if (kn < q && (kn % G) == b) {
+      update(kn, k);
+      publish(kn);
+    }
+    // own rows below k
+    int r0 = kn + ((b - kn) % G + G) % G;
+    for (int r = r0; r < q; r += G) {
+      if (r == kn) continue;
+      update(r, k);
+    }
+  }
+}
+
+__global__ void add_diag_kernel(double* __restrict__ G, int q, int64_t ld, double s) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < q) G[(int64_t)i * ld + i] += s;
+}
+
+__global__ void diag_kernel(const double* __restrict__ T, int q, int64_t ld, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < q) out[i] = T[(int64_t)i * ld + i];
+}
+
+__global__ void trace_kernel(const double* __restrict__ G, int q, int64_t ld, double* __restrict__ out) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < q; i += 256) s += G[(int64_t)i * ld + i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+
+struct OrthWs {
+  DevBuf gram, linv, tmp, prow, flags, scal;
+};
+
+int chol_inverse(basq_ctx* ctx, OrthWs& ws, int q, double floor_val) {
+  CholDev d;
+  d.G = ws.gram.as<double>();
+  d.W = ws.linv.as<double>();
+  d.q = q;
+  d.ld = q;
+  d.prow = ws.prow.as<double>();
+  d.floor = floor_val;
+  d.bar = ws.flags.as<unsigned>();
+  d.status = ws.flags.as<int>() + 2;
+  BASQ_CUDA(cudaMemsetAsync(ws.flags.p, 0, 8, ctx->stream));
+  const size_t smem = sizeof(double) * 2 * q;
+  BASQ_CHECK(smem <= ctx->smem_optin, BASQ_ERR_UNSUPPORTED, "nystrom: q=%d too large for the Cholesky kernel", q);
+  BASQ_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int G = (q + 1) / 2;
+  if (G > ctx->num_sms) G = ctx->num_sms;
+  if (G < 1) G = 1;
+  void* args[] = {(void*)&d};
+  BASQ_CUDA(cudaLaunchCooperativeKernel((const void*)chol_inv_kernel, dim3(G), dim3(CH_THREADS), args, smem,
+                                        ctx->stream));
+  ctx->launches++;
+  return BASQ_OK;
+}
+
+// Y [M, q] (ld = q) <- orthonormal basis of span(Y): shifted CholeskyQR, three passes
+int orthonormalise(basq_ctx* ctx, OrthWs& ws, double* Y, int64_t M, int q) {
+  for (int pass = 0; pass < 3; ++pass) {
+    BASQ_TRY(dgemm(ctx, true, false, q, q, (int)M, 1.0, Y, q, Y, q, 0.0, ws.gram.as<double>(), q));
+    trace_kernel<<<1, 256, 0, ctx->stream>>>(ws.gram.as<double>(), q, q, ws.scal.as<double>());
+    ctx->launches++;
+    double tr = 0.0;
+    BASQ_CUDA(cudaMemcpyAsync(&tr, ws.scal.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    BASQ_CHECK(isfinite(tr) && tr > 0.0, BASQ_ERR_NUMERIC, "nystrom: Gram trace %g is not positive/finite", tr);
+    const double eps = 2.220446049250313e-16;
+    // shift of Fukaya et al. (shifted CholeskyQR3): 11 (M q + q (q+1)) u |Y|_2^2 ; |Y|_2^2 <= trace
+    const double shift = (pass == 0) ? 11.0 * ((double)M * q + (double)q * (q + 1)) * eps * tr : 0.0;
+    if (shift > 0.0) {
+      add_diag_kernel<<<ceil_div(q, 256), 256, 0, ctx->stream>>>(ws.gram.as<double>(), q, q, shift);
+      ctx->launches++;
+    }
+    BASQ_TRY(chol_inverse(ctx, ws, q, tr * 1e-30));
+    // Y <- Y L^-T
+    BASQ_TRY(dgemm(ctx, false, true, (int)M, q, q, 1.0, Y, q, ws.linv.as<double>(), q, 0.0, ws.tmp.as<double>(), q));
+    BASQ_CUDA(cudaMemcpyAsync(Y, ws.tmp.p, sizeof(double) * (size_t)M * q, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  int status = 0;
+  BASQ_CUDA(cudaMemcpyAsync(&status, ws.flags.as<int>() + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  BASQ_CHECK(status == 0, BASQ_ERR_NUMERIC, "nystrom: grid barrier watchdog fired in the Cholesky kernel");
+  return BASQ_OK;
+}
+
+}  // namespace
+
+int nystrom_basis(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, int64_t M, int q, const double* Omega,
+                  int niter, double* U_out, double* S_out) {
+  PhaseTimer timer(ctx, PH_NYS);
+  BASQ_CHECK(q >= 1 && q <= M, BASQ_ERR_INVALID, "nystrom: need 1 <= q <= M (q=%d M=%lld)", q, (long long)M);
+  BASQ_CHECK(M <= 46000, BASQ_ERR_UNSUPPORTED, "nystrom: M=%lld landmarks need a %.1f GB Gram matrix", (long long)M,
+             8.0 * M * M / 1e9);
+  BASQ_CHECK(niter >= 0 && niter <= 16, BASQ_ERR_INVALID, "nystrom: niter out of range");
+  DevBuf K, Y, Y2;
+  BASQ_TRY(K.alloc(sizeof(double) * (size_t)M * M));
+  BASQ_TRY(Y.alloc(sizeof(double) * (size_t)M * q));
+  OrthWs ws;
+  BASQ_TRY(ws.gram.alloc(sizeof(double) * (size_t)q * q));
+  BASQ_TRY(ws.linv.alloc(sizeof(double) * (size_t)q * q));
+  BASQ_TRY(ws.tmp.alloc(sizeof(double) * (size_t)M * q));
+  BASQ_TRY(ws.prow.alloc(sizeof(double) * 4 * q));
+  BASQ_TRY(ws.flags.alloc(64));
+  BASQ_CUDA(cudaMemsetAsync(ws.flags.p, 0, 64, ctx->stream));
+  BASQ_TRY(ws.scal.alloc(64));
+  BASQ_TRY(basq_gram(ctx, desc, Z, M, Z, M, K.as<double>()));
+
+  const int Mi = (int)M;
+  BASQ_TRY(dgemm(ctx, false, false, Mi, q, Mi, 1.0, K.as<double>(), M, Omega, q, 0.0, Y.as<double>(), q));
+  BASQ_TRY(orthonormalise(ctx, ws, Y.as<double>(), M, q));
+  BASQ_TRY(Y2.alloc(sizeof(double) * (size_t)M * q));
+  for (int it = 0; it < niter; ++it) {
+    BASQ_TRY(dgemm(ctx, true, false, Mi, q, Mi, 1.0, K.as<double>(), M, Y.as<double>(), q, 0.0, Y2.as<double>(), q));
+    BASQ_TRY(orthonormalise(ctx, ws, Y2.as<double>(), M, q));
+    BASQ_TRY(dgemm(ctx, false, false, Mi, q, Mi, 1.0, K.as<double>(), M, Y2.as<double>(), q, 0.0, Y.as<double>(), q));
+    BASQ_TRY(orthonormalise(ctx, ws, Y.as<double>(), M, q));
+  }
+  // U = Q^T  [q, M]  (transpose through a GEMM with the identity would waste flops: use geam-like copy)
+  {
+    // ws.gram <- I (q x q), then U = I * Q^T via dgemm(NT)
+    BASQ_CUDA(cudaMemsetAsync(ws.gram.p, 0, sizeof(double) * (size_t)q * q, ctx->stream));
+    add_diag_kernel<<<ceil_div(q, 256), 256, 0, ctx->stream>>>(ws.gram.as<double>(), q, q, 1.0);
+    ctx->launches++;
+    BASQ_TRY(dgemm(ctx, false, true, q, Mi, q, 1.0, ws.gram.as<double>(), q, Y.as<double>(), q, 0.0, U_out, M));
+  }
+  if (S_out) {
+    // Rayleigh quotients q_i^T K q_i
+    BASQ_TRY(dgemm(ctx, false, false, Mi, q, Mi, 1.0, K.as<double>(), M, Y.as<double>(), q, 0.0, Y2.as<double>(), q));
+    BASQ_TRY(dgemm(ctx, true, false, q, q, Mi, 1.0, Y.as<double>(), q, Y2.as<double>(), q, 0.0, ws.gram.as<double>(), q));
+    diag_kernel<<<ceil_div(q, 256), 256, 0, ctx->stream>>>(ws.gram.as<double>(), q, q, S_out);
+    ctx->launches++;
+  }
+  BASQ_CUDA(cudaGetLastError());
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BASQ_OK;
+}
+
+}  // namespace basq

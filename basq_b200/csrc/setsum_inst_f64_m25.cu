@@ -1,0 +1,7 @@
+// Instantiations of the set-sum kernel: double evaluation, BASQ_MATERN25.
+#include "setsum_impl.cuh"
+namespace basq {
+int launch_setsum_f64_m25(basq_ctx* ctx, int dp, const SetSumDev& dev) {
+  return launch_setsum_family<double, BASQ_MATERN25>(ctx, dp, dev);
+}
+}  // namespace basq

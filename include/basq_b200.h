@@ -1,0 +1,156 @@
+/*
+ * basq_b200 - C ABI of the B200-native kernel-recombination (RCHQ) hot path of BASQ.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.
+ * The reference is pure Python, so there is no existing FFI; each entry point cites the
+ * reference function (file:line under the ma921/BASQ tree) whose work it replaces.  The
+ * Python shim that a maintainer binds against these symbols is basq_b200/_lib.py (ctypes);
+ * INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every pointer is DEVICE memory on the context's device unless its name ends in _host;
+ *   - matrices are dense row-major; coordinates X/Z/Xobs are [rows, d] in desc->dtype;
+ *   - all calls are ordered on the context's stream; calls that return host scalars
+ *     synchronise that stream before returning;
+ *   - return value: BASQ_OK or an error code, text via basq_last_error() (thread local).
+ * There is no CPU fallback: without a CUDA device every compute call fails with BASQ_ERR_CUDA.
+ */
+#ifndef BASQ_B200_H
+#define BASQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BASQ_ABI_VERSION 1
+#define BASQ_MAX_DIM 32
+
+enum basq_status {
+  BASQ_OK = 0,
+  BASQ_ERR_INVALID = 1,     /* bad argument */
+  BASQ_ERR_CUDA = 2,        /* CUDA runtime error / no device */
+  BASQ_ERR_NUMERIC = 3,     /* degenerate numerical state (e.g. barrier watchdog, NaN input) */
+  BASQ_ERR_UNSUPPORTED = 4  /* shape or option outside the compiled range */
+};
+
+enum basq_family { BASQ_RBF = 0, BASQ_MATERN15 = 1, BASQ_MATERN25 = 2 };
+
+/* Kernel handed to recombination. */
+enum basq_mode {
+  BASQ_PLAIN = 0,     /* covar_module.forward                (SOBER/_kernel.py:27-28)            */
+  BASQ_PRED_COV = 1,  /* predictive_covariance               (BASQ/_gp.py:259-277)               */
+  BASQ_WSABI_L = 2,   /* m(x) C(x,y) m(y)                    (BASQ/_wsabi.py:205-226, SOBER/_kernel.py:33-47) */
+  BASQ_WSABI_M = 3,   /* m(x) C m(y) + C^2/2                 (BASQ/_wsabi.py:228-249)            */
+  BASQ_MMLT_G = 4     /* mu_g(x) mu_g(y) (exp C_h - 1)       (SOBER/BASQ/_scale_mmlt.py:258-278) */
+};
+
+enum basq_dtype { BASQ_F32 = 0, BASQ_F64 = 1 };
+
+typedef struct basq_ctx basq_ctx;
+typedef struct basq_session basq_session;
+
+/* POD description of the GP kernel; extracted from the reference's kernel objects by the shim. */
+typedef struct basq_kernel_desc {
+  int32_t family;                    /* basq_family */
+  int32_t mode;                      /* basq_mode */
+  int32_t dtype;                     /* basq_dtype of X / Z / Xobs and of the kernel evaluation */
+  int32_t d;                         /* input dimension, 1..BASQ_MAX_DIM */
+  double outputscale;                /* ScaleKernel.outputscale (sigma_f^2) */
+  double lengthscale[BASQ_MAX_DIM];  /* per-dimension lengthscale (replicate a scalar) */
+  double noise;                      /* likelihood.noise (sigma_n^2) */
+  double mean_const;                 /* ConstantMean constant (0 for ZeroMean) */
+  double diag_add;                   /* added to the first min(a,b) diagonal entries by basq_gram
+                                        (BASQ/_gp.py:275-276 quirk / wsabi jitter); 0 = off */
+  int32_t n_obs;                     /* GP observations; 0 for BASQ_PLAIN */
+  int32_t reserved;
+  const void* Xobs;                  /* [n_obs, d] in dtype */
+  const double* W;                   /* [n_obs, n_obs] (K_XX + sigma_n^2 I)^-1, fp64 (BASQ/_gp.py:233-256) */
+  const double* alpha;               /* [n_obs] mean cache (K_XX + sigma_n^2 I)^-1 (y - c), fp64 */
+} basq_kernel_desc;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int basq_abi_version(void);
+const char* basq_last_error(void);
+/* stream: a cudaStream_t (0 = the legacy default stream). */
+int basq_ctx_create(int device, void* stream, basq_ctx** out);
+void basq_ctx_destroy(basq_ctx* ctx);
+/* number of kernels this library has launched on ctx so far (bench.py's gpu_launches) */
+int64_t basq_ctx_launch_count(const basq_ctx* ctx);
+/* CUDA-event timings (ms) accumulated per phase since the last reset:
+   0 prepare, 1 set-sum, 2 projection GEMM, 3 Caratheodory, 4 apply/compact, 5 nystrom, 6 gp predict.
+   Only recorded when enabled (adds stream synchronisation). */
+int basq_ctx_profile(basq_ctx* ctx, int enable);
+int basq_ctx_profile_read(basq_ctx* ctx, double* ms_host /*[8]*/, int64_t* calls_host /*[8]*/, int reset);
+
+/* ---- kernel evaluations -------------------------------------------------------------------- */
+/* out[a,b] (fp64) = kernel(X[a], Y[b]) in desc->mode.  Replaces the reference's kernel callable. */
+int basq_gram(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t a,
+              const void* Y, int64_t b, double* out);
+/* GP posterior over candidates, predict() of BASQ/_gp.py:213-230 with exact variance.
+   space 0: the warped GP itself (mean, var incl. likelihood noise);
+   space 1: the model space of desc->mode (wsabil_predict / wsabim_predict / gspace_predict),
+            `offset` is the WSABI alpha added to the mean.  var_out may be NULL. */
+int basq_gp_predict(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t N,
+                    int space, double offset, double* mean_out, double* var_out);
+
+/* ---- Nystrom eigenbasis: ker_svd_sparsify, BASQ/_rchq.py:28-31 ------------------------------ */
+/* Randomised range finder (Halko alg. 4.4, niter subspace iterations, as torch.svd_lowrank) on
+   K(Z,Z) with the caller's Gaussian test matrix Omega[M,q] (fp64), followed by a Rayleigh-Ritz
+   rotation.  U_out[q,M] has orthonormal rows; S_out[q] (may be NULL) the Ritz values, descending. */
+int basq_nystrom_basis(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, int64_t M,
+                       int q, const double* Omega, int niter, double* U_out, double* S_out);
+
+/* ---- test functions ------------------------------------------------------------------------ */
+/* Phi[N,q] (fp64) = (U @ kernel(Z, X))^T : the features whose moments recombination preserves. */
+int basq_features(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t N,
+                  const void* Z, int64_t M, const double* U, int q, double* Phi_out);
+
+/* ---- Caratheodory step: Tchernychova_Lyons_CAR, BASQ/_rchq.py:133-175 ------------------------ */
+/* A[n, S] (ld = lda) holds UNNORMALISED barycentres: row 0 the set masses, rows 1.. the weighted
+   feature sums.  Finds omega[S] >= 0 with at most n non-zeros and A omega = A 1 (i.e. the kept
+   sets, each mass rescaled by omega_j).  A is destroyed.  n_kept_host may be NULL. */
+int basq_car(basq_ctx* ctx, double* A, int n, int S, int lda, double* omega_out, int* n_kept_host);
+
+/* ---- recombination: recombination / rc_kernel_svd / Mod_Tchernychova_Lyons, BASQ/_rchq.py:4-130 */
+/* X[N,d] candidates, Z[M,d] landmarks, U[q,M] basis (fp64), mu[N] fp64 weights or NULL (uniform).
+   Writes at most q+1 ascending indices and positive weights summing to sum(mu). */
+int basq_recombine(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t N,
+                   const void* Z, int64_t M, const double* U, int q, const double* mu,
+                   int64_t* idx_out, double* w_out, int* n_out_host);
+/* Same with HOST buffers for X, Z, U, mu and the outputs (the copies are part of the call);
+   desc->Xobs / W / alpha stay device pointers (they belong to the GP model, not to the call).
+   If U_host is NULL the basis is built on the device from Omega_host[M,q] (basq_nystrom_basis). */
+int basq_recombine_host(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X_host, int64_t N,
+                        const void* Z_host, int64_t M, const double* U_host, int q,
+                        const double* Omega_host, int niter, const double* mu_host,
+                        int64_t* idx_out_host, double* w_out_host, int* n_out_host);
+
+/* ---- staged session: the same loop, one stage per call, for candidates sharded over ranks ---- */
+/* Rank-local shard X[N_loc]; idx_base = global index of its first row; N_glob = total count
+   (uniform weight 1/N_glob when mu == NULL).  Z, U and the GP caches are replicated. */
+int basq_session_create(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t N_loc,
+                        int64_t N_glob, int64_t idx_base, const void* Z, int64_t M,
+                        const double* U, int q, const double* mu, basq_session** out);
+void basq_session_destroy(basq_session* s);
+/* live local points (after dropping zero weights / after the last apply) */
+int basq_session_count(const basq_session* s, int64_t* R_loc_host);
+/* Local part of the round's barycentre system: A[n = q+1, S = 2n] (ld = S), columns >= min(S,R_glob)
+   zero.  off_glob = number of live points on lower ranks.  Sum A over ranks before basq_car. */
+int basq_session_partial(basq_session* s, int64_t R_glob, int64_t off_glob, double* A_out);
+/* Rescale the kept sets by omega[S], drop the rest, compact.  Returns the new local count. */
+int basq_session_apply(basq_session* s, int64_t R_glob, int64_t off_glob, const double* omega,
+                       int64_t* R_loc_new_host);
+/* surviving local points: global indices (ascending) and weights; cap = capacity of the outputs */
+int basq_session_result(basq_session* s, int64_t* idx_out, double* w_out, int cap, int* n_out_host);
+
+/* ---- small dense helper exposed for tests ---------------------------------------------------- */
+/* C[m,n] = alpha * op(A) op(B) + beta * C, fp64 row-major; op = transpose when the flag is set. */
+int basq_dgemm(basq_ctx* ctx, int transA, int transB, int m, int n, int k, double alpha,
+               const double* A, int lda, const double* B, int ldb, double beta, double* C, int ldc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BASQ_B200_H */
