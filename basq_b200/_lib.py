@@ -1,0 +1,137 @@
+"""ctypes binding of libbasq_b200.so (the C ABI in include/basq_b200.h).
+
+There is no CPU fallback: if the shared library is missing the import of this module fails, and
+every compute entry point fails with BasqError when no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbasq_b200.so")
+
+BASQ_MAX_DIM = 32
+OK, ERR_INVALID, ERR_CUDA, ERR_NUMERIC, ERR_UNSUPPORTED = range(5)
+RBF, MATERN15, MATERN25 = 0, 1, 2
+PLAIN, PRED_COV, WSABI_L, WSABI_M, MMLT_G = 0, 1, 2, 3, 4
+F32, F64 = 0, 1
+PHASES = ("prepare", "set_sum", "projection", "caratheodory", "apply", "nystrom", "gp_predict", "other")
+
+
+class BasqError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"basq_b200 error {code}: {msg}")
+        self.code = code
+
+
+class KernelDesc(C.Structure):
+    _fields_ = [
+        ("family", C.c_int32), ("mode", C.c_int32), ("dtype", C.c_int32), ("d", C.c_int32),
+        ("outputscale", C.c_double),
+        ("lengthscale", C.c_double * BASQ_MAX_DIM),
+        ("noise", C.c_double), ("mean_const", C.c_double), ("diag_add", C.c_double),
+        ("n_obs", C.c_int32), ("reserved", C.c_int32),
+        ("Xobs", C.c_void_p), ("W", C.c_void_p), ("alpha", C.c_void_p),
+    ]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build the CUDA extension first (python buildlib.py). "
+            "basq_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    P, I, L, D = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    KD = C.POINTER(KernelDesc)
+    sig = {
+        "basq_abi_version": (I, []),
+        "basq_last_error": (C.c_char_p, []),
+        "basq_ctx_create": (I, [I, P, C.POINTER(P)]),
+        "basq_ctx_destroy": (None, [P]),
+        "basq_ctx_launch_count": (L, [P]),
+        "basq_ctx_pair_evals": (L, [P]),
+        "basq_ctx_profile": (I, [P, I]),
+        "basq_ctx_profile_read": (I, [P, C.POINTER(D), C.POINTER(L), I]),
+        "basq_gram": (I, [P, KD, P, L, P, L, P]),
+        "basq_gp_predict": (I, [P, KD, P, L, I, D, P, P]),
+        "basq_nystrom_basis": (I, [P, KD, P, L, I, P, I, P, P]),
+        "basq_features": (I, [P, KD, P, L, P, L, P, I, P]),
+        "basq_car": (I, [P, P, I, I, I, P, C.POINTER(I)]),
+        "basq_recombine": (I, [P, KD, P, L, P, L, P, I, P, P, P, C.POINTER(I)]),
+        "basq_recombine_host": (I, [P, KD, P, L, P, L, P, I, P, I, P, P, P, C.POINTER(I)]),
+        "basq_session_create": (I, [P, KD, P, L, L, L, P, L, P, I, P, C.POINTER(P)]),
+        "basq_session_destroy": (None, [P]),
+        "basq_session_count": (I, [P, C.POINTER(L)]),
+        "basq_session_partial": (I, [P, L, L, P]),
+        "basq_session_apply": (I, [P, L, L, P, C.POINTER(L)]),
+        "basq_session_result": (I, [P, P, P, I, C.POINTER(I)]),
+        "basq_dgemm": (I, [P, I, I, I, I, I, D, P, I, P, I, D, P, I]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib, tuple(sig)
+
+
+lib, SYMBOLS = _load()
+
+
+def check(code):
+    if code != OK:
+        raise BasqError(code, lib.basq_last_error().decode("utf-8", "replace"))
+
+
+class Context:
+    """One basq_ctx per (device, stream)."""
+
+    def __init__(self, device_index: int, stream_ptr: int = 0):
+        h = C.c_void_p()
+        check(lib.basq_ctx_create(int(device_index), C.c_void_p(stream_ptr or None), C.byref(h)))
+        self.handle = h
+        self.device_index = device_index
+        self.stream_ptr = stream_ptr
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            lib.basq_ctx_destroy(h)
+
+    @property
+    def launches(self) -> int:
+        return int(lib.basq_ctx_launch_count(self.handle))
+
+    @property
+    def pair_evals(self) -> int:
+        return int(lib.basq_ctx_pair_evals(self.handle))
+
+    def profile(self, enable: bool):
+        check(lib.basq_ctx_profile(self.handle, 1 if enable else 0))
+
+    def profile_read(self, reset=True):
+        ms = (C.c_double * 8)()
+        calls = (C.c_int64 * 8)()
+        check(lib.basq_ctx_profile_read(self.handle, ms, calls, 1 if reset else 0))
+        return {PHASES[i]: (float(ms[i]), int(calls[i])) for i in range(8)}
+
+
+_contexts = {}
+
+
+def context_for(device) -> Context:
+    """Context bound to torch's current stream on `device` (a torch.device with type cuda)."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise BasqError(ERR_CUDA, "no CUDA device available; basq_b200 has no CPU fallback")
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise BasqError(ERR_CUDA, f"device {dev} is not a CUDA device; basq_b200 has no CPU fallback")
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    stream = torch.cuda.current_stream(index).cuda_stream
+    key = (index, stream)
+    ctx = _contexts.get(key)
+    if ctx is None:
+        ctx = _contexts[key] = Context(index, stream)
+    return ctx

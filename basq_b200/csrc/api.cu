@@ -369,6 +369,7 @@ void basq_ctx_destroy(basq_ctx* ctx) {
 }
 
 int64_t basq_ctx_launch_count(const basq_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t basq_ctx_pair_evals(const basq_ctx* ctx) { return ctx ? ctx->pair_evals : 0; }
 
 int basq_ctx_profile(basq_ctx* ctx, int enable) {
   BASQ_CHECK(ctx, BASQ_ERR_INVALID, "ctx is NULL");

@@ -53,6 +53,7 @@ struct basq_ctx {
   int num_sms = 0;
   size_t smem_optin = 0;
   int64_t launches = 0;
+  int64_t pair_evals = 0;
   bool profile = false;
   int timer_depth = 0;
   double phase_ms[basq::PH_COUNT] = {0};

@@ -10,6 +10,7 @@ int set_sums(basq_ctx* ctx, const KParams& kp, const SetSumArgs& a) {
   BASQ_CHECK(a.p_lo >= 0 && a.p_hi <= pool.count && a.p_lo <= a.p_hi, BASQ_ERR_INVALID, "set_sums: bad point range");
   BASQ_CHECK(a.S >= 1, BASQ_ERR_INVALID, "set_sums: S must be positive");
   if (a.nl != NL_LIN) BASQ_CHECK(a.corrT != nullptr, BASQ_ERR_INVALID, "set_sums: non-linear mode needs corrT");
+  ctx->pair_evals += (int64_t)lm.count * (a.p_hi - a.p_lo);
   SetSumDev dev;
   dev.recs = pool.buf[pool.cur].as<unsigned char>();
   dev.rec_bytes = pool.rec_bytes;

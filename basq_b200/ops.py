@@ -1,0 +1,204 @@
+"""Thin torch-tensor wrappers over the C ABI (device pointers in, torch tensors out).
+
+torch is used for device memory and streams only; all arithmetic happens inside libbasq_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .kernels import KernelSpec, describe_kernel
+
+
+def _prep(x: torch.Tensor, device, dtype):
+    return x.detach().to(device=device, dtype=dtype).contiguous()
+
+
+def _common(kernel, X, device=None):
+    spec = describe_kernel(kernel)
+    device = torch.device(device) if device is not None else X.device
+    dtype = X.dtype if X.dtype in (torch.float32, torch.float64) else torch.float32
+    ctx = _lib.context_for(device)
+    return spec, ctx, device, dtype
+
+
+def gram(kernel, X, Y, device=None) -> torch.Tensor:
+    """kernel(X, Y) as an fp64 [a, b] tensor - replaces the reference's kernel callable."""
+    spec, ctx, device, dtype = _common(kernel, X, device)
+    Xd, Yd = _prep(X, device, dtype), _prep(Y, device, dtype)
+    desc, keep = spec.to_desc(Xd.shape[1], device, dtype)
+    out = torch.empty(len(Xd), len(Yd), dtype=torch.float64, device=device)
+    _lib.check(_lib.lib.basq_gram(ctx.handle, C.byref(desc), Xd.data_ptr(), len(Xd), Yd.data_ptr(), len(Yd),
+                                  out.data_ptr()))
+    return out
+
+
+def gp_predict(kernel, X, space=0, want_var=True, device=None):
+    """GP posterior mean / variance over candidates (BASQ/_gp.py:213-230, exact variance).
+    space=1 returns the model-space moments of the kernel's mode (wsabi*_predict / gspace_predict)."""
+    spec, ctx, device, dtype = _common(kernel, X, device)
+    Xd = _prep(X, device, dtype)
+    desc, keep = spec.to_desc(Xd.shape[1], device, dtype)
+    mean = torch.empty(len(Xd), dtype=torch.float64, device=device)
+    var = torch.empty(len(Xd), dtype=torch.float64, device=device) if want_var else None
+    _lib.check(_lib.lib.basq_gp_predict(ctx.handle, C.byref(desc), Xd.data_ptr(), len(Xd), int(space),
+                                        float(spec.offset), mean.data_ptr(), var.data_ptr() if want_var else None))
+    return mean, var
+
+
+def nystrom_basis(kernel, Z, q, omega=None, niter=2, device=None):
+    """(S, U): Ritz values and an orthonormal basis U [q, M] of the randomised range of K(Z, Z)
+    (ker_svd_sparsify, BASQ/_rchq.py:28-31).  omega [M, q] defaults to torch.randn on the device,
+    consuming torch's global RNG exactly where torch.svd_lowrank would."""
+    spec, ctx, device, dtype = _common(kernel, Z, device)
+    Zd = _prep(Z, device, dtype)
+    M = len(Zd)
+    if omega is None:
+        omega = torch.randn(M, q, dtype=torch.float64, device=device)
+    omega = _prep(omega, device, torch.float64)
+    desc, keep = spec.to_desc(Zd.shape[1], device, dtype)
+    U = torch.empty(q, M, dtype=torch.float64, device=device)
+    S = torch.empty(q, dtype=torch.float64, device=device)
+    _lib.check(_lib.lib.basq_nystrom_basis(ctx.handle, C.byref(desc), Zd.data_ptr(), M, int(q), omega.data_ptr(),
+                                           int(niter), U.data_ptr(), S.data_ptr()))
+    return S, U
+
+
+def features(kernel, X, Z, U, device=None) -> torch.Tensor:
+    """Phi [N, q] = (U @ kernel(Z, X))^T in fp64 - the test functions recombination preserves."""
+    spec, ctx, device, dtype = _common(kernel, X, device)
+    Xd, Zd = _prep(X, device, dtype), _prep(Z, device, dtype)
+    Ud = _prep(U, device, torch.float64)
+    desc, keep = spec.to_desc(Xd.shape[1], device, dtype)
+    q = Ud.shape[0]
+    Phi = torch.empty(len(Xd), q, dtype=torch.float64, device=device)
+    _lib.check(_lib.lib.basq_features(ctx.handle, C.byref(desc), Xd.data_ptr(), len(Xd), Zd.data_ptr(), len(Zd),
+                                      Ud.data_ptr(), q, Phi.data_ptr()))
+    return Phi
+
+
+def caratheodory(A: torch.Tensor) -> torch.Tensor:
+    """omega [S] >= 0 with <= n non-zeros and A omega = A 1 for A [n, S] (row 0 = set masses)."""
+    ctx = _lib.context_for(A.device)
+    Ad = A.detach().to(torch.float64).contiguous().clone()
+    n, S = Ad.shape
+    omega = torch.zeros(S, dtype=torch.float64, device=A.device)
+    _lib.check(_lib.lib.basq_car(ctx.handle, Ad.data_ptr(), n, S, S, omega.data_ptr(), None))
+    return omega
+
+
+def dgemm(A, B, transA=False, transB=False):
+    ctx = _lib.context_for(A.device)
+    A = A.contiguous(); B = B.contiguous()
+    m = A.shape[1] if transA else A.shape[0]
+    k = A.shape[0] if transA else A.shape[1]
+    n = B.shape[0] if transB else B.shape[1]
+    Cm = torch.empty(m, n, dtype=torch.float64, device=A.device)
+    _lib.check(_lib.lib.basq_dgemm(ctx.handle, int(transA), int(transB), m, n, k, 1.0, A.data_ptr(), A.shape[1],
+                                   B.data_ptr(), B.shape[1], 0.0, Cm.data_ptr(), n))
+    return Cm
+
+
+def recombine(kernel, pts_rec, pts_nys, U, mu=None, device=None):
+    """Tchernychova-Lyons recombination with a given basis U [q, M]: (idx int64, w fp64) on device."""
+    spec, ctx, device, dtype = _common(kernel, pts_rec, device)
+    Xd, Zd = _prep(pts_rec, device, dtype), _prep(pts_nys, device, dtype)
+    Ud = _prep(U, device, torch.float64)
+    q = Ud.shape[0]
+    if Ud.shape[1] != len(Zd):
+        raise ValueError(f"U has {Ud.shape[1]} columns for {len(Zd)} Nystrom points")
+    mud = None
+    if mu is not None:
+        mud = _prep(mu, device, torch.float64)
+        if mud.shape != (len(Xd),):
+            raise ValueError("init_weights must have one entry per candidate")
+    desc, keep = spec.to_desc(Xd.shape[1], device, dtype)
+    idx = torch.empty(q + 1, dtype=torch.int64, device=device)
+    w = torch.empty(q + 1, dtype=torch.float64, device=device)
+    n_out = C.c_int(0)
+    _lib.check(_lib.lib.basq_recombine(ctx.handle, C.byref(desc), Xd.data_ptr(), len(Xd), Zd.data_ptr(), len(Zd),
+                                       Ud.data_ptr(), q, mud.data_ptr() if mud is not None else None,
+                                       idx.data_ptr(), w.data_ptr(), C.byref(n_out)))
+    return idx[: n_out.value], w[: n_out.value]
+
+
+def recombine_host(kernel, X_host, Z_host, q, U_host=None, omega_host=None, mu_host=None, niter=2, device="cuda"):
+    """The same through basq_recombine_host: HOST (ideally pinned) buffers in, host tensors out;
+    all host<->device copies happen inside the call (bench.py's end-to-end leg)."""
+    spec = describe_kernel(kernel)
+    device = torch.device(device)
+    ctx = _lib.context_for(device)
+    dtype = X_host.dtype
+    assert X_host.device.type == "cpu" and Z_host.device.type == "cpu"
+    X_host, Z_host = X_host.contiguous(), Z_host.contiguous()
+    desc, keep = spec.to_desc(X_host.shape[1], device, dtype)
+    idx = torch.empty(q + 1, dtype=torch.int64)
+    w = torch.empty(q + 1, dtype=torch.float64)
+    n_out = C.c_int(0)
+    ptr = lambda t: (t.contiguous().data_ptr() if t is not None else None)
+    if U_host is not None:
+        U_host = U_host.to(torch.float64).contiguous()
+    if omega_host is not None:
+        omega_host = omega_host.to(torch.float64).contiguous()
+    if mu_host is not None:
+        mu_host = mu_host.to(torch.float64).contiguous()
+    _lib.check(_lib.lib.basq_recombine_host(ctx.handle, C.byref(desc), X_host.data_ptr(), len(X_host),
+                                            Z_host.data_ptr(), len(Z_host), ptr(U_host), int(q), ptr(omega_host),
+                                            int(niter), ptr(mu_host), idx.data_ptr(), w.data_ptr(),
+                                            C.byref(n_out)))
+    return idx[: n_out.value], w[: n_out.value]
+
+
+class Session:
+    """Staged recombination over a rank-local shard (basq_session_* in the C ABI)."""
+
+    def __init__(self, kernel, X_loc, Z, U, N_glob, idx_base, mu_loc=None, device=None):
+        spec, ctx, device, dtype = _common(kernel, X_loc, device)
+        self.ctx, self.device = ctx, device
+        Xd, Zd = _prep(X_loc, device, dtype), _prep(Z, device, dtype)
+        Ud = _prep(U, device, torch.float64)
+        self.q = Ud.shape[0]
+        self.n = self.q + 1
+        self.S = 2 * self.n
+        mud = _prep(mu_loc, device, torch.float64) if mu_loc is not None else None
+        desc, keep = spec.to_desc(Zd.shape[1], device, dtype)
+        self._keep = keep + [Xd, Zd, Ud, mud]
+        h = C.c_void_p()
+        _lib.check(_lib.lib.basq_session_create(ctx.handle, C.byref(desc), Xd.data_ptr() if len(Xd) else None,
+                                                len(Xd), int(N_glob), int(idx_base), Zd.data_ptr(), len(Zd),
+                                                Ud.data_ptr(), self.q,
+                                                mud.data_ptr() if mud is not None else None, C.byref(h)))
+        self.handle = h
+
+    def close(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            _lib.lib.basq_session_destroy(h)
+
+    __del__ = close
+
+    def count(self) -> int:
+        c = C.c_int64(0)
+        _lib.check(_lib.lib.basq_session_count(self.handle, C.byref(c)))
+        return int(c.value)
+
+    def partial(self, R_glob, off_glob, A: torch.Tensor):
+        assert A.dtype == torch.float64 and A.is_contiguous() and A.shape == (self.n, self.S)
+        _lib.check(_lib.lib.basq_session_partial(self.handle, int(R_glob), int(off_glob), A.data_ptr()))
+
+    def car(self, A: torch.Tensor, S_eff: int, omega: torch.Tensor):
+        _lib.check(_lib.lib.basq_car(self.ctx.handle, A.data_ptr(), self.n, int(S_eff), self.S, omega.data_ptr(), None))
+
+    def apply(self, R_glob, off_glob, omega: torch.Tensor) -> int:
+        c = C.c_int64(0)
+        _lib.check(_lib.lib.basq_session_apply(self.handle, int(R_glob), int(off_glob), omega.data_ptr(), C.byref(c)))
+        return int(c.value)
+
+    def result(self):
+        idx = torch.empty(self.n, dtype=torch.int64, device=self.device)
+        w = torch.empty(self.n, dtype=torch.float64, device=self.device)
+        k = C.c_int(0)
+        _lib.check(_lib.lib.basq_session_result(self.handle, idx.data_ptr(), w.data_ptr(), self.n, C.byref(k)))
+        return idx[: k.value], w[: k.value]

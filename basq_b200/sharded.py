@@ -1,0 +1,110 @@
+"""Recombination of a candidate set sharded over ranks (one process per GPU).
+
+Per Tchernychova-Lyons round every rank forms the barycentre numerators of ITS points
+(set = global position mod S), one all-reduce sums the small [n, S] system over NVLink, every rank
+runs the same deterministic Caratheodory kernel on the identical reduced system, and rescales /
+compacts its own shard.  Counts and offsets after a round follow analytically from the kept sets,
+so the only collective on the data path is that all-reduce.
+
+The loop is written against a tiny engine interface so the host logic can be exercised on CPU with
+gloo and an oracle-backed engine (tests/test_sharded_gloo.py); the product engine is ops.Session.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(N, world, rank):
+    """Contiguous shard [lo, hi) of N candidates for `rank`."""
+    base, rem = divmod(N, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def kept_before(g, S, keep_prefix, K):
+    """Number of kept points among global positions < g when the kept sets have exclusive prefix
+    counts keep_prefix[0..S] (keep_prefix[S] = K)."""
+    e, j = divmod(int(g), S)
+    return e * K + int(keep_prefix[j])
+
+
+def recombine_sharded(engine, n, S, group=None, device=None, max_rounds=256):
+    """Run the round loop on `engine` (count/partial/car/apply/result).  Returns this rank's
+    surviving (idx, w); concatenate over ranks (gather_result) for the full rule."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    device = device if device is not None else getattr(engine, "device", "cpu")
+    counts = torch.zeros(world, dtype=torch.int64, device=device)
+    counts[rank] = engine.count()
+    if world > 1:
+        dist.all_reduce(counts, group=group)
+    counts = counts.cpu().tolist()
+    A = torch.zeros(n, S, dtype=torch.float64, device=device)
+    omega = torch.zeros(S, dtype=torch.float64, device=device)
+    rounds = 0
+    while sum(counts) > n:
+        rounds += 1
+        if rounds > max_rounds:
+            raise RuntimeError("recombine_sharded: no convergence")
+        R = sum(counts)
+        off = sum(counts[:rank])
+        engine.partial(R, off, A)
+        if world > 1:
+            dist.all_reduce(A, group=group)
+        S_eff = min(S, R)
+        omega.zero_()
+        engine.car(A, S_eff, omega)
+        new_local = engine.apply(R, off, omega)
+        # every rank derives every rank's new count from the kept sets: no extra collective
+        keep = (omega[:S_eff] > 0).to(torch.int64).cpu()
+        prefix = torch.zeros(S + 1, dtype=torch.int64)
+        prefix[1:S_eff + 1] = torch.cumsum(keep, 0)
+        prefix[S_eff + 1:] = prefix[S_eff]
+        K = int(prefix[S])
+        new_counts, o = [], 0
+        for c in counts:
+            new_counts.append(kept_before(o + c, S, prefix, K) - kept_before(o, S, prefix, K))
+            o += c
+        if new_counts[rank] != new_local:
+            raise RuntimeError(f"rank {rank}: survivor count mismatch {new_counts[rank]} != {new_local}")
+        if sum(new_counts) >= R:
+            raise RuntimeError("recombine_sharded: round made no progress")
+        counts = new_counts
+    return engine.result()
+
+
+def gather_result(idx, w, n, group=None):
+    """All-gather the per-rank survivors into one ascending (idx, w) on every rank."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return idx, w
+    world = dist.get_world_size(group)
+    dev = idx.device
+    pad_i = torch.full((n,), -1, dtype=torch.int64, device=dev)
+    pad_w = torch.zeros(n, dtype=torch.float64, device=dev)
+    pad_i[: len(idx)] = idx
+    pad_w[: len(w)] = w
+    all_i = [torch.empty_like(pad_i) for _ in range(world)]
+    all_w = [torch.empty_like(pad_w) for _ in range(world)]
+    dist.all_gather(all_i, pad_i, group=group)
+    dist.all_gather(all_w, pad_w, group=group)
+    I, W = torch.cat(all_i), torch.cat(all_w)
+    m = I >= 0
+    I, W = I[m], W[m]
+    order = torch.argsort(I)
+    return I[order], W[order]
+
+
+def recombination_sharded(pts_rec_local, pts_nys, num_pts, kernel, N_glob, idx_base, U, init_weights_local=None,
+                          group=None):
+    """Sharded counterpart of recombination(): this rank holds pts_rec_local = rows
+    [idx_base, idx_base + len) of the global candidate set; pts_nys, U and the GP caches are
+    replicated.  Returns the full (idx, w) on every rank."""
+    from . import ops
+
+    sess = ops.Session(kernel, pts_rec_local, pts_nys, U, N_glob, idx_base, mu_loc=init_weights_local)
+    try:
+        idx, w = recombine_sharded(sess, sess.n, sess.S, group=group, device=sess.device)
+        return gather_result(idx, w, sess.n, group=group)
+    finally:
+        sess.close()

@@ -1,6 +1,9 @@
-"""Build libbasq_b200.so (hand-written CUDA for sm_100a) in-tree with nvcc.
+"""Build basq_b200/libbasq_b200.so (hand-written CUDA for sm_100a) in-tree with nvcc.
 
-    python -m basq_b200.build [--force]
+    python buildlib.py [--force]
+
+Kept outside the package so that it can run when the library is missing or stale (importing
+basq_b200 loads the library and fails loudly without it).
 
 nvcc cross-compiles without a GPU; the resulting .so is git-ignored but travels to the GPU box.
 """
@@ -13,7 +16,7 @@ import os
 import subprocess
 import sys
 
-HERE = os.path.dirname(os.path.abspath(__file__))
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "basq_b200")
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libbasq_b200.so")

@@ -78,6 +78,8 @@ int basq_ctx_create(int device, void* stream, basq_ctx** out);
 void basq_ctx_destroy(basq_ctx* ctx);
 /* number of kernels this library has launched on ctx so far (bench.py's gpu_launches) */
 int64_t basq_ctx_launch_count(const basq_ctx* ctx);
+/* kernel evaluations k(z, x) performed by the set-sum kernel on ctx so far (roofline accounting) */
+int64_t basq_ctx_pair_evals(const basq_ctx* ctx);
 /* CUDA-event timings (ms) accumulated per phase since the last reset:
    0 prepare, 1 set-sum, 2 projection GEMM, 3 Caratheodory, 4 apply/compact, 5 nystrom, 6 gp predict.
    Only recorded when enabled (adds stream synchronisation). */

@@ -1,0 +1,106 @@
+"""Host-side logic that needs no GPU: kernel recognition (duck typing of the reference's kernel
+objects), descriptor filling, argument parsing of the two recombination signatures, shard maths."""
+import math
+
+import pytest
+import torch
+
+from basq_b200 import _lib, _rchq, kernels, sharded
+from oracle import gp_kernels as ogp
+
+
+def _model(noise=1e-4, mean_const=0.3, family="rbf"):
+    return ogp.make_gp(3, 12, family=family, lengthscale=1.3, outputscale=0.7, noise=noise, mean_const=mean_const)
+
+
+def test_describe_reference_kernel_objects():
+    m = _model()
+    cases = [
+        (ogp.VanillaGP(m).predictive_kernel, _lib.PRED_COV),
+        (ogp.WsabiGP(m, alpha=0.2).predictive_kernel, _lib.PRED_COV),
+        (ogp.WsabiGP(m, alpha=0.2).wsabil_kernel, _lib.WSABI_L),
+        (ogp.WsabiGP(m, alpha=0.2).wsabim_kernel, _lib.WSABI_M),
+        (ogp.ScaleMmltGP(m).gspace_kernel, _lib.MMLT_G),
+        (ogp.ScaleMmltGP(m).hspace_kernel, _lib.PRED_COV),
+        (ogp.Kernel(m, "predictive_covariance"), _lib.PRED_COV),
+        (ogp.Kernel(m, "weighted_predictive_covariance"), _lib.WSABI_L),
+        (ogp.Kernel(m, "kernel"), _lib.PLAIN),
+        (m.covar_module.forward, _lib.PLAIN),
+        (m.covar_module, _lib.PLAIN),
+    ]
+    for k, mode in cases:
+        spec = kernels.describe_kernel(k)
+        assert spec.mode == mode and spec.family == _lib.RBF
+        assert abs(spec.outputscale - 0.7) < 1e-12 and abs(float(spec.lengthscale[0]) - 1.3) < 1e-12
+        if mode != _lib.PLAIN:
+            assert abs(spec.noise - 1e-4) < 1e-15 and abs(spec.mean_const - 0.3) < 1e-12
+            W, Xobs, _ = ogp.get_cov_cache(m)
+            assert torch.allclose(spec.W, W) and spec.Xobs is Xobs
+    assert kernels.describe_kernel(ogp.WsabiGP(m, alpha=0.2).wsabil_kernel).offset == 0.2
+    assert kernels.describe_kernel(ogp.VanillaGP(m, add_noise_diag=True).predictive_kernel).diag_add == pytest.approx(1e-4)
+    assert kernels.describe_kernel(ogp.VanillaGP(m).predictive_kernel).diag_add == 0.0
+    mat = _model(family="matern")
+    assert kernels.describe_kernel(mat.covar_module.forward).family == _lib.MATERN25
+
+
+def test_unknown_callable_is_rejected():
+    with pytest.raises(TypeError, match="no generic"):
+        kernels.describe_kernel(lambda x, y: x @ y.T)
+    with pytest.raises(ValueError):
+        kernels.describe_kernel(ogp.Kernel(_model(), "nonsense"))
+
+
+def test_descriptor_fields():
+    m = _model()
+    spec = kernels.describe_kernel(ogp.VanillaGP(m).predictive_kernel)
+    desc, keep = spec.to_desc(3, torch.device("cpu"), torch.float32)
+    assert (desc.family, desc.mode, desc.dtype, desc.d, desc.n_obs) == (_lib.RBF, _lib.PRED_COV, _lib.F32, 3, 12)
+    assert [desc.lengthscale[i] for i in range(3)] == [1.3, 1.3, 1.3]
+    assert keep[0].dtype == torch.float32 and keep[1].dtype == torch.float64
+    with pytest.raises(ValueError):
+        spec.to_desc(4, torch.device("cpu"), torch.float32)
+    with pytest.raises(TypeError):
+        spec.to_desc(3, torch.device("cpu"), torch.float16)
+
+
+def test_recombination_signatures(monkeypatch):
+    seen = {}
+
+    def fake(samp, pt, s, kernel, device, mu=None, use_obj=True):
+        seen.update(dtype=samp.dtype, mu=mu, s=s)
+        return torch.arange(2), torch.ones(2)
+
+    monkeypatch.setattr(_rchq, "rc_kernel_svd", fake)
+    X, Z = torch.randn(20, 2), torch.randn(5, 2)
+    w0 = torch.rand(20)
+    _rchq.recombination(X, Z, 4, "k", "cpu")                                   # BASQ, default init_weights=0
+    assert seen["mu"] is None and seen["dtype"] == torch.float32
+    _rchq.recombination(X, Z, 4, "k", "cpu", w0)                               # BASQ ignores weights (:53)
+    assert seen["mu"] is None
+    _rchq.recombination(X, Z, 4, "k", "cpu", init_weights=w0)
+    assert seen["mu"] is None
+    _rchq.recombination(X, Z, 4, "k", "cpu", torch.float64, w0)                # SOBER honours them
+    assert seen["mu"] is w0 and seen["dtype"] == torch.float64
+    _rchq.recombination(X, Z, 4, "k", "cpu", dtype=torch.float64, init_weights=None, calc_obj=None)
+    assert seen["mu"] is None
+    monkeypatch.setattr(_rchq, "HONOUR_INIT_WEIGHTS_IN_BASQ_SIGNATURE", True)
+    _rchq.recombination(X, Z, 4, "k", "cpu", w0)
+    assert seen["mu"] is w0
+    with pytest.raises(ValueError):
+        _rchq.recombination(X, Z, 4, "k", "cpu", torch.float64, torch.rand(7))
+    with pytest.raises(NotImplementedError):
+        _rchq.recombination(X, Z, 4, "k", "cpu", torch.float64, None, lambda x: x)
+
+
+def test_shard_bounds_and_survivor_counts():
+    for N, W in [(10, 3), (7, 8), (1000, 4)]:
+        spans = [sharded.shard_bounds(N, W, r) for r in range(W)]
+        assert spans[0][0] == 0 and spans[-1][1] == N
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(W - 1))
+    # kept_before equals a brute-force count
+    S, R = 8, 53
+    keep = torch.tensor([1, 0, 1, 1, 0, 0, 1, 0])
+    prefix = torch.zeros(S + 1, dtype=torch.int64); prefix[1:] = torch.cumsum(keep, 0)
+    K = int(prefix[S])
+    brute = [sum(int(keep[g % S]) for g in range(p)) for p in range(R + 1)]
+    assert [sharded.kept_before(p, S, prefix, K) for p in range(R + 1)] == brute
