@@ -2,6 +2,7 @@
 // session and the single-call recombination loop.
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <memory>
@@ -292,7 +293,9 @@ int recombine_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, i
   BASQ_CHECK(idx_out && w_out && n_out_host, BASQ_ERR_INVALID, "recombine: NULL output");
   std::unique_ptr<basq_session> s(new (std::nothrow) basq_session());
   BASQ_CHECK(s, BASQ_ERR_INVALID, "out of host memory");
+  trace_point(ctx, "recombine: enter");
   BASQ_TRY(session_create_impl(ctx, desc, X, N, N, 0, Z, M, U, q, mu, 0, s.get()));
+  trace_point(ctx, "recombine: session created");
   const int n = s->n, S = s->S;
   DevBuf A, omega;
   BASQ_TRY(A.alloc(sizeof(double) * (size_t)n * S));
@@ -302,13 +305,17 @@ int recombine_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, i
   while (R > n) {
     BASQ_CHECK(++rounds <= 256, BASQ_ERR_NUMERIC, "recombine: no convergence after 256 rounds");
     BASQ_TRY(session_partial_impl(s.get(), R, 0, A.as<double>()));
+    trace_point(ctx, "  round: partial");
     const int S_eff = (int)std::min<int64_t>(S, R);
     BASQ_TRY(caratheodory(ctx, A.as<double>(), n, S_eff, S, omega.as<double>()));
+    trace_point(ctx, "  round: caratheodory");
     int64_t Rn = 0;
     BASQ_TRY(session_apply_impl(s.get(), R, 0, omega.as<double>(), &Rn));
+    trace_point(ctx, "  round: apply");
     BASQ_CHECK(Rn < R, BASQ_ERR_NUMERIC, "recombine: round %d made no progress (%lld points)", rounds, (long long)R);
     R = Rn;
   }
+  trace_point(ctx, "recombine: rounds done");
   BASQ_TRY(extract_result(ctx, s->pool, 0, idx_out, w_out));
   BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
   *n_out_host = (int)R;
@@ -355,6 +362,8 @@ int basq_ctx_create(int device, void* stream, basq_ctx** out) {
     set_error("basq_b200 is built for sm_100a (Blackwell B200); device %d is sm_%d%d", device, prop.major, prop.minor);
     return BASQ_ERR_CUDA;
   }
+  { const char* t = getenv("BASQ_TRACE"); c->trace = t && t[0] == '1'; }
+  { const char* t = getenv("BASQ_CAR_GENERAL"); c->force_general_car = t && t[0] == '1'; }
   cudaEventCreate(&c->ev0);
   cudaEventCreate(&c->ev1);
   *out = c;
@@ -539,6 +548,7 @@ int basq_recombine_host(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
   BASQ_CHECK(U_host || Omega_host, BASQ_ERR_INVALID, "basq_recombine_host: need U_host or Omega_host");
   BASQ_CUDA(cudaSetDevice(ctx->device));
   const size_t esz = desc->dtype == BASQ_F64 ? 8 : 4;
+  trace_point(ctx, "host: enter");
   DevBuf dX, dZ, dU, dOm, dmu, didx, dw;
   BASQ_TRY(dX.alloc(esz * (size_t)N * desc->d));
   BASQ_TRY(dZ.alloc(esz * (size_t)M * desc->d));
@@ -554,10 +564,12 @@ int basq_recombine_host(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
   if (U_host) {
     BASQ_CUDA(cudaMemcpyAsync(dU.p, U_host, sizeof(double) * (size_t)q * M, cudaMemcpyHostToDevice, ctx->stream));
   } else {
+    trace_point(ctx, "host: X/Z copied");
     BASQ_TRY(dOm.alloc(sizeof(double) * (size_t)M * q));
     BASQ_CUDA(cudaMemcpyAsync(dOm.p, Omega_host, sizeof(double) * (size_t)M * q, cudaMemcpyHostToDevice, ctx->stream));
     BASQ_TRY(nystrom_basis(ctx, desc, dZ.p, M, q, dOm.as<double>(), niter, dU.as<double>(), nullptr));
   }
+  trace_point(ctx, "host: inputs + basis on device");
   int n_out = 0;
   BASQ_TRY(recombine_impl(ctx, desc, dX.p, N, dZ.p, M, dU.as<double>(), q, mu_host ? dmu.as<double>() : nullptr,
                           didx.as<int64_t>(), dw.as<double>(), &n_out));
@@ -565,6 +577,7 @@ int basq_recombine_host(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
   BASQ_CUDA(cudaMemcpyAsync(w_out_host, dw.p, sizeof(double) * n_out, cudaMemcpyDeviceToHost, ctx->stream));
   BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
   *n_out_host = n_out;
+  trace_point(ctx, "host: results copied back");
   return BASQ_OK;
 }
 

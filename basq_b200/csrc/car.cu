@@ -317,9 +317,28 @@ __global__ void __launch_bounds__(CAR_THREADS, 1) car_kernel(const CarDev a) {
 
 }  // namespace
 
+bool caratheodory_fast_supported(const basq_ctx* ctx, int n, int S);
+int caratheodory_fast(basq_ctx* ctx, double* A, int n, int S, int lda, double* omega_out, int* status_out);
+
 int caratheodory(basq_ctx* ctx, double* A, int n, int S, int lda, double* omega_out) {
   PhaseTimer timer(ctx, PH_CAR);
   BASQ_CHECK(n >= 1 && S >= 1 && lda >= S, BASQ_ERR_INVALID, "caratheodory: bad shape n=%d S=%d lda=%d", n, S, lda);
+  if (S > n && !ctx->force_general_car && caratheodory_fast_supported(ctx, n, S)) {
+    // register-resident block-pivot kernel (car2.cu).  It can only run out of room when the
+    // system is rank deficient AND large; keep a copy of A for that case.
+    DevBuf backup;
+    const bool risky = (S + 7) / 8 > ctx->num_sms;
+    if (risky) {
+      BASQ_TRY(backup.alloc(sizeof(double) * (size_t)n * lda));
+      BASQ_CUDA(cudaMemcpyAsync(backup.p, A, sizeof(double) * (size_t)n * lda, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    int st = 0;
+    BASQ_TRY(caratheodory_fast(ctx, A, n, S, lda, omega_out, &st));
+    if (st == 0) return BASQ_OK;
+    BASQ_CHECK(risky, BASQ_ERR_NUMERIC, "caratheodory: fast kernel overflowed without a backup");
+    BASQ_CUDA(cudaMemcpyAsync(A, backup.p, sizeof(double) * (size_t)n * lda, cudaMemcpyDeviceToDevice, ctx->stream));
+    BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   if (S <= n) {
     // nothing to eliminate: every set keeps its weight
     std::vector<double> ones((size_t)S, 1.0);
@@ -344,10 +363,13 @@ int caratheodory(basq_ctx* ctx, double* A, int n, int S, int lda, double* omega_
   const size_t sz_prow = sizeof(double) * 2 * S, sz_rows = sizeof(double) * n, sz_tc = sizeof(double) * (size_t)S * n,
                sz_pcol = sizeof(double) * 2 * n, sz_sinfo = sizeof(double) * 4;
   const size_t sz_int = sizeof(int) * (2 + (size_t)S + n + 2 + 4);
-  BASQ_TRY(ws.alloc(sz_prow + sz_rows + sz_tc + sz_pcol + sz_sinfo + sz_int + 256));
+  BASQ_TRY(ws.alloc(512 + sz_prow + sz_rows + sz_tc + sz_pcol + sz_sinfo + sz_int + 256));
   unsigned char* w = ws.as<unsigned char>();
   CarDev d;
   d.A = A; d.n = n; d.S = S; d.lda = lda;
+  d.bar = reinterpret_cast<unsigned*>(w);            // 256 B: arrival counter + flag line
+  d.status = reinterpret_cast<int*>(w + 256);
+  w += 512;
   d.prow = reinterpret_cast<double*>(w); w += sz_prow;
   d.rowscale = reinterpret_cast<double*>(w); w += sz_rows;
   d.Tc = reinterpret_cast<double*>(w); w += sz_tc;
@@ -356,10 +378,9 @@ int caratheodory(basq_ctx* ctx, double* A, int n, int S, int lda, double* omega_
   d.pinfo = reinterpret_cast<int*>(w); w += sizeof(int) * 2;
   d.colbasis = reinterpret_cast<int*>(w); w += sizeof(int) * S;
   d.rowpoint = reinterpret_cast<int*>(w); w += sizeof(int) * n;
-  d.bar = reinterpret_cast<unsigned*>(w); w += sizeof(int) * 2;
-  d.status = reinterpret_cast<int*>(w); w += sizeof(int) * 2;
   d.omega = omega_out;
   d.tol = 1e-13;
+  BASQ_CUDA(cudaMemsetAsync(ws.p, 0, 512, ctx->stream));
   BASQ_CUDA(cudaMemsetAsync(d.pinfo, 0, sz_int, ctx->stream));
   void* args[] = {(void*)&d};
   BASQ_CUDA(cudaLaunchCooperativeKernel((const void*)car_kernel, dim3(G), dim3(CAR_THREADS), args, smem, ctx->stream));

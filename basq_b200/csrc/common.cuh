@@ -56,6 +56,9 @@ struct basq_ctx {
   int64_t pair_evals = 0;
   bool profile = false;
   int timer_depth = 0;
+  bool force_general_car = false;  // BASQ_CAR_GENERAL=1: always use the global-memory kernel (tests)
+  bool trace = false;      // BASQ_TRACE=1: wall-clock trace points on stderr (synchronising)
+  double trace_t0 = 0.0;
   double phase_ms[basq::PH_COUNT] = {0};
   int64_t phase_calls[basq::PH_COUNT] = {0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -113,6 +116,9 @@ struct DevBuf {
   template <typename T>
   T* as() const { return reinterpret_cast<T*>(p); }
 };
+
+// wall-clock trace point (debug aid; synchronises the stream when enabled)
+void trace_point(basq_ctx* ctx, const char* label);
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

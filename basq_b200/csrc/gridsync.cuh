@@ -9,24 +9,39 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned atom_add_acq_rel_u32(unsigned* p, unsigned v) {
+  unsigned old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
 
-// Monotone-counter grid barrier (all CTAs are co-resident: cooperative launch).  A watchdog turns
-// a would-be hang into an error flag; the return value (uniform over the CTA) says "abort".
-__device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned& target, int* status, int* abort_sh) {
+// Arrival counter and release flag live in DIFFERENT 128-byte lines: bar[0] = monotone arrival
+// count, bar[32] = generation flag.  The last arriver of a generation publishes the flag; everyone
+// else polls the flag (with a short sleep), so the polls never queue in front of the arrival
+// atomics at the L2 slice.  `gen` counts barriers passed (per thread 0).  A watchdog turns a
+// would-be hang into an error flag; the return value (uniform over the CTA) says "abort".
+constexpr int BASQ_BAR_WORDS = 64;  // unsigned words to reserve (and zero) per barrier
+
+__device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned& gen, int* status, int* abort_sh) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    target += gridDim.x;
-    atomicAdd(bar, 1u);
-    long long spins = 0;
-    while ((int)(ld_acquire_u32(bar) - target) < 0) {
-      ++spins;
-      if ((spins & 1023) == 0) {
-        if (*reinterpret_cast<volatile int*>(status) != 0) break;
-        if (spins > (1ll << 26)) { atomicExch(status, 2); break; }
+    gen += 1;
+    const unsigned old = atom_add_acq_rel_u32(bar, 1u);
+    if (old + 1u == gen * gridDim.x) {
+      st_release_u32(bar + 32, gen);
+    } else {
+      long long spins = 0;
+      while ((int)(ld_acquire_u32(bar + 32) - gen) < 0) {
+        __nanosleep(20);
+        if ((++spins & 4095) == 0) {
+          if (*reinterpret_cast<volatile int*>(status) != 0) break;
+          if (spins > (1ll << 26)) { atomicExch(status, 2); break; }
+        }
       }
     }
-    __threadfence();
     *abort_sh = *reinterpret_cast<volatile int*>(status);
   }
   __syncthreads();

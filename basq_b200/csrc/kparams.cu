@@ -2,6 +2,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <string.h>
+#include <time.h>
 
 #include "common.cuh"
 #include "prep.cuh"
@@ -19,6 +20,16 @@ void set_error(const char* fmt, ...) {
   g_last_error = buf;
 }
 const char* last_error_cstr() { return g_last_error.c_str(); }
+
+void trace_point(basq_ctx* ctx, const char* label) {
+  if (!ctx->trace) return;
+  cudaStreamSynchronize(ctx->stream);
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  fprintf(stderr, "[basq trace] %-28s +%9.3f ms\n", label, ctx->trace_t0 > 0 ? now - ctx->trace_t0 : 0.0);
+  ctx->trace_t0 = now;
+}
 
 int make_kparams(const basq_kernel_desc* desc, KParams* kp) {
   BASQ_CHECK(desc != nullptr, BASQ_ERR_INVALID, "kernel descriptor is NULL");

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chol_inv_kernel(const CholDev a
   __shared__ double bcast;
   __shared__ int abort_sh;
   const int q = a.q, G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
-  unsigned target = 0;
+  unsigned target = 0;  // barriers passed
 
   // W = I on own rows
   for (int r = b; r < q; r += G)
@@ -102,6 +102,165 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chol_inv_kernel(const CholDev a
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Register-resident block version of the same elimination (the fast path for 2q <= 2048): CTA k
+// keeps rows [kB, kB+B) of [G | I] in registers (thread t holds columns t, t+512, ...), performs its
+// B diagonal pivots locally and streams the scaled rows to L2; one grid barrier per block; the CTAs
+// below replay the B rank-1 updates.  See car2.cu for the same scheme with pivot search.
+// ---------------------------------------------------------------------------------------------
+constexpr int C2_NT = 512, C2_CPT = 4;
+
+struct Chol2Dev {
+  const double* G;  // [q, q]
+  double* W;        // [q, q] out: L^-1
+  int q;
+  double* prow;     // [q][2q]
+  double floor;
+  unsigned* bar;
+  int* status;
+};
+
+template <int B>
+__global__ void __launch_bounds__(C2_NT, 1) chol2_kernel(const Chol2Dev a) {
+  __shared__ double fbuf[2][8];
+  __shared__ double pbcast;
+  __shared__ int abort_sh;
+  const int q = a.q, W2 = 2 * a.q, b = blockIdx.x, tid = threadIdx.x;
+  unsigned gen = 0;
+  int par = 0;
+  const int G1 = (q + B - 1) / B;
+  const int r0 = b * B;
+  const int rows_mine = max(0, min(B, q - r0));
+  double reg[B][C2_CPT];
+#pragma unroll
+  for (int i = 0; i < B; ++i)
+#pragma unroll
+    for (int j = 0; j < C2_CPT; ++j) {
+      const int c = tid + j * C2_NT;
+      double v = 0.0;
+      if (i < rows_mine && c < W2) v = (c < q) ? a.G[(int64_t)(r0 + i) * q + c] : ((c - q == r0 + i) ? 1.0 : 0.0);
+      reg[i][j] = v;
+    }
+
+  for (int k = 0; k < G1; ++k) {
+    const int kr0 = k * B;
+    const int krows = min(B, q - kr0);
+    if (b == k) {
+#pragma unroll
+      for (int i = 0; i < B; ++i) {
+        if (i < krows) {
+          const int r = kr0 + i;
+          const bool mine = (r % C2_NT) == tid;
+          const int js = r / C2_NT;
+          if (mine) {
+            double p = 0.0;
+#pragma unroll
+            for (int j = 0; j < C2_CPT; ++j)
+              if (j == js) p = reg[i][j];
+            if (!(p > a.floor)) p = a.floor;
+            pbcast = 1.0 / sqrt(p);
+          }
+          __syncthreads();
+          const double inv = pbcast;
+#pragma unroll
+          for (int j = 0; j < C2_CPT; ++j) {
+            const int c = tid + j * C2_NT;
+            reg[i][j] *= inv;
+            if (c < W2) __stcg(&a.prow[(int64_t)r * W2 + c], reg[i][j]);
+          }
+          if (mine) {
+            double d = 1.0;
+#pragma unroll
+            for (int j = 0; j < C2_CPT; ++j)
+              if (j == js) d = reg[i][j];
+#pragma unroll
+            for (int i2 = 0; i2 < B; ++i2) {
+              double f = 0.0;
+#pragma unroll
+              for (int j = 0; j < C2_CPT; ++j)
+                if (j == js) f = reg[i2][j];
+              fbuf[par][i2] = f / d;
+            }
+          }
+          __syncthreads();
+#pragma unroll
+          for (int i2 = 0; i2 < B; ++i2) {
+            if (i2 > i && i2 < krows) {
+              const double f = fbuf[par][i2];
+#pragma unroll
+              for (int j = 0; j < C2_CPT; ++j)
+                reg[i2][j] = (tid + j * C2_NT == r) ? 0.0 : fma(-f, reg[i][j], reg[i2][j]);
+            }
+          }
+          par ^= 1;
+        }
+      }
+    }
+    if (grid_barrier(a.bar, gen, a.status, &abort_sh)) return;
+    if (b > k) {
+      double cur[C2_CPT], nxt[C2_CPT];
+#pragma unroll
+      for (int j = 0; j < C2_CPT; ++j) {
+        const int c = tid + j * C2_NT;
+        cur[j] = (c < W2) ? __ldcg(&a.prow[(int64_t)kr0 * W2 + c]) : 0.0;
+      }
+      for (int i = 0; i < krows; ++i) {
+        const int r = kr0 + i;
+#pragma unroll
+        for (int j = 0; j < C2_CPT; ++j) {
+          const int c = tid + j * C2_NT;
+          nxt[j] = (i + 1 < krows && c < W2) ? __ldcg(&a.prow[(int64_t)(r + 1) * W2 + c]) : 0.0;
+        }
+        const int js = r / C2_NT;
+        if ((r % C2_NT) == tid) {
+          double d = 1.0;
+#pragma unroll
+          for (int j = 0; j < C2_CPT; ++j)
+            if (j == js) d = cur[j];
+#pragma unroll
+          for (int i2 = 0; i2 < B; ++i2) {
+            double f = 0.0;
+#pragma unroll
+            for (int j = 0; j < C2_CPT; ++j)
+              if (j == js) f = reg[i2][j];
+            fbuf[par][i2] = f / d;
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i2 = 0; i2 < B; ++i2) {
+          if (i2 < rows_mine) {
+            const double f = fbuf[par][i2];
+#pragma unroll
+            for (int j = 0; j < C2_CPT; ++j)
+              reg[i2][j] = (tid + j * C2_NT == r) ? 0.0 : fma(-f, cur[j], reg[i2][j]);
+          }
+        }
+        par ^= 1;
+#pragma unroll
+        for (int j = 0; j < C2_CPT; ++j) cur[j] = nxt[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < B; ++i)
+    if (i < rows_mine) {
+#pragma unroll
+      for (int j = 0; j < C2_CPT; ++j) {
+        const int c = tid + j * C2_NT;
+        if (c >= q && c < W2) a.W[(int64_t)(r0 + i) * q + (c - q)] = reg[i][j];
+      }
+    }
+}
+
+template <int B>
+int launch_chol2(basq_ctx* ctx, const Chol2Dev& d, int grid) {
+  void* args[] = {(void*)&d};
+  BASQ_CUDA(cudaLaunchCooperativeKernel((const void*)chol2_kernel<B>, dim3(grid), dim3(C2_NT), args, 0, ctx->stream));
+  return BASQ_OK;
+}
+
 __global__ void add_diag_kernel(double* __restrict__ G, int q, int64_t ld, double s) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < q) G[(int64_t)i * ld + i] += s;
@@ -126,10 +285,32 @@ __global__ void trace_kernel(const double* __restrict__ G, int q, int64_t ld, do
 }
 
 struct OrthWs {
-  DevBuf gram, linv, tmp, prow, flags, scal;
+  DevBuf gram, linv, tmp, prow, prow2, flags, scal;
 };
 
 int chol_inverse(basq_ctx* ctx, OrthWs& ws, int q, double floor_val) {
+  if (2 * q <= C2_NT * C2_CPT && q <= 8 * ctx->num_sms) {
+    int B = 1;
+    while (B < 8 && (q + B - 1) / B > ctx->num_sms) B *= 2;
+    Chol2Dev d2;
+    d2.G = ws.gram.as<double>();
+    d2.W = ws.linv.as<double>();
+    d2.q = q;
+    d2.prow = ws.prow2.as<double>();
+    d2.floor = floor_val;
+    d2.bar = ws.flags.as<unsigned>();
+    d2.status = ws.flags.as<int>() + 64;
+    BASQ_CUDA(cudaMemsetAsync(ws.flags.p, 0, 256, ctx->stream));
+    const int grid = (q + B - 1) / B;
+    switch (B) {
+      case 1: BASQ_TRY(launch_chol2<1>(ctx, d2, grid)); break;
+      case 2: BASQ_TRY(launch_chol2<2>(ctx, d2, grid)); break;
+      case 4: BASQ_TRY(launch_chol2<4>(ctx, d2, grid)); break;
+      default: BASQ_TRY(launch_chol2<8>(ctx, d2, grid)); break;
+    }
+    ctx->launches++;
+    return BASQ_OK;
+  }
   CholDev d;
   d.G = ws.gram.as<double>();
   d.W = ws.linv.as<double>();
@@ -138,8 +319,8 @@ int chol_inverse(basq_ctx* ctx, OrthWs& ws, int q, double floor_val) {
   d.prow = ws.prow.as<double>();
   d.floor = floor_val;
   d.bar = ws.flags.as<unsigned>();
-  d.status = ws.flags.as<int>() + 2;
-  BASQ_CUDA(cudaMemsetAsync(ws.flags.p, 0, 8, ctx->stream));
+  d.status = ws.flags.as<int>() + 64;
+  BASQ_CUDA(cudaMemsetAsync(ws.flags.p, 0, 256, ctx->stream));
   const size_t smem = sizeof(double) * 2 * q;
   BASQ_CHECK(smem <= ctx->smem_optin, BASQ_ERR_UNSUPPORTED, "nystrom: q=%d too large for the Cholesky kernel", q);
   BASQ_CUDA(cudaFuncSetAttribute(chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -153,9 +334,11 @@ int chol_inverse(basq_ctx* ctx, OrthWs& ws, int q, double floor_val) {
   return BASQ_OK;
 }
 
-// Y [M, q] (ld = q) <- orthonormal basis of span(Y): shifted CholeskyQR, three passes
-int orthonormalise(basq_ctx* ctx, OrthWs& ws, double* Y, int64_t M, int q) {
-  for (int pass = 0; pass < 3; ++pass) {
+// Y [M, q] (ld = q) <- basis of span(Y) by shifted CholeskyQR: `passes` = 3 gives an orthonormal
+// basis to machine precision (sCholQR3); 2 is enough between subspace iterations, where only the
+// conditioning of the basis matters
+int orthonormalise(basq_ctx* ctx, OrthWs& ws, double* Y, int64_t M, int q, int passes) {
+  for (int pass = 0; pass < passes; ++pass) {
     BASQ_TRY(dgemm(ctx, true, false, q, q, (int)M, 1.0, Y, q, Y, q, 0.0, ws.gram.as<double>(), q));
     trace_kernel<<<1, 256, 0, ctx->stream>>>(ws.gram.as<double>(), q, q, ws.scal.as<double>());
     ctx->launches++;
@@ -176,7 +359,7 @@ int orthonormalise(basq_ctx* ctx, OrthWs& ws, double* Y, int64_t M, int q) {
     BASQ_CUDA(cudaMemcpyAsync(Y, ws.tmp.p, sizeof(double) * (size_t)M * q, cudaMemcpyDeviceToDevice, ctx->stream));
   }
   int status = 0;
-  BASQ_CUDA(cudaMemcpyAsync(&status, ws.flags.as<int>() + 2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  BASQ_CUDA(cudaMemcpyAsync(&status, ws.flags.as<int>() + 64, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
   BASQ_CHECK(status == 0, BASQ_ERR_NUMERIC, "nystrom: grid barrier watchdog fired in the Cholesky kernel");
   return BASQ_OK;
@@ -199,20 +382,21 @@ int nystrom_basis(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, in
   BASQ_TRY(ws.linv.alloc(sizeof(double) * (size_t)q * q));
   BASQ_TRY(ws.tmp.alloc(sizeof(double) * (size_t)M * q));
   BASQ_TRY(ws.prow.alloc(sizeof(double) * 4 * q));
-  BASQ_TRY(ws.flags.alloc(64));
-  BASQ_CUDA(cudaMemsetAsync(ws.flags.p, 0, 64, ctx->stream));
+  BASQ_TRY(ws.prow2.alloc(sizeof(double) * 2 * (size_t)q * q));
+  BASQ_TRY(ws.flags.alloc(512));
+  BASQ_CUDA(cudaMemsetAsync(ws.flags.p, 0, 512, ctx->stream));
   BASQ_TRY(ws.scal.alloc(64));
   BASQ_TRY(basq_gram(ctx, desc, Z, M, Z, M, K.as<double>()));
 
   const int Mi = (int)M;
   BASQ_TRY(dgemm(ctx, false, false, Mi, q, Mi, 1.0, K.as<double>(), M, Omega, q, 0.0, Y.as<double>(), q));
-  BASQ_TRY(orthonormalise(ctx, ws, Y.as<double>(), M, q));
+  BASQ_TRY(orthonormalise(ctx, ws, Y.as<double>(), M, q, niter > 0 ? 2 : 3));
   BASQ_TRY(Y2.alloc(sizeof(double) * (size_t)M * q));
   for (int it = 0; it < niter; ++it) {
     BASQ_TRY(dgemm(ctx, true, false, Mi, q, Mi, 1.0, K.as<double>(), M, Y.as<double>(), q, 0.0, Y2.as<double>(), q));
-    BASQ_TRY(orthonormalise(ctx, ws, Y2.as<double>(), M, q));
+    BASQ_TRY(orthonormalise(ctx, ws, Y2.as<double>(), M, q, 2));
     BASQ_TRY(dgemm(ctx, false, false, Mi, q, Mi, 1.0, K.as<double>(), M, Y2.as<double>(), q, 0.0, Y.as<double>(), q));
-    BASQ_TRY(orthonormalise(ctx, ws, Y.as<double>(), M, q));
+    BASQ_TRY(orthonormalise(ctx, ws, Y.as<double>(), M, q, it + 1 == niter ? 3 : 2));
   }
   // U = Q^T  [q, M]  (transpose through a GEMM with the identity would waste flops: use geam-like copy)
   {

@@ -201,6 +201,23 @@ def test_car_rank_deficient_and_trivial(bq):
     assert len(idx2) == 10 and torch.allclose(w2.cpu(), mu[:10])
 
 
+def test_car_large_rank_deficient_falls_back(bq):
+    """S = 2000 sets but only ~500 independent features: more non-basic sets than the
+    register-resident kernel can hold -> the general kernel takes over (car.cu)."""
+    basq_b200, _, _ = bq
+    g = torch.Generator().manual_seed(4)
+    S, q, r = 2000, 999, 500
+    base = torch.randn(S, r, generator=g, dtype=torch.float64)
+    mix = torch.randn(r, q - r, generator=g, dtype=torch.float64) / math.sqrt(r)
+    X = torch.cat([base, base @ mix], 1)
+    mu = torch.rand(S, generator=g, dtype=torch.float64) + 0.01
+    mu /= mu.sum()
+    w, idx, *_ = basq_b200.Tchernychova_Lyons_CAR(X.to(DEV), mu.to(DEV), DEV)
+    A = torch.cat([torch.ones(S, 1, dtype=torch.float64), X], 1)
+    res = float(torch.linalg.norm(A.T @ mu - A[idx.cpu()].T @ w.cpu()) / torch.linalg.norm(A.T @ mu))
+    assert res < 1e-9 and len(idx) <= r + 1 and bool((w > 0).all())
+
+
 # ------------------------------------------------------------------------------------------- features
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.float64, 1e-11)])
 @pytest.mark.parametrize("name", ["forward", "pred_cov", "wsabil", "wsabim", "mmlt"])
