@@ -71,7 +71,7 @@ def ker_svd_sparsify(pt, s, kernel, device=None):
 def rc_kernel_svd(samp, pt, s, kernel, device, mu=None, use_obj=True):
     """BASQ/_rchq.py:34-40: Nystrom basis, then the Tchernychova-Lyons loop.  Returns (idx, w)."""
     device = torch.device(device)
-    _, U = ops.nystrom_basis(kernel, pt, s - 1, device=device)
+    _, U = ops.nystrom_basis(kernel, pt, s - 1, device=device, want_S=False)
     w_star, idx_star = Mod_Tchernychova_Lyons(samp, U, pt, kernel, device, mu=mu)
     return idx_star, w_star
 

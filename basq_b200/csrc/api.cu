@@ -166,14 +166,14 @@ int session_create_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
   DevBuf sx;
   const bool has_factor = (mode == BASQ_WSABI_L || mode == BASQ_WSABI_M || mode == BASQ_MMLT_G);
   if (has_factor) {
-    BASQ_TRY(s->sz.alloc(sizeof(double) * M));
+    BASQ_TRY(s->sz.alloc(ctx, sizeof(double) * M));
     BASQ_TRY(warp_factor(ctx, desc, s->kp, s->lmobs.view(), Z, M, s->sz.as<double>()));
-    BASQ_TRY(sx.alloc(sizeof(double) * std::max<int64_t>(N_loc, 1)));
+    BASQ_TRY(sx.alloc(ctx, sizeof(double) * std::max<int64_t>(N_loc, 1)));
     BASQ_TRY(warp_factor(ctx, desc, s->kp, s->lmobs.view(), X, N_loc, sx.as<double>()));
   }
 
   // projection matrix U' [q, Mtot]
-  BASQ_TRY(s->Uprime.alloc(sizeof(double) * (size_t)q * s->Mtot));
+  BASQ_TRY(s->Uprime.alloc(ctx, sizeof(double) * (size_t)q * s->Mtot));
   BASQ_CUDA(cudaMemcpy2DAsync(s->Uprime.p, sizeof(double) * s->Mtot, U, sizeof(double) * M, sizeof(double) * M, q,
                               cudaMemcpyDeviceToDevice, ctx->stream));
   if (mode == BASQ_WSABI_L) {
@@ -184,8 +184,8 @@ int session_create_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
   if (mode != BASQ_PLAIN) {
     // Az = K(Z, Xobs) W   (BASQ/_gp.py:270-273: KxX @ woodbury_inv)
     DevBuf KzX;
-    BASQ_TRY(KzX.alloc(sizeof(double) * (size_t)M * n_obs));
-    BASQ_TRY(s->Az.alloc(sizeof(double) * (size_t)M * n_obs));
+    BASQ_TRY(KzX.alloc(ctx, sizeof(double) * (size_t)M * n_obs));
+    BASQ_TRY(s->Az.alloc(ctx, sizeof(double) * (size_t)M * n_obs));
     BASQ_TRY(base_gram(ctx, s->kp, s->lm.view(0, (int)M), desc->Xobs, n_obs, KzX.as<double>(), n_obs));
     BASQ_TRY(dgemm(ctx, false, false, (int)M, n_obs, n_obs, 1.0, KzX.as<double>(), n_obs, desc->W, n_obs, 0.0,
                    s->Az.as<double>(), n_obs));
@@ -204,14 +204,14 @@ int session_create_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
                          !nonlin, &s->pool));
 
   s->ldg = s->S;
-  BASQ_TRY(s->G.alloc(sizeof(double) * (size_t)s->Mtot * s->ldg));
-  BASQ_TRY(s->rank.alloc(sizeof(int) * s->S));
+  BASQ_TRY(s->G.alloc(ctx, sizeof(double) * (size_t)s->Mtot * s->ldg));
+  BASQ_TRY(s->rank.alloc(ctx, sizeof(int) * s->S));
   if (nonlin) {
     int64_t P = (int64_t)(96ll << 20) / (8ll * std::max<int64_t>(M, n_obs));
     P = std::max<int64_t>(1024, std::min<int64_t>(P, 65536));
     s->chunkP = P;
-    BASQ_TRY(s->V.alloc(sizeof(double) * (size_t)n_obs * P));
-    BASQ_TRY(s->corrT.alloc(sizeof(double) * (size_t)M * P));
+    BASQ_TRY(s->V.alloc(ctx, sizeof(double) * (size_t)n_obs * P));
+    BASQ_TRY(s->corrT.alloc(ctx, sizeof(double) * (size_t)M * P));
   }
   s->omega_host.resize(s->S);
   s->rank_host.resize(s->S);
@@ -276,7 +276,7 @@ int session_features(basq_session* s, double* Phi_out) {
   const int64_t N = s->pool.count;
   const int64_t P = 16384;
   DevBuf Gc;
-  BASQ_TRY(Gc.alloc(sizeof(double) * (size_t)s->Mtot * P));
+  BASQ_TRY(Gc.alloc(ctx, sizeof(double) * (size_t)s->Mtot * P));
   for (int64_t p0 = 0; p0 < N; p0 += P) {
     const int64_t p1 = std::min(N, p0 + P);
     BASQ_TRY(session_set_sums(s, -p0, (int)P, p0, p1, Gc.as<double>(), P));
@@ -298,8 +298,8 @@ int recombine_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, i
   trace_point(ctx, "recombine: session created");
   const int n = s->n, S = s->S;
   DevBuf A, omega;
-  BASQ_TRY(A.alloc(sizeof(double) * (size_t)n * S));
-  BASQ_TRY(omega.alloc(sizeof(double) * S));
+  BASQ_TRY(A.alloc(ctx, sizeof(double) * (size_t)n * S));
+  BASQ_TRY(omega.alloc(ctx, sizeof(double) * S));
   int64_t R = s->pool.count;
   int rounds = 0;
   while (R > n) {
@@ -362,6 +362,15 @@ int basq_ctx_create(int device, void* stream, basq_ctx** out) {
     set_error("basq_b200 is built for sm_100a (Blackwell B200); device %d is sm_%d%d", device, prop.major, prop.minor);
     return BASQ_ERR_CUDA;
   }
+  {
+    // keep freed scratch in the stream-ordered pool instead of returning it to the driver
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    (void)cudaGetLastError();
+  }
   { const char* t = getenv("BASQ_TRACE"); c->trace = t && t[0] == '1'; }
   { const char* t = getenv("BASQ_CAR_GENERAL"); c->force_general_car = t && t[0] == '1'; }
   cudaEventCreate(&c->ev0);
@@ -423,9 +432,9 @@ int basq_gram(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_
     Landmarks lmobs;
     BASQ_TRY(prep_landmarks(ctx, kp, desc->dtype, desc->Xobs, n_obs, nullptr, 0, &lmobs));
     DevBuf KxX, T, KXy, fx, fy;
-    BASQ_TRY(KxX.alloc(sizeof(double) * (size_t)a * n_obs));
-    BASQ_TRY(T.alloc(sizeof(double) * (size_t)a * n_obs));
-    BASQ_TRY(KXy.alloc(sizeof(double) * (size_t)n_obs * b));
+    BASQ_TRY(KxX.alloc(ctx, sizeof(double) * (size_t)a * n_obs));
+    BASQ_TRY(T.alloc(ctx, sizeof(double) * (size_t)a * n_obs));
+    BASQ_TRY(KXy.alloc(ctx, sizeof(double) * (size_t)n_obs * b));
     BASQ_TRY(base_gram(ctx, kp, lmx.view(), desc->Xobs, n_obs, KxX.as<double>(), n_obs));
     BASQ_TRY(base_gram(ctx, kp, lmobs.view(), Y, b, KXy.as<double>(), b));
     BASQ_CHECK(a < (1ll << 31) && b < (1ll << 31), BASQ_ERR_UNSUPPORTED, "basq_gram: operand too large");
@@ -435,8 +444,8 @@ int basq_gram(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_
                    out, b));
     const bool warped = (mode == BASQ_WSABI_L || mode == BASQ_WSABI_M || mode == BASQ_MMLT_G);
     if (warped) {
-      BASQ_TRY(fx.alloc(sizeof(double) * a));
-      BASQ_TRY(fy.alloc(sizeof(double) * b));
+      BASQ_TRY(fx.alloc(ctx, sizeof(double) * a));
+      BASQ_TRY(fy.alloc(ctx, sizeof(double) * b));
       BASQ_TRY(warp_factor(ctx, desc, kp, lmobs.view(), X, a, fx.as<double>()));
       BASQ_TRY(warp_factor(ctx, desc, kp, lmobs.view(), Y, b, fy.as<double>()));
     }
@@ -477,7 +486,7 @@ int basq_gp_predict(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, 
   DevBuf vtmp;
   double* var = var_out;
   if (need_var && !var) {
-    BASQ_TRY(vtmp.alloc(sizeof(double) * N));
+    BASQ_TRY(vtmp.alloc(ctx, sizeof(double) * N));
     var = vtmp.as<double>();
   }
   BASQ_TRY(gp_predict_impl(ctx, &d2, kp, lmobs.view(), X, N, mean_out, need_var ? var : nullptr));
@@ -507,7 +516,7 @@ int basq_features(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, in
   BASQ_CHECK(s, BASQ_ERR_INVALID, "out of host memory");
   // unit weights: the feature of a point is its set sum with weight 1 (S = 4 keeps the round buffers tiny)
   DevBuf ones;
-  BASQ_TRY(ones.alloc(sizeof(double) * N));
+  BASQ_TRY(ones.alloc(ctx, sizeof(double) * N));
   {
     std::vector<double> h((size_t)N, 1.0);
     BASQ_CUDA(cudaMemcpyAsync(ones.p, h.data(), sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
@@ -550,22 +559,22 @@ int basq_recombine_host(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
   const size_t esz = desc->dtype == BASQ_F64 ? 8 : 4;
   trace_point(ctx, "host: enter");
   DevBuf dX, dZ, dU, dOm, dmu, didx, dw;
-  BASQ_TRY(dX.alloc(esz * (size_t)N * desc->d));
-  BASQ_TRY(dZ.alloc(esz * (size_t)M * desc->d));
-  BASQ_TRY(dU.alloc(sizeof(double) * (size_t)q * M));
-  BASQ_TRY(didx.alloc(sizeof(int64_t) * (q + 1)));
-  BASQ_TRY(dw.alloc(sizeof(double) * (q + 1)));
+  BASQ_TRY(dX.alloc(ctx, esz * (size_t)N * desc->d));
+  BASQ_TRY(dZ.alloc(ctx, esz * (size_t)M * desc->d));
+  BASQ_TRY(dU.alloc(ctx, sizeof(double) * (size_t)q * M));
+  BASQ_TRY(didx.alloc(ctx, sizeof(int64_t) * (q + 1)));
+  BASQ_TRY(dw.alloc(ctx, sizeof(double) * (q + 1)));
   BASQ_CUDA(cudaMemcpyAsync(dX.p, X_host, esz * (size_t)N * desc->d, cudaMemcpyHostToDevice, ctx->stream));
   BASQ_CUDA(cudaMemcpyAsync(dZ.p, Z_host, esz * (size_t)M * desc->d, cudaMemcpyHostToDevice, ctx->stream));
   if (mu_host) {
-    BASQ_TRY(dmu.alloc(sizeof(double) * N));
+    BASQ_TRY(dmu.alloc(ctx, sizeof(double) * N));
     BASQ_CUDA(cudaMemcpyAsync(dmu.p, mu_host, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
   }
   if (U_host) {
     BASQ_CUDA(cudaMemcpyAsync(dU.p, U_host, sizeof(double) * (size_t)q * M, cudaMemcpyHostToDevice, ctx->stream));
   } else {
     trace_point(ctx, "host: X/Z copied");
-    BASQ_TRY(dOm.alloc(sizeof(double) * (size_t)M * q));
+    BASQ_TRY(dOm.alloc(ctx, sizeof(double) * (size_t)M * q));
     BASQ_CUDA(cudaMemcpyAsync(dOm.p, Omega_host, sizeof(double) * (size_t)M * q, cudaMemcpyHostToDevice, ctx->stream));
     BASQ_TRY(nystrom_basis(ctx, desc, dZ.p, M, q, dOm.as<double>(), niter, dU.as<double>(), nullptr));
   }

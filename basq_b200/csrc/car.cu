@@ -329,7 +329,7 @@ int caratheodory(basq_ctx* ctx, double* A, int n, int S, int lda, double* omega_
     DevBuf backup;
     const bool risky = (S + 7) / 8 > ctx->num_sms;
     if (risky) {
-      BASQ_TRY(backup.alloc(sizeof(double) * (size_t)n * lda));
+      BASQ_TRY(backup.alloc(ctx, sizeof(double) * (size_t)n * lda));
       BASQ_CUDA(cudaMemcpyAsync(backup.p, A, sizeof(double) * (size_t)n * lda, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     int st = 0;
@@ -363,7 +363,7 @@ int caratheodory(basq_ctx* ctx, double* A, int n, int S, int lda, double* omega_
   const size_t sz_prow = sizeof(double) * 2 * S, sz_rows = sizeof(double) * n, sz_tc = sizeof(double) * (size_t)S * n,
                sz_pcol = sizeof(double) * 2 * n, sz_sinfo = sizeof(double) * 4;
   const size_t sz_int = sizeof(int) * (2 + (size_t)S + n + 2 + 4);
-  BASQ_TRY(ws.alloc(512 + sz_prow + sz_rows + sz_tc + sz_pcol + sz_sinfo + sz_int + 256));
+  BASQ_TRY(ws.alloc(ctx, 512 + sz_prow + sz_rows + sz_tc + sz_pcol + sz_sinfo + sz_int + 256));
   unsigned char* w = ws.as<unsigned char>();
   CarDev d;
   d.A = A; d.n = n; d.S = S; d.lda = lda;

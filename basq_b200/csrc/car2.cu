@@ -431,7 +431,7 @@ int caratheodory_fast(basq_ctx* ctx, double* A, int n, int S, int lda, double* o
   DevBuf ws;
   const size_t sz_prow = sizeof(double) * (size_t)n * S, sz_pcol = sizeof(double) * (size_t)S * n,
                sz_sinfo = sizeof(double) * 2 * S, sz_int = sizeof(int) * ((size_t)n + 8);
-  BASQ_TRY(ws.alloc(512 + sz_prow + sz_pcol + sz_sinfo + sz_int + 64));
+  BASQ_TRY(ws.alloc(ctx, 512 + sz_prow + sz_pcol + sz_sinfo + sz_int + 64));
   unsigned char* w = ws.as<unsigned char>();
   Car2Dev d;
   d.A = A; d.n = n; d.S = S; d.lda = lda;

@@ -88,26 +88,33 @@ struct PhaseTimer {
   }
 };
 
-// Device buffer with RAII (stream-agnostic cudaMalloc; sessions live across many launches).
+// Device buffer with RAII, carved from the device's stream-ordered memory pool on the context's
+// stream (cudaMallocAsync / cudaFreeAsync; the pool's release threshold is raised at context
+// creation, so in steady state neither call reaches the driver or synchronises the device - the
+// round loop allocates and frees scratch every round).  Everything the library launches runs on
+// that one stream, so a freed block may be handed to the next allocation without a fence.
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  cudaStream_t stream = nullptr;
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, stream);
     p = nullptr;
     bytes = 0;
   }
-  int alloc(size_t n) {
+  int alloc(basq_ctx* ctx, size_t n) {
     release();
     if (n == 0) n = 16;
-    cudaError_t e = cudaMalloc(&p, n);
+    stream = ctx->stream;
+    cudaError_t e = cudaMallocAsync(&p, n, stream);
     if (e != cudaSuccess) {
-      set_error("cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e));
+      set_error("cudaMallocAsync(%zu bytes) failed: %s", n, cudaGetErrorString(e));
       p = nullptr;
+      (void)cudaGetLastError();
       return BASQ_ERR_CUDA;
     }
     bytes = n;

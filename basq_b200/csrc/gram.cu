@@ -181,8 +181,8 @@ int gp_predict_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const KParams& 
   P = (P / 128) * 128;
   if (P > N) P = N;
   DevBuf V, Y;
-  BASQ_TRY(V.alloc(sizeof(double) * n_obs * P));
-  BASQ_TRY(Y.alloc(sizeof(double) * n_obs * P));
+  BASQ_TRY(V.alloc(ctx, sizeof(double) * n_obs * P));
+  BASQ_TRY(Y.alloc(ctx, sizeof(double) * n_obs * P));
   const size_t esz = desc->dtype == BASQ_F64 ? 8 : 4;
   for (int64_t p0 = 0; p0 < N; p0 += P) {
     const int64_t cnt = (N - p0 < P) ? N - p0 : P;
@@ -206,7 +206,7 @@ int warp_factor(basq_ctx* ctx, const basq_kernel_desc* desc, const KParams& kp, 
     return gp_predict_impl(ctx, desc, kp, lmobs, X, N, out, nullptr);
   if (desc->mode == BASQ_MMLT_G) {
     DevBuf var;
-    BASQ_TRY(var.alloc(sizeof(double) * N));
+    BASQ_TRY(var.alloc(ctx, sizeof(double) * N));
     BASQ_TRY(gp_predict_impl(ctx, desc, kp, lmobs, X, N, out, var.as<double>()));
     mmlt_factor_kernel<<<ceil_div(N, 256), 256, 0, ctx->stream>>>(out, var.as<double>(), N, out);
     ctx->launches++;

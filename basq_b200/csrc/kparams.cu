@@ -85,7 +85,7 @@ __global__ void column_mean_kernel(const T* __restrict__ Z, int64_t M, int d, do
 
 int compute_center(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, int64_t M, KParams* kp) {
   DevBuf tmp;
-  BASQ_TRY(tmp.alloc(sizeof(double) * BASQ_MAX_DIM));
+  BASQ_TRY(tmp.alloc(ctx, sizeof(double) * BASQ_MAX_DIM));
   if (desc->dtype == BASQ_F32)
     column_mean_kernel<float><<<desc->d, 256, 0, ctx->stream>>>((const float*)Z, M, desc->d, tmp.as<double>());
   else
@@ -138,8 +138,8 @@ int prep_landmarks(basq_ctx* ctx, const KParams& kp, int dtype, const void* Z0, 
   const void* src[2] = {Z0, Z1};
   const int64_t cnt[2] = {M0, M1};
   if (dtype == BASQ_F32) {
-    BASQ_TRY(out->zz.alloc(sizeof(float) * M * kp.dp));
-    BASQ_TRY(out->b.alloc(sizeof(float) * M));
+    BASQ_TRY(out->zz.alloc(ctx, sizeof(float) * M * kp.dp));
+    BASQ_TRY(out->b.alloc(ctx, sizeof(float) * M));
     int64_t row0 = 0;
     for (int s = 0; s < 2; ++s) {
       if (cnt[s] == 0) continue;
@@ -149,7 +149,7 @@ int prep_landmarks(basq_ctx* ctx, const KParams& kp, int dtype, const void* Z0, 
       row0 += cnt[s];
     }
   } else {
-    BASQ_TRY(out->zz.alloc(sizeof(double) * M * kp.dp));
+    BASQ_TRY(out->zz.alloc(ctx, sizeof(double) * M * kp.dp));
     int64_t row0 = 0;
     for (int s = 0; s < 2; ++s) {
       if (cnt[s] == 0) continue;

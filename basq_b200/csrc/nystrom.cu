@@ -375,23 +375,23 @@ int nystrom_basis(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, in
              8.0 * M * M / 1e9);
   BASQ_CHECK(niter >= 0 && niter <= 16, BASQ_ERR_INVALID, "nystrom: niter out of range");
   DevBuf K, Y, Y2;
-  BASQ_TRY(K.alloc(sizeof(double) * (size_t)M * M));
-  BASQ_TRY(Y.alloc(sizeof(double) * (size_t)M * q));
+  BASQ_TRY(K.alloc(ctx, sizeof(double) * (size_t)M * M));
+  BASQ_TRY(Y.alloc(ctx, sizeof(double) * (size_t)M * q));
   OrthWs ws;
-  BASQ_TRY(ws.gram.alloc(sizeof(double) * (size_t)q * q));
-  BASQ_TRY(ws.linv.alloc(sizeof(double) * (size_t)q * q));
-  BASQ_TRY(ws.tmp.alloc(sizeof(double) * (size_t)M * q));
-  BASQ_TRY(ws.prow.alloc(sizeof(double) * 4 * q));
-  BASQ_TRY(ws.prow2.alloc(sizeof(double) * 2 * (size_t)q * q));
-  BASQ_TRY(ws.flags.alloc(512));
+  BASQ_TRY(ws.gram.alloc(ctx, sizeof(double) * (size_t)q * q));
+  BASQ_TRY(ws.linv.alloc(ctx, sizeof(double) * (size_t)q * q));
+  BASQ_TRY(ws.tmp.alloc(ctx, sizeof(double) * (size_t)M * q));
+  BASQ_TRY(ws.prow.alloc(ctx, sizeof(double) * 4 * q));
+  BASQ_TRY(ws.prow2.alloc(ctx, sizeof(double) * 2 * (size_t)q * q));
+  BASQ_TRY(ws.flags.alloc(ctx, 512));
   BASQ_CUDA(cudaMemsetAsync(ws.flags.p, 0, 512, ctx->stream));
-  BASQ_TRY(ws.scal.alloc(64));
+  BASQ_TRY(ws.scal.alloc(ctx, 64));
   BASQ_TRY(basq_gram(ctx, desc, Z, M, Z, M, K.as<double>()));
 
   const int Mi = (int)M;
   BASQ_TRY(dgemm(ctx, false, false, Mi, q, Mi, 1.0, K.as<double>(), M, Omega, q, 0.0, Y.as<double>(), q));
   BASQ_TRY(orthonormalise(ctx, ws, Y.as<double>(), M, q, niter > 0 ? 2 : 3));
-  BASQ_TRY(Y2.alloc(sizeof(double) * (size_t)M * q));
+  BASQ_TRY(Y2.alloc(ctx, sizeof(double) * (size_t)M * q));
   for (int it = 0; it < niter; ++it) {
     BASQ_TRY(dgemm(ctx, true, false, Mi, q, Mi, 1.0, K.as<double>(), M, Y.as<double>(), q, 0.0, Y2.as<double>(), q));
     BASQ_TRY(orthonormalise(ctx, ws, Y2.as<double>(), M, q, 2));

@@ -113,18 +113,18 @@ int build_records(basq_ctx* ctx, const KParams& kp, int dtype, const void* X, in
   pool->cur = 0;
   pool->count = 0;
   pool->capacity = N;
-  BASQ_TRY(pool->buf[0].alloc((size_t)(N + 1) * pool->rec_bytes));
+  BASQ_TRY(pool->buf[0].alloc(ctx, (size_t)(N + 1) * pool->rec_bytes));
   // the second buffer only ever receives the survivors of a round (about half), but the first
   // round of a weighted run may keep more: size it for the worst case of one halving round + 1.
-  BASQ_TRY(pool->buf[1].alloc((size_t)(N + 1) * pool->rec_bytes));
+  BASQ_TRY(pool->buf[1].alloc(ctx, (size_t)(N + 1) * pool->rec_bytes));
   if (N == 0) return BASQ_OK;
   const int nb = ceil_div(N, 256);
   DevBuf counts, offs, total;
   int64_t kept = N;
   if (mu) {
-    BASQ_TRY(counts.alloc(sizeof(int) * nb));
-    BASQ_TRY(offs.alloc(sizeof(int64_t) * nb));
-    BASQ_TRY(total.alloc(sizeof(int64_t)));
+    BASQ_TRY(counts.alloc(ctx, sizeof(int) * nb));
+    BASQ_TRY(offs.alloc(ctx, sizeof(int64_t) * nb));
+    BASQ_TRY(total.alloc(ctx, sizeof(int64_t)));
     count_kept_kernel<<<nb, 256, 0, ctx->stream>>>(mu, N, counts.as<int>());
     scan_counts_kernel<<<1, 1024, 0, ctx->stream>>>(counts.as<int>(), nb, offs.as<int64_t>(), total.as<int64_t>());
     ctx->launches += 2;

@@ -48,10 +48,11 @@ def gp_predict(kernel, X, space=0, want_var=True, device=None):
     return mean, var
 
 
-def nystrom_basis(kernel, Z, q, omega=None, niter=2, device=None):
+def nystrom_basis(kernel, Z, q, omega=None, niter=2, device=None, want_S=True):
     """(S, U): Ritz values and an orthonormal basis U [q, M] of the randomised range of K(Z, Z)
     (ker_svd_sparsify, BASQ/_rchq.py:28-31).  omega [M, q] defaults to torch.randn on the device,
-    consuming torch's global RNG exactly where torch.svd_lowrank would."""
+    consuming torch's global RNG exactly where torch.svd_lowrank would.  want_S=False skips the
+    Ritz values (the reference discards them, BASQ/_rchq.py:36) and returns S = None."""
     spec, ctx, device, dtype = _common(kernel, Z, device)
     Zd = _prep(Z, device, dtype)
     M = len(Zd)
@@ -60,9 +61,9 @@ def nystrom_basis(kernel, Z, q, omega=None, niter=2, device=None):
     omega = _prep(omega, device, torch.float64)
     desc, keep = spec.to_desc(Zd.shape[1], device, dtype)
     U = torch.empty(q, M, dtype=torch.float64, device=device)
-    S = torch.empty(q, dtype=torch.float64, device=device)
+    S = torch.empty(q, dtype=torch.float64, device=device) if want_S else None
     _lib.check(_lib.lib.basq_nystrom_basis(ctx.handle, C.byref(desc), Zd.data_ptr(), M, int(q), omega.data_ptr(),
-                                           int(niter), U.data_ptr(), S.data_ptr()))
+                                           int(niter), U.data_ptr(), S.data_ptr() if want_S else None))
     return S, U
 
 

@@ -187,7 +187,7 @@ def run_ours(a, rank, world, local_rank):
     Omega = torch.randn(a.M, q, generator=gO, device=dev, dtype=torch.float64)
 
     def step_device():
-        _, U = ops.nystrom_basis(kern, Z, q, omega=Omega)
+        _, U = ops.nystrom_basis(kern, Z, q, omega=Omega, want_S=False)
         if world == 1:
             return ops.recombine(kern, X, Z, U)
         return sharded.recombination_sharded(X, Z, a.n, kern, N_glob, rank * N_loc, U)
@@ -205,7 +205,7 @@ def run_ours(a, rank, world, local_rank):
         Xd = X_host.to(dev, non_blocking=True)
         Zd = Z_host.to(dev, non_blocking=True)
         Od = Om_host.to(dev, non_blocking=True)
-        _, U = ops.nystrom_basis(kern, Zd, q, omega=Od)
+        _, U = ops.nystrom_basis(kern, Zd, q, omega=Od, want_S=False)
         idx, w = sharded.recombination_sharded(Xd, Zd, a.n, kern, N_glob, rank * N_loc, U)
         return idx.cpu(), w.cpu()
 
