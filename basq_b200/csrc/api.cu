@@ -373,6 +373,7 @@ int basq_ctx_create(int device, void* stream, basq_ctx** out) {
   }
   { const char* t = getenv("BASQ_TRACE"); c->trace = t && t[0] == '1'; }
   { const char* t = getenv("BASQ_CAR_GENERAL"); c->force_general_car = t && t[0] == '1'; }
+  { const char* t = getenv("BASQ_SETSUM_SCALAR"); c->scalar_setsum = t && t[0] == '1'; }
   cudaEventCreate(&c->ev0);
   cudaEventCreate(&c->ev1);
   *out = c;

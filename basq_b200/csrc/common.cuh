@@ -57,6 +57,7 @@ struct basq_ctx {
   bool profile = false;
   int timer_depth = 0;
   bool force_general_car = false;  // BASQ_CAR_GENERAL=1: always use the global-memory kernel (tests)
+  bool scalar_setsum = false;      // BASQ_SETSUM_SCALAR=1: CUDA-core set-sum kernel for fp32 too (A/B timing)
   bool trace = false;      // BASQ_TRACE=1: wall-clock trace points on stderr (synchronising)
   double trace_t0 = 0.0;
   double phase_ms[basq::PH_COUNT] = {0};
@@ -265,6 +266,7 @@ __device__ __forceinline__ double nl_apply(int nl, double c, double sz, double s
 struct LmView {
   const void* zz = nullptr;  // f32: [count, dp] floats (2z' / -2z') ; f64: [count, dp] doubles (z')
   const float* b = nullptr;  // f32: [count] floats
+  const float* lmA = nullptr;  // f32, whole-set views only: tile-blocked tensor-core operand (setsum_mma.cuh)
   int count = 0;
   int dp = 0;
   int dtype = BASQ_F32;
@@ -276,9 +278,11 @@ struct Landmarks {
   int dtype = BASQ_F32;
   DevBuf zz;
   DevBuf b;
+  DevBuf lmA;
   LmView view(int first = 0, int cnt = -1) const {
     LmView v;
     if (cnt < 0) cnt = count - first;
+    if (first == 0 && cnt == count && dtype == BASQ_F32) v.lmA = lmA.as<float>();
     const size_t esz = dtype == BASQ_F32 ? 4 : 8;
     v.zz = (const unsigned char*)zz.p + (size_t)first * dp * esz;
     v.b = dtype == BASQ_F32 ? b.as<float>() + first : nullptr;

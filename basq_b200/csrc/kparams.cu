@@ -6,6 +6,7 @@
 
 #include "common.cuh"
 #include "prep.cuh"
+#include "setsum_mma.cuh"
 
 namespace basq {
 
@@ -148,6 +149,9 @@ int prep_landmarks(basq_ctx* ctx, const KParams& kp, int dtype, const void* Z0, 
       ctx->launches++;
       row0 += cnt[s];
     }
+    BASQ_CUDA(cudaGetLastError());
+    BASQ_TRY(out->lmA.alloc(ctx, sizeof(float) * lmA_floats(kp.dp, (int)M)));
+    BASQ_TRY(build_lmA(ctx, kp.dp, out->zz.as<float>(), out->b.as<float>(), (int)M, out->lmA.as<float>()));
   } else {
     BASQ_TRY(out->zz.alloc(ctx, sizeof(double) * M * kp.dp));
     int64_t row0 = 0;

@@ -1,5 +1,6 @@
 // Host-side dispatch of the set-sum kernel (see setsum_impl.cuh).
 #include "setsum_impl.cuh"
+#include "setsum_mma.cuh"
 
 namespace basq {
 
@@ -31,6 +32,28 @@ int set_sums(basq_ctx* ctx, const KParams& kp, const SetSumArgs& a) {
   dev.G = a.G;
   dev.ldg = a.ldg;
   dev.accumulate = a.accumulate ? 1 : 0;
+  if (pool.dtype == BASQ_F32 && a.nl == NL_LIN && lm.lmA != nullptr && !ctx->scalar_setsum) {
+    // fp32 linear modes: argument tiles on the tensor cores (setsum_mma.cuh)
+    SetSumMmaDev md;
+    md.recs = dev.recs;
+    md.count = dev.count;
+    md.off = dev.off;
+    md.S = dev.S;
+    md.p_lo = dev.p_lo;
+    md.p_hi = dev.p_hi;
+    md.lmA = lm.lmA;
+    md.Mtot = lm.count;
+    md.n_mgroups = md.n_jgroups = 0;
+    md.os_f = kp.os_f;
+    md.G = dev.G;
+    md.ldg = dev.ldg;
+    md.accumulate = dev.accumulate;
+    switch (kp.family) {
+      case BASQ_RBF: return launch_setsum_mma_rbf(ctx, kp.dp, md);
+      case BASQ_MATERN15: return launch_setsum_mma_m15(ctx, kp.dp, md);
+      default: return launch_setsum_mma_m25(ctx, kp.dp, md);
+    }
+  }
   if (pool.dtype == BASQ_F32) {
     switch (kp.family) {
       case BASQ_RBF: return launch_setsum_f32_rbf(ctx, kp.dp, dev);

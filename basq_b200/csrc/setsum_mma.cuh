@@ -1,0 +1,506 @@
+// Weighted set sums of Gram columns on the 5th-generation tensor cores (fp32 data, linear modes).
+//
+//   G[m, j] (+)= sum over local points p with (off + p) mod S == j of  w_p * k(z_m, x_p)
+//
+// The exponent argument of every kernel family is bilinear in prepared operands,
+//   arg(m, p) = a_p + b_m + sum_i x'_{p,i} zz_{m,i}        (see common.cuh: KParams),
+// so a 128-landmark x NT-point tile of arguments is ONE small GEMM with K = 3 DP + 6:
+//   * x' and zz are split into tf32 "hi + lo" parts and the three significant cross products
+//     (hi hi, lo hi, hi lo) occupy three K columns per dimension (3xTF32: ~2^-21 relative);
+//   * a_p and b_m ride along as three tf32 pieces each against constant-one columns.
+// tcgen05.mma (kind::tf32, M = 128, N = NT, operands K-major in shared memory, no swizzle) writes the
+// argument tile into TMEM; the epilogue warps read it back with tcgen05.ld, apply exp2 / the Matern
+// polynomial on the MUFU/FMA pipes and accumulate w_p * k in fp64 - one accumulator per (landmark,
+// set).  What remains on the CUDA cores per pair is 1 MUFU + 2 integer ops + 1 DFMA; the DP-long
+// FFMA chain of the scalar kernel moved to the tensor pipe.
+//
+// CTA = 13 warps, one CTA per SM, persistent over work items (MT landmark tiles x JT sets):
+//   warps 0-7   epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31 (one landmark per thread) and
+//               column half w / 4 of every accumulator buffer
+//   warps 8-11  producers: candidate records (HBM/L2) -> hi/lo split -> K-major B stage in smem
+//   warp  12    TMEM allocation, landmark (A) tile bulk copies, tcgen05.mma issue (one lane)
+// Pipelines (mbarriers): B stages full/empty (3-deep ring), TMEM accumulators full/empty (2 buffers),
+// A tiles full/empty.
+#pragma once
+#include "common.cuh"
+
+namespace basq {
+
+struct SetSumMmaDev {
+  const unsigned char* recs;
+  int64_t count;
+  int64_t off;
+  int S;
+  int64_t p_lo, p_hi;
+  const float* lmA;  // [n_mtiles_alloc][KA/4][128][4] landmark operand, tile-blocked
+  int Mtot;
+  int n_mgroups;     // ceil(Mtot / (MT * 128))
+  int n_jgroups;     // ceil(S / JT)
+  float os_f;
+  double* G;
+  int64_t ldg;
+  int accumulate;
+};
+
+template <int DP>
+struct MmaCfg {
+  static constexpr int KA = (3 * DP + 6 + 7) / 8 * 8;  // K columns (multiple of the tf32 MMA K = 8)
+  static constexpr int NT = KA <= 40 ? 256 : 128;      // points per tile (MMA N)
+  static constexpr int MT = KA > 80 ? 1 : 2;           // landmark tiles (of 128) per work item
+  static constexpr int JT = 8;                         // sets per work item
+  static constexpr int EC = NT / JT;                   // set members per tile
+  static constexpr int NSTAGE = 3;
+  static constexpr int RB = ((24 + 4 * DP) + 15) / 16 * 16;  // record bytes (rec_bytes_f32)
+  static constexpr int A_TILE_BYTES = KA * 128 * 4;
+  static constexpr int B_STAGE_BYTES = KA * NT * 4;
+  static constexpr int W_STAGE_BYTES = NT * 8;
+  static constexpr int COMB_BYTES = MT * 128 * JT * 8;
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_B = OFF_A + MT * A_TILE_BYTES;
+  static constexpr int OFF_W = OFF_B + NSTAGE * B_STAGE_BYTES;
+  static constexpr int OFF_COMB = OFF_W + NSTAGE * W_STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_COMB + COMB_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256;
+  static constexpr int TMEM_COLS = 2 * NT;             // two accumulator buffers (256 or 512)
+  static constexpr int EPI_WARPS = 8, PROD_WARPS = 4;
+  static constexpr int THREADS = (EPI_WARPS + PROD_WARPS + 1) * 32;
+};
+
+namespace mma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major operand without swizzle, stored as [K / 4][rows][4 floats]: 8-row core matrices are
+// contiguous (SBO = 128 B), the next 16-byte K chunk lies one plane further (LBO = rows * 16 B).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// the three tf32 pieces of an fp32 value (sum reproduces it to ~2^-33 relative)
+__device__ __forceinline__ void split3(float v, float& p1, float& p2, float& p3) {
+  p1 = tf32_rna(v);
+  const float r = __fsub_rn(v, p1);
+  p2 = tf32_rna(r);
+  p3 = tf32_rna(__fsub_rn(r, p2));
+}
+
+}  // namespace mma
+
+// ---------------------------------------------------------------------------------------------
+// landmark operand: lmA[tile][kc][row][4] from the prepared zz [Mtot, DP] / b [Mtot]
+//   K column 3i   : zz_hi_i   (x hi)      3i+1 : zz_hi_i  (x lo)      3i+2 : zz_lo_i  (x hi)
+//   3DP .. 3DP+2  : 1 (a pieces)          3DP+3 .. 3DP+5 : b pieces (x 1)      rest : 0
+// ---------------------------------------------------------------------------------------------
+template <int DP>
+__global__ void build_lmA_kernel(const float* __restrict__ zz, const float* __restrict__ bz, int Mtot, int n_tiles,
+                                 float* __restrict__ lmA) {
+  using Cfg = MmaCfg<DP>;
+  constexpr int KA = Cfg::KA;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_tiles * 128) return;
+  float vals[KA];
+#pragma unroll
+  for (int k = 0; k < KA; ++k) vals[k] = 0.f;
+  if (m < Mtot) {
+#pragma unroll
+    for (int i = 0; i < DP; ++i) {
+      const float z = zz[(int64_t)m * DP + i];
+      const float zh = mma::tf32_rna(z);
+      const float zl = mma::tf32_rna(__fsub_rn(z, zh));
+      vals[3 * i] = zh;
+      vals[3 * i + 1] = zh;
+      vals[3 * i + 2] = zl;
+    }
+    vals[3 * DP] = vals[3 * DP + 1] = vals[3 * DP + 2] = 1.f;
+    mma::split3(bz[m], vals[3 * DP + 3], vals[3 * DP + 4], vals[3 * DP + 5]);
+  }
+  const int tile = m >> 7, row = m & 127;
+  float4* dst = reinterpret_cast<float4*>(lmA) + (int64_t)tile * (KA / 4) * 128 + row;
+#pragma unroll
+  for (int kc = 0; kc < KA / 4; ++kc)
+    dst[kc * 128] = make_float4(vals[4 * kc], vals[4 * kc + 1], vals[4 * kc + 2], vals[4 * kc + 3]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int FAM, int DP>
+__global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(const SetSumMmaDev a) {
+  using Cfg = MmaCfg<DP>;
+  constexpr int KA = Cfg::KA, NT = Cfg::NT, MT = Cfg::MT, JT = Cfg::JT, EC = Cfg::EC, NSTAGE = Cfg::NSTAGE,
+                RB = Cfg::RB;
+  extern __shared__ __align__(1024) unsigned char smem_mma[];
+  unsigned char* const smem = smem_mma;
+  unsigned char* sA = smem + Cfg::OFF_A;
+  unsigned char* sB = smem + Cfg::OFF_B;
+  double* sW = reinterpret_cast<double*>(smem + Cfg::OFF_W);
+  double* sComb = reinterpret_cast<double*>(smem + Cfg::OFF_COMB);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* b_full = bars;               // [NSTAGE]
+  uint64_t* b_empty = bars + NSTAGE;     // [NSTAGE]
+  uint64_t* t_full = bars + 2 * NSTAGE;  // [2]
+  uint64_t* t_empty = t_full + 2;        // [2]
+  uint64_t* a_full = t_empty + 2;        // [1]
+  uint64_t* a_empty = a_full + 1;        // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mma::mbar_init(&b_full[s], Cfg::PROD_WARPS * 32);
+      mma::mbar_init(&b_empty[s], 1 + Cfg::EPI_WARPS);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mma::mbar_init(&t_full[b], 1);
+      mma::mbar_init(&t_empty[b], Cfg::EPI_WARPS);
+    }
+    mma::mbar_init(a_full, 1);
+    mma::mbar_init(a_empty, 1);
+    mma::fence_barrier_init();
+  }
+  if (warp == Cfg::EPI_WARPS + Cfg::PROD_WARPS) mma::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  mma::tc_fence_before();
+  __syncthreads();
+  mma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t S = a.S;
+  const int n_items = a.n_mgroups * a.n_jgroups;
+
+  // member range [e_lo, e_hi) of the JT sets starting at j0 that falls into [p_lo, p_hi)
+  auto item_range = [&](int j0, int64_t& e_lo, int64_t& n_tiles) {
+    const int64_t num_lo = a.p_lo + a.off - (int64_t)(j0 + JT - 1);
+    e_lo = num_lo <= 0 ? 0 : (num_lo + S - 1) / S;
+    const int64_t num_hi = a.p_hi - 1 + a.off - (int64_t)j0;
+    const int64_t e_hi = num_hi < 0 ? 0 : num_hi / S + 1;
+    const int64_t n_e = e_hi > e_lo ? e_hi - e_lo : 0;
+    n_tiles = (n_e + EC - 1) / EC;
+  };
+
+  if (warp < Cfg::EPI_WARPS) {
+    // ======================================================================== epilogue
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;
+    constexpr int HALF_COLS = NT / 2;
+    uint32_t it = 0, tc = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int mg = item % a.n_mgroups, jg = item / a.n_mgroups;
+      const int j0 = jg * JT;
+      int64_t e_lo, n_tiles;
+      item_range(j0, e_lo, n_tiles);
+      double acc[MT][JT];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int jj = 0; jj < JT; ++jj) acc[mt][jj] = 0.0;
+      for (int64_t t = 0; t < n_tiles; ++t, ++it) {
+        const int stage = it % NSTAGE;
+        const double* wst = sW + stage * NT + half * HALF_COLS;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt, ++tc) {
+          const uint32_t buf = tc & 1u;
+          mma::mbar_wait(&t_full[buf], (tc >> 1) & 1u);
+          mma::tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * NT + half * HALF_COLS;
+#pragma unroll 1
+          for (int cb = 0; cb < HALF_COLS; cb += 32) {
+            uint32_t v[32];
+            mma::tmem_ld32(taddr + cb, v);
+            mma::tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+              const double2 w2 = *reinterpret_cast<const double2*>(wst + cb + c);
+              const float k0 = finish_f32(FAM, __uint_as_float(v[c]), a.os_f);
+              const float k1 = finish_f32(FAM, __uint_as_float(v[c + 1]), a.os_f);
+              acc[mt][c % JT] = fma(f2d_pos(k0), w2.x, acc[mt][c % JT]);
+              acc[mt][(c + 1) % JT] = fma(f2d_pos(k1), w2.y, acc[mt][(c + 1) % JT]);
+            }
+          }
+          mma::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mma::mbar_arrive(&t_empty[buf]);
+        }
+        // the weights of this stage have been consumed by this warp
+        __syncwarp();
+        if (lane == 0) mma::mbar_arrive(&b_empty[stage]);
+      }
+      // ---- combine the two column halves and write G
+      if (half == 1) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int jj = 0; jj < JT; ++jj) sComb[(mt * 128 + row) * JT + jj] = acc[mt][jj];
+      }
+      mma::named_bar_sync(1, Cfg::EPI_WARPS * 32);
+      if (half == 0) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int m = (mg * MT + mt) * 128 + row;
+          if (m < a.Mtot) {
+#pragma unroll
+            for (int jj = 0; jj < JT; ++jj) {
+              const int j = j0 + jj;
+              if (j < a.S) {
+                const double v = acc[mt][jj] + sComb[(mt * 128 + row) * JT + jj];
+                double* dst = a.G + (int64_t)m * a.ldg + j;
+                *dst = a.accumulate ? (*dst + v) : v;
+              }
+            }
+          }
+        }
+      }
+      mma::named_bar_sync(1, Cfg::EPI_WARPS * 32);
+    }
+  } else if (warp < Cfg::EPI_WARPS + Cfg::PROD_WARPS) {
+    // ======================================================================== producers
+    const int ptid = tid - Cfg::EPI_WARPS * 32;
+    constexpr int NPROD = Cfg::PROD_WARPS * 32;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int jg = item / a.n_mgroups;
+      const int j0 = jg * JT;
+      int64_t e_lo, n_tiles;
+      item_range(j0, e_lo, n_tiles);
+      for (int64_t t = 0; t < n_tiles; ++t, ++it) {
+        const int stage = it % NSTAGE;
+        mma::mbar_wait(&b_empty[stage], ((it / NSTAGE) & 1u) ^ 1u);
+        float4* bst = reinterpret_cast<float4*>(sB + (size_t)stage * Cfg::B_STAGE_BYTES);
+        double* wst = sW + stage * NT;
+#pragma unroll
+        for (int c = ptid; c < NT; c += NPROD) {
+          const int ei = c / JT, jj = c % JT;
+          const int64_t e = e_lo + t * EC + ei;
+          const int64_t p = (int64_t)(j0 + jj) + e * S - a.off;
+          const bool ok = (j0 + jj < a.S) && (p >= a.p_lo) && (p < a.p_hi);
+          float vals[KA];
+#pragma unroll
+          for (int k = 0; k < KA; ++k) vals[k] = 0.f;
+          double w = 0.0;
+          if (ok) {
+            const uint4* rec = reinterpret_cast<const uint4*>(a.recs + p * RB);
+            constexpr int NV = RB / 16;
+            uint4 q[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) q[v] = __ldg(rec + v);
+            w = __hiloint2double((int)q[0].y, (int)q[0].x);
+            float f[(NV - 1) * 4];  // [idx, a, x0, x1, ...]
+#pragma unroll
+            for (int v = 1; v < NV; ++v) {
+              f[(v - 1) * 4 + 0] = __uint_as_float(q[v].x);
+              f[(v - 1) * 4 + 1] = __uint_as_float(q[v].y);
+              f[(v - 1) * 4 + 2] = __uint_as_float(q[v].z);
+              f[(v - 1) * 4 + 3] = __uint_as_float(q[v].w);
+            }
+#pragma unroll
+            for (int i = 0; i < DP; ++i) {
+              const float x = f[2 + i];
+              const float xh = mma::tf32_rna(x);
+              const float xl = mma::tf32_rna(__fsub_rn(x, xh));
+              vals[3 * i] = xh;
+              vals[3 * i + 1] = xl;
+              vals[3 * i + 2] = xh;
+            }
+            mma::split3(f[1], vals[3 * DP], vals[3 * DP + 1], vals[3 * DP + 2]);
+            vals[3 * DP + 3] = vals[3 * DP + 4] = vals[3 * DP + 5] = 1.f;
+          }
+#pragma unroll
+          for (int kc = 0; kc < KA / 4; ++kc)
+            bst[kc * NT + c] = make_float4(vals[4 * kc], vals[4 * kc + 1], vals[4 * kc + 2], vals[4 * kc + 3]);
+          wst[c] = w;
+        }
+        mma::fence_proxy_async();
+        mma::mbar_arrive(&b_full[stage]);
+      }
+    }
+  } else {
+    // ======================================================================== MMA issuer
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+    uint32_t it = 0, tc = 0, ac = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int mg = item % a.n_mgroups, jg = item / a.n_mgroups;
+      int64_t e_lo, n_tiles;
+      item_range(jg * JT, e_lo, n_tiles);
+      if (n_tiles == 0) continue;
+      // landmark tiles of this item: wait until the previous item's MMAs released the buffer
+      if (ac > 0) mma::mbar_wait(a_empty, (ac - 1) & 1u);
+      if (lane == 0) {
+        mma::mbar_expect_tx(a_full, MT * Cfg::A_TILE_BYTES);
+        mma::bulk_g2s(sA, a.lmA + (size_t)mg * MT * (Cfg::A_TILE_BYTES / 4), MT * Cfg::A_TILE_BYTES, a_full);
+      }
+      mma::mbar_wait(a_full, ac & 1u);
+      ++ac;
+      for (int64_t t = 0; t < n_tiles; ++t, ++it) {
+        const int stage = it % NSTAGE;
+        mma::mbar_wait(&b_full[stage], (it / NSTAGE) & 1u);
+        mma::tc_fence_after();
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt, ++tc) {
+          const uint32_t buf = tc & 1u;
+          mma::mbar_wait(&t_empty[buf], ((tc >> 1) & 1u) ^ 1u);
+          mma::tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_base = mma::smem_u32(sA + mt * Cfg::A_TILE_BYTES);
+            const uint32_t b_base = mma::smem_u32(sB + (size_t)stage * Cfg::B_STAGE_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < KA / 8; ++ks) {
+              const uint64_t ad = mma::smem_desc(a_base + ks * 2 * (128 * 16), 128 * 16, 128);
+              const uint64_t bd = mma::smem_desc(b_base + ks * 2 * (NT * 16), NT * 16, 128);
+              mma::umma_tf32(tmem_base + buf * NT, ad, bd, IDESC, ks > 0 ? 1u : 0u);
+            }
+            mma::umma_commit(&t_full[buf]);
+          }
+          __syncwarp();
+        }
+        if (lane == 0) mma::umma_commit(&b_empty[stage]);
+        __syncwarp();
+      }
+      if (lane == 0) mma::umma_commit(a_empty);
+      __syncwarp();
+    }
+  }
+
+  mma::tc_fence_before();
+  __syncthreads();
+  if (warp == Cfg::EPI_WARPS + Cfg::PROD_WARPS) {
+    mma::tc_fence_after();
+    mma::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int FAM, int DP>
+int launch_setsum_mma_dp(basq_ctx* ctx, SetSumMmaDev dev) {
+  using Cfg = MmaCfg<DP>;
+  dev.n_mgroups = ceil_div(dev.Mtot, Cfg::MT * 128);
+  dev.n_jgroups = ceil_div(dev.S, Cfg::JT);
+  const int64_t n_items = (int64_t)dev.n_mgroups * dev.n_jgroups;
+  BASQ_CHECK(n_items < (1ll << 31), BASQ_ERR_UNSUPPORTED, "set_sums: too many work items");
+  BASQ_CHECK((size_t)Cfg::SMEM_BYTES <= ctx->smem_optin, BASQ_ERR_UNSUPPORTED,
+             "set_sums: kernel needs %d B shared memory (limit %zu)", Cfg::SMEM_BYTES, ctx->smem_optin);
+  BASQ_CUDA(cudaFuncSetAttribute(setsum_mma_kernel<FAM, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::SMEM_BYTES));
+  const int grid = (int)std::min<int64_t>(ctx->num_sms, n_items);
+  setsum_mma_kernel<FAM, DP><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(dev);
+  ctx->launches++;
+  BASQ_CUDA(cudaGetLastError());
+  return BASQ_OK;
+}
+
+template <int FAM>
+int launch_setsum_mma_family(basq_ctx* ctx, int dp, const SetSumMmaDev& dev) {
+  switch (dp) {
+    case 2: return launch_setsum_mma_dp<FAM, 2>(ctx, dev);
+    case 4: return launch_setsum_mma_dp<FAM, 4>(ctx, dev);
+    case 6: return launch_setsum_mma_dp<FAM, 6>(ctx, dev);
+    case 8: return launch_setsum_mma_dp<FAM, 8>(ctx, dev);
+    case 10: return launch_setsum_mma_dp<FAM, 10>(ctx, dev);
+    case 12: return launch_setsum_mma_dp<FAM, 12>(ctx, dev);
+    case 16: return launch_setsum_mma_dp<FAM, 16>(ctx, dev);
+    case 20: return launch_setsum_mma_dp<FAM, 20>(ctx, dev);
+    case 24: return launch_setsum_mma_dp<FAM, 24>(ctx, dev);
+    case 32: return launch_setsum_mma_dp<FAM, 32>(ctx, dev);
+  }
+  set_error("set_sums: no tensor-core kernel compiled for padded dimension %d", dp);
+  return BASQ_ERR_UNSUPPORTED;
+}
+
+template <int DP>
+int launch_build_lmA_dp(basq_ctx* ctx, const float* zz, const float* bz, int Mtot, int n_tiles, float* lmA) {
+  build_lmA_kernel<DP><<<ceil_div((int64_t)n_tiles * 128, 128), 128, 0, ctx->stream>>>(zz, bz, Mtot, n_tiles, lmA);
+  ctx->launches++;
+  BASQ_CUDA(cudaGetLastError());
+  return BASQ_OK;
+}
+
+// one definition per translation unit (setsum_mma_*.cu)
+int launch_setsum_mma_rbf(basq_ctx*, int, const SetSumMmaDev&);
+int launch_setsum_mma_m15(basq_ctx*, int, const SetSumMmaDev&);
+int launch_setsum_mma_m25(basq_ctx*, int, const SetSumMmaDev&);
+// allocation size (floats) and tile count of the landmark operand for `count` landmarks
+int lmA_tiles(int dp, int count);
+size_t lmA_floats(int dp, int count);
+int build_lmA(basq_ctx* ctx, int dp, const float* zz, const float* bz, int Mtot, float* lmA);
+
+}  // namespace basq
