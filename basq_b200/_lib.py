@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbasq_b200.so")
+LIB_PATH = os.environ.get("BASQ_B200_LIB") or os.path.join(_HERE, "libbasq_b200.so")  # override: A/B builds
 
 BASQ_MAX_DIM = 32
 OK, ERR_INVALID, ERR_CUDA, ERR_NUMERIC, ERR_UNSUPPORTED = range(5)
@@ -95,7 +95,7 @@ class Context:
 
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None
-        if h:
+        if h and lib is not None:          # lib is None while the interpreter shuts down
             lib.basq_ctx_destroy(h)
 
     @property

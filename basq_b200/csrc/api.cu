@@ -374,16 +374,14 @@ int basq_ctx_create(int device, void* stream, basq_ctx** out) {
   { const char* t = getenv("BASQ_TRACE"); c->trace = t && t[0] == '1'; }
   { const char* t = getenv("BASQ_CAR_GENERAL"); c->force_general_car = t && t[0] == '1'; }
   { const char* t = getenv("BASQ_SETSUM_SCALAR"); c->scalar_setsum = t && t[0] == '1'; }
-  cudaEventCreate(&c->ev0);
-  cudaEventCreate(&c->ev1);
   *out = c;
   return BASQ_OK;
 }
 
 void basq_ctx_destroy(basq_ctx* ctx) {
   if (!ctx) return;
-  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  ctx->resolve_spans();
+  for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
   delete ctx;
 }
 
@@ -392,12 +390,14 @@ int64_t basq_ctx_pair_evals(const basq_ctx* ctx) { return ctx ? ctx->pair_evals 
 
 int basq_ctx_profile(basq_ctx* ctx, int enable) {
   BASQ_CHECK(ctx, BASQ_ERR_INVALID, "ctx is NULL");
+  if (!enable) ctx->resolve_spans();
   ctx->profile = enable != 0;
   return BASQ_OK;
 }
 
 int basq_ctx_profile_read(basq_ctx* ctx, double* ms_host, int64_t* calls_host, int reset) {
   BASQ_CHECK(ctx && ms_host, BASQ_ERR_INVALID, "NULL argument");
+  ctx->resolve_spans();
   for (int i = 0; i < PH_COUNT; ++i) {
     ms_host[i] = ctx->phase_ms[i];
     if (calls_host) calls_host[i] = ctx->phase_calls[i];

@@ -62,29 +62,57 @@ struct basq_ctx {
   double trace_t0 = 0.0;
   double phase_ms[basq::PH_COUNT] = {0};
   int64_t phase_calls[basq::PH_COUNT] = {0};
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // phase spans recorded since the last read: (phase, start event, stop event); events come from a
+  // free list so that profiling never synchronises inside the timed region
+  struct Span { int phase; cudaEvent_t e0, e1; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> free_events;
+  cudaEvent_t take_event() {
+    if (!free_events.empty()) { cudaEvent_t e = free_events.back(); free_events.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+  // fold finished spans into phase_ms / phase_calls (synchronises the stream)
+  void resolve_spans() {
+    if (spans.empty()) return;
+    cudaStreamSynchronize(stream);
+    for (const Span& s : spans) {
+      float ms = 0.f;
+      if (s.e0 && s.e1 && cudaEventElapsedTime(&ms, s.e0, s.e1) == cudaSuccess) {
+        phase_ms[s.phase] += ms;
+        phase_calls[s.phase] += 1;
+      }
+      if (s.e0) free_events.push_back(s.e0);
+      if (s.e1) free_events.push_back(s.e1);
+    }
+    spans.clear();
+    (void)cudaGetLastError();
+  }
 };
 
 namespace basq {
 
-// RAII phase timer (only active when ctx->profile).
+// RAII phase timer (only active when ctx->profile): records a start/stop event pair on the context's
+// stream without synchronising; basq_ctx_profile_read resolves them.  Nested timers are ignored.
 struct PhaseTimer {
   basq_ctx* ctx;
   int phase;
-  bool outer;
+  bool active;
+  cudaEvent_t e0 = nullptr;
   PhaseTimer(basq_ctx* c, int ph) : ctx(c), phase(ph) {
-    outer = (ctx->timer_depth++ == 0);
-    if (ctx->profile && outer) cudaEventRecord(ctx->ev0, ctx->stream);
+    active = (ctx->timer_depth++ == 0) && ctx->profile;
+    if (active) {
+      e0 = ctx->take_event();
+      cudaEventRecord(e0, ctx->stream);
+    }
   }
   ~PhaseTimer() {
     ctx->timer_depth--;
-    if (ctx->profile && outer) {
-      cudaEventRecord(ctx->ev1, ctx->stream);
-      cudaEventSynchronize(ctx->ev1);
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-      ctx->phase_ms[phase] += ms;
-      ctx->phase_calls[phase] += 1;
+    if (active) {
+      cudaEvent_t e1 = ctx->take_event();
+      cudaEventRecord(e1, ctx->stream);
+      ctx->spans.push_back({phase, e0, e1});
     }
   }
 };

@@ -14,11 +14,12 @@
 // set).  What remains on the CUDA cores per pair is 1 MUFU + 2 integer ops + 1 DFMA; the DP-long
 // FFMA chain of the scalar kernel moved to the tensor pipe.
 //
-// CTA = 13 warps, one CTA per SM, persistent over work items (MT landmark tiles x JT sets):
-//   warps 0-7   epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31 (one landmark per thread) and
-//               column half w / 4 of every accumulator buffer
-//   warps 8-11  producers: candidate records (HBM/L2) -> hi/lo split -> K-major B stage in smem
-//   warp  12    TMEM allocation, landmark (A) tile bulk copies, tcgen05.mma issue (one lane)
+// CTA = 21 warps, one CTA per SM, persistent over work items (MT landmark tiles x JT sets):
+//   warps 0-15  epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31 (one landmark per thread) and
+//               column part w / 4 of every accumulator buffer (4 warps per scheduler hide the
+//               tcgen05.ld / MUFU / DFMA latencies of one another; the MUFU pipe is the bound)
+//   warps 16-19 producers: candidate records (HBM/L2) -> hi/lo split -> K-major B stage in smem
+//   warp  20    TMEM allocation, landmark (A) tile bulk copies, tcgen05.mma issue (one lane)
 // Pipelines (mbarriers): B stages full/empty (3-deep ring), TMEM accumulators full/empty (2 buffers),
 // A tiles full/empty.
 #pragma once
@@ -62,7 +63,8 @@ struct MmaCfg {
   static constexpr int OFF_BAR = OFF_COMB + COMB_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256;
   static constexpr int TMEM_COLS = 2 * NT;             // two accumulator buffers (256 or 512)
-  static constexpr int EPI_WARPS = 8, PROD_WARPS = 4;
+  static constexpr int EPI_WARPS = 16, PROD_WARPS = 4;
+  static constexpr int NPART = EPI_WARPS / 4;          // column parts of an accumulator buffer (one warp each per lane quarter)
   static constexpr int THREADS = (EPI_WARPS + PROD_WARPS + 1) * 32;
 };
 
@@ -262,9 +264,11 @@ __global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(cons
 
   if (warp < Cfg::EPI_WARPS) {
     // ======================================================================== epilogue
-    const int quarter = warp & 3, half = warp >> 2;
+    const int quarter = warp & 3, part = warp >> 2;
     const int row = quarter * 32 + lane;
-    constexpr int HALF_COLS = NT / 2;
+    constexpr int NPART = Cfg::NPART;
+    constexpr int PART_COLS = NT / NPART;
+    static_assert(PART_COLS % 32 == 0, "column part must be a multiple of the tcgen05.ld width");
     uint32_t it = 0, tc = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int mg = item % a.n_mgroups, jg = item / a.n_mgroups;
@@ -278,15 +282,15 @@ __global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(cons
         for (int jj = 0; jj < JT; ++jj) acc[mt][jj] = 0.0;
       for (int64_t t = 0; t < n_tiles; ++t, ++it) {
         const int stage = it % NSTAGE;
-        const double* wst = sW + stage * NT + half * HALF_COLS;
+        const double* wst = sW + stage * NT + part * PART_COLS;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt, ++tc) {
           const uint32_t buf = tc & 1u;
           mma::mbar_wait(&t_full[buf], (tc >> 1) & 1u);
           mma::tc_fence_after();
-          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * NT + half * HALF_COLS;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * NT + part * PART_COLS;
 #pragma unroll 1
-          for (int cb = 0; cb < HALF_COLS; cb += 32) {
+          for (int cb = 0; cb < PART_COLS; cb += 32) {
             uint32_t v[32];
             mma::tmem_ld32(taddr + cb, v);
             mma::tmem_ld_wait();
@@ -307,15 +311,21 @@ __global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(cons
         __syncwarp();
         if (lane == 0) mma::mbar_arrive(&b_empty[stage]);
       }
-      // ---- combine the two column halves and write G
-      if (half == 1) {
+      // ---- combine the column parts in a fixed order (deterministic sums) and write G
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
+      for (int pp = NPART - 1; pp >= 1; --pp) {
+        if (part == pp) {
 #pragma unroll
-          for (int jj = 0; jj < JT; ++jj) sComb[(mt * 128 + row) * JT + jj] = acc[mt][jj];
+          for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int jj = 0; jj < JT; ++jj) {
+              double* c = &sComb[(mt * 128 + row) * JT + jj];
+              *c = (pp == NPART - 1) ? acc[mt][jj] : (*c + acc[mt][jj]);
+            }
+        }
+        mma::named_bar_sync(1, Cfg::EPI_WARPS * 32);
       }
-      mma::named_bar_sync(1, Cfg::EPI_WARPS * 32);
-      if (half == 0) {
+      if (part == 0) {
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           const int m = (mg * MT + mt) * 128 + row;

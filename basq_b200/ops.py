@@ -175,7 +175,7 @@ class Session:
 
     def close(self):
         h, self.handle = getattr(self, "handle", None), None
-        if h:
+        if h and _lib is not None and _lib.lib is not None:
             _lib.lib.basq_session_destroy(h)
 
     __del__ = close

@@ -232,10 +232,17 @@ def run_ours(a, rank, world, local_rank):
 
     for _ in range(max(a.warmup, 3)):
         out = step_device()
-    launches0 = ctx.launches
+    # phase spans are recorded as CUDA-event pairs on the library's stream (= torch's current stream)
+    # without synchronising, so they are taken live inside the timed region and read afterwards
+    ctx.profile(True)
+    ctx.profile_read(reset=True)
+    launches0, pe0 = ctx.launches, ctx.pair_evals
     with ClockSampler(local_rank) as clk:
         ms_step, out = timed(step_device, a.steps)
     launches = ctx.launches - launches0
+    pairs_step = (ctx.pair_evals - pe0) / a.steps
+    prof = ctx.profile_read(reset=True)
+    ctx.profile(False)
     idx, w = out
     assert 1 <= len(idx) <= a.n and bool((w > 0).all()), "invalid quadrature rule"
     assert abs(float(w.sum()) - 1.0) < 1e-9, float(w.sum())
@@ -250,16 +257,6 @@ def run_ours(a, rank, world, local_rank):
         e2e = {"value": N_glob / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
 
-    # phase breakdown + roofline of the dominant kernel from one profiled step (CUDA events on the
-    # library's stream around each phase; this step is not part of the timed region)
-    ctx.profile(True)
-    ctx.profile_read(reset=True)
-    pe0 = ctx.pair_evals
-    step_device()
-    pairs_step = ctx.pair_evals - pe0
-    prof = ctx.profile_read(reset=True)
-    ctx.profile(False)
-
     line = None
     if rank == 0:
         peaks = {}
@@ -268,38 +265,48 @@ def run_ours(a, rank, world, local_rank):
         except Exception:
             pass
         bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        peak_src = "measured (MEASURED_PEAKS.json bf16 sustained)" if peaks else "fallback"
-        Mtot = a.M + a.n_obs
-        ss_ms, ss_calls = prof["set_sum"]
-        pairs, n_rounds = pairs_step, ss_calls
-        flop_per_pair = 2 * a.d + 4
-        ach = pairs * flop_per_pair / (ss_ms * 1e-3) / 1e12 if ss_ms > 0 else None
+        peak_src = ("measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)"
+                    if peaks else "fallback (B200_PROFILING.md: 1.4 PFLOP/s sustained)")
+        ss_ms_tot, ss_calls = prof["set_sum"]
+        ss_ms = ss_ms_tot / a.steps                    # set-sum kernel time per step (one launch per round)
+        n_rounds = ss_calls // a.steps
+        ss_launch_ms = ss_ms_tot / max(ss_calls, 1)    # average launch duration
+        pairs_launch = pairs_step / max(n_rounds, 1)   # kernel evaluations k(z, x) per launch (average)
+        flop_per_pair = 2 * a.d + 4                    # algorithmic: d-term distance contraction (2d), bias adds, exp, weighted add
+        ach = pairs_launch * flop_per_pair / (ss_launch_ms * 1e-3) / 1e12 if ss_ms > 0 else None
         clocks = clk.summary()
-        sm_mhz = clocks.get("sm_mhz") or 1500.0
-        issue_peak = 148 * 128 * sm_mhz * 1e6 / 1e12     # thread-instructions/s (Tinst/s)
-        inst_per_pair = a.d + 6                          # d FFMA + FADD + MUFU + 3 int (widen) + DFMA
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        mufu_peak = 148 * 16 * sm_mhz * 1e6            # ex2.approx lanes/s: 16 per clock per SM
+        pair_rate = pairs_launch / (ss_launch_ms * 1e-3) if ss_ms > 0 else None
+        traffic = None
+        try:   # per-launch DRAM bytes of this kernel from the committed ncu --set full capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "setsum_traffic.json")))["dram_bytes_per_launch_avg"]
+        except Exception:
+            pass
         line = {
             "metric": "candidate points recombined/sec (N->n, d=10)", "value": value, "unit": "points/s",
             "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 kernel evaluation, f64 accumulation/projection/Caratheodory", "data": "synthetic",
+            "dtype": "f32 kernel evaluation (3xTF32 distance contraction), f64 accumulation/projection/Caratheodory",
+            "data": "synthetic",
             "config": {"workload": workload_name(a), "N_total": N_glob, "parallelism": f"dp{world}",
-                       "l2_policy": "inputs (400 MB of candidates per GPU) exceed the 126 MB L2"},
+                       "l2_policy": "inputs (640 MB of candidate records per GPU) exceed the 126 MB L2"},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
-            "phases_ms": {k: round(v[0], 3) for k, v in prof.items()}, "rounds": n_rounds,
+            "phases_ms": {k: round(v[0] / a.steps, 3) for k, v in prof.items()}, "rounds": n_rounds,
             "roofline": {
-                "bound": "tensor", "kernel": "setsum_kernel<float,RBF,10>", "achieved": ach, "peak": bf16_peak,
-                "unit": "TFLOP/s", "frac": (ach / bf16_peak) if ach else None, "traffic": None,
-                "peak_source": peak_src,
-                "note": ("sum-first formulation: the kernel evaluates M x R kernel entries per round on the "
-                         "FP32/MUFU pipes with fp64 accumulation and needs no N-scale tensor-core contraction; "
-                         "the tensor-pipe peak is therefore not its bound - see sm_roofline and DESIGN.md"),
+                "bound": "tensor", "kernel": "setsum_mma_kernel<RBF, 10> (tcgen05 kind::tf32 distance contraction + ex2 epilogue)",
+                "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": (ach / bf16_peak) if ach else None,
+                "traffic": traffic, "peak_source": peak_src,
+                "flop_per_pair": flop_per_pair, "pairs_per_launch_avg": pairs_launch, "launch_ms_avg": ss_launch_ms,
+                "note": ("algorithmic flop = (2d+4) per kernel evaluation k(z,x); the kernel issues 80 tf32 MMA "
+                         "flop per evaluation (K = 3d+6 padded to 40, 3xTF32) and is bound by the MUFU pipe "
+                         "(one ex2 per evaluation), not by the tensor pipe - see sfu_roofline and DESIGN.md 4"),
             },
-            "sm_roofline": {
-                "bound": "sm_issue", "achieved": (pairs * inst_per_pair / (ss_ms * 1e-3) / 1e12) if ss_ms > 0 else None,
-                "peak": issue_peak, "unit": "Tinst/s (thread instructions, 148 SMs x 128 lanes x measured clock)",
-                "frac": (pairs * inst_per_pair / (ss_ms * 1e-3) / 1e12 / issue_peak) if ss_ms > 0 else None,
-                "pairs_per_step": pairs, "set_sum_ms_per_step": ss_ms, "set_sum_launches": ss_calls,
+            "sfu_roofline": {
+                "bound": "mufu", "achieved": pair_rate, "peak": mufu_peak,
+                "unit": "kernel evaluations/s (one ex2.approx each; peak = 148 SMs x 16 lanes/clk x measured SM clock)",
+                "frac": (pair_rate / mufu_peak) if pair_rate else None,
+                "pairs_per_step": pairs_step, "set_sum_ms_per_step": ss_ms, "set_sum_launches_per_step": n_rounds,
             },
         }
     if rank == 0 and not a.no_cpu_baseline and world == 1:

@@ -24,7 +24,7 @@ LIB = os.path.join(HERE, "libbasq_b200.so")
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC",
-]
+] + os.environ.get("BASQ_EXTRA_NVCC", "").split()
 
 
 def _nvcc():

@@ -82,7 +82,8 @@ int64_t basq_ctx_launch_count(const basq_ctx* ctx);
 int64_t basq_ctx_pair_evals(const basq_ctx* ctx);
 /* CUDA-event timings (ms) accumulated per phase since the last reset:
    0 prepare, 1 set-sum, 2 projection GEMM, 3 Caratheodory, 4 apply/compact, 5 nystrom, 6 gp predict.
-   Only recorded when enabled (adds stream synchronisation). */
+   Only recorded when enabled: event pairs are recorded on the stream without synchronising;
+   basq_ctx_profile_read synchronises the stream and folds them in. */
 int basq_ctx_profile(basq_ctx* ctx, int enable);
 int basq_ctx_profile_read(basq_ctx* ctx, double* ms_host /*[8]*/, int64_t* calls_host /*[8]*/, int reset);
 
