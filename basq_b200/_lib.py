@@ -67,6 +67,7 @@ def _load():
         "basq_session_apply": (I, [P, L, L, P, C.POINTER(L)]),
         "basq_session_result": (I, [P, P, P, I, C.POINTER(I)]),
         "basq_dgemm": (I, [P, I, I, I, I, I, D, P, I, P, I, D, P, I]),
+        "basq_tgemm": (I, [P, I, I, I, P, I, P, I, P, I]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -9,6 +9,7 @@
 #include <new>
 
 #include "common.cuh"
+#include "tgemm.cuh"
 
 namespace basq {
 const char* last_error_cstr();
@@ -373,6 +374,7 @@ int basq_ctx_create(int device, void* stream, basq_ctx** out) {
   }
   { const char* t = getenv("BASQ_TRACE"); c->trace = t && t[0] == '1'; }
   { const char* t = getenv("BASQ_CAR_GENERAL"); c->force_general_car = t && t[0] == '1'; }
+  { const char* t = getenv("BASQ_NYSTROM_FP64"); c->no_tensor_nystrom = t && t[0] == '1'; }
   { const char* t = getenv("BASQ_SETSUM_SCALAR"); c->scalar_setsum = t && t[0] == '1'; }
   *out = c;
   return BASQ_OK;
@@ -414,6 +416,21 @@ int basq_dgemm(basq_ctx* ctx, int transA, int transB, int m, int n, int k, doubl
   BASQ_CHECK(ctx && A && B && C, BASQ_ERR_INVALID, "basq_dgemm: NULL argument");
   BASQ_CUDA(cudaSetDevice(ctx->device));
   return dgemm(ctx, transA != 0, transB != 0, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+}
+
+int basq_tgemm(basq_ctx* ctx, int m, int n, int k, const double* A, int lda, const double* B, int ldb, double* C,
+               int ldc) {
+  BASQ_CHECK(ctx && A && B && C, BASQ_ERR_INVALID, "basq_tgemm: NULL argument");
+  BASQ_CHECK(m >= 1 && n >= 1 && k >= 1 && lda >= k && ldb >= k && ldc >= n, BASQ_ERR_INVALID, "basq_tgemm: bad shape");
+  BASQ_CUDA(cudaSetDevice(ctx->device));
+  BlkOperand a, b;
+  BASQ_TRY(a.alloc(ctx, m, k));
+  BASQ_TRY(b.alloc(ctx, n, k));
+  BASQ_TRY(blk_from_f64(ctx, A, lda, false, &a));
+  BASQ_TRY(blk_from_f64(ctx, B, ldb, false, &b));
+  BASQ_TRY(tgemm(ctx, a, b, 1.0, C, ldc, false));
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BASQ_OK;
 }
 
 int basq_gram(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t a, const void* Y, int64_t b,

@@ -58,6 +58,7 @@ struct basq_ctx {
   int timer_depth = 0;
   bool force_general_car = false;  // BASQ_CAR_GENERAL=1: always use the global-memory kernel (tests)
   bool scalar_setsum = false;      // BASQ_SETSUM_SCALAR=1: CUDA-core set-sum kernel for fp32 too (A/B timing)
+  bool no_tensor_nystrom = false;  // BASQ_NYSTROM_FP64=1: fp64 GEMMs in the Nystrom iteration for fp32 kernels too (A/B)
   bool trace = false;      // BASQ_TRACE=1: wall-clock trace points on stderr (synchronising)
   double trace_t0 = 0.0;
   double phase_ms[basq::PH_COUNT] = {0};

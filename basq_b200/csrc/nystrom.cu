@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "gridsync.cuh"
+#include "tgemm.cuh"
 
 namespace basq {
 
@@ -389,13 +390,28 @@ int nystrom_basis(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, in
   BASQ_TRY(basq_gram(ctx, desc, Z, M, Z, M, K.as<double>()));
 
   const int Mi = (int)M;
-  BASQ_TRY(dgemm(ctx, false, false, Mi, q, Mi, 1.0, K.as<double>(), M, Omega, q, 0.0, Y.as<double>(), q));
+  // Y_out [M, q] = K Y_in.  fp32 kernels: on the tensor cores (3xTF32, tgemm.cu) - the Gram matrix itself
+  // is only fp32-accurate, and the subspace iteration re-orthonormalises in fp64 after every product;
+  // fp64 kernels: fp64 GEMM.  K is symmetric, so K^T Y = K Y.
+  const bool tensor = (desc->dtype == BASQ_F32) && !ctx->no_tensor_nystrom;
+  BlkOperand Kb, Yb;
+  if (tensor) {
+    BASQ_TRY(Kb.alloc(ctx, Mi, Mi));
+    BASQ_TRY(blk_from_f64(ctx, K.as<double>(), M, false, &Kb));
+    BASQ_TRY(Yb.alloc(ctx, q, Mi));
+  }
+  auto multiply = [&](const double* Yin, double* Yout) -> int {
+    if (!tensor) return dgemm(ctx, false, false, Mi, q, Mi, 1.0, K.as<double>(), M, Yin, q, 0.0, Yout, q);
+    BASQ_TRY(blk_from_f64(ctx, Yin, q, true, &Yb));                 // Y^T as [q, M] operand
+    return tgemm(ctx, Yb, Kb, 1.0, Yout, q, true);                  // (Y^T K^T)^T = K Y
+  };
+  BASQ_TRY(multiply(Omega, Y.as<double>()));
   BASQ_TRY(orthonormalise(ctx, ws, Y.as<double>(), M, q, niter > 0 ? 2 : 3));
   BASQ_TRY(Y2.alloc(ctx, sizeof(double) * (size_t)M * q));
   for (int it = 0; it < niter; ++it) {
-    BASQ_TRY(dgemm(ctx, true, false, Mi, q, Mi, 1.0, K.as<double>(), M, Y.as<double>(), q, 0.0, Y2.as<double>(), q));
+    BASQ_TRY(multiply(Y.as<double>(), Y2.as<double>()));
     BASQ_TRY(orthonormalise(ctx, ws, Y2.as<double>(), M, q, 2));
-    BASQ_TRY(dgemm(ctx, false, false, Mi, q, Mi, 1.0, K.as<double>(), M, Y2.as<double>(), q, 0.0, Y.as<double>(), q));
+    BASQ_TRY(multiply(Y2.as<double>(), Y.as<double>()));
     BASQ_TRY(orthonormalise(ctx, ws, Y.as<double>(), M, q, it + 1 == niter ? 3 : 2));
   }
   // U = Q^T  [q, M]  (transpose through a GEMM with the identity would waste flops: use geam-like copy)

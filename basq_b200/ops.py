@@ -102,6 +102,18 @@ def dgemm(A, B, transA=False, transB=False):
     return Cm
 
 
+def tgemm(A, B):
+    """A @ B.T on the tensor cores with fp32 accuracy (3xTF32); fp64 tensors in and out."""
+    ctx = _lib.context_for(A.device)
+    A = A.to(torch.float64).contiguous(); B = B.to(torch.float64).contiguous()
+    m, k = A.shape
+    n = B.shape[0]
+    assert B.shape[1] == k
+    Cm = torch.empty(m, n, dtype=torch.float64, device=A.device)
+    _lib.check(_lib.lib.basq_tgemm(ctx.handle, m, n, k, A.data_ptr(), k, B.data_ptr(), k, Cm.data_ptr(), n))
+    return Cm
+
+
 def recombine(kernel, pts_rec, pts_nys, U, mu=None, device=None):
     """Tchernychova-Lyons recombination with a given basis U [q, M]: (idx int64, w fp64) on device."""
     spec, ctx, device, dtype = _common(kernel, pts_rec, device)

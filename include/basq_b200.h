@@ -153,6 +153,12 @@ int basq_session_result(basq_session* s, int64_t* idx_out, double* w_out, int ca
 int basq_dgemm(basq_ctx* ctx, int transA, int transB, int m, int n, int k, double alpha,
                const double* A, int lda, const double* B, int ldb, double beta, double* C, int ldc);
 
+/* C[m,n] = A[m,k] B[n,k]^T on the tensor cores with fp32 accuracy (3xTF32 split operands, fp32
+   accumulation in TMEM; inputs rounded to fp32 first).  fp64 row-major in and out.  This is the GEMM
+   behind the Nystrom subspace iteration and the posterior-variance contraction for fp32 kernels. */
+int basq_tgemm(basq_ctx* ctx, int m, int n, int k, const double* A, int lda, const double* B, int ldb,
+               double* C, int ldc);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,26 @@ def test_dgemm(bq, ta, tb, m, n, k):
     assert rel(C, ref) < 1e-13
 
 
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (65, 33, 17), (128, 256, 32), (129, 257, 33), (300, 700, 1001),
+                                   (999, 640, 2048)])
+def test_tgemm_3xtf32(bq, m, n, k):
+    """Tensor-core GEMM (tcgen05, 3xTF32 split): fp32-level accuracy against an fp64 product."""
+    _, _, ops = bq
+    g = torch.Generator().manual_seed(m * 11 + n)
+    A = torch.randn(m, k, generator=g, dtype=torch.float64).to(DEV)
+    B = torch.randn(n, k, generator=g, dtype=torch.float64).to(DEV)
+    C = ops.tgemm(A, B)
+    ref = A @ B.T
+    # error relative to the magnitude of the sum's terms: 3xTF32 drops the lo*lo product (2^-22) and
+    # the accumulator in TMEM is fp32 (growth with k like an fp32 GEMM)
+    scale = float((A.abs() @ B.abs().T).max())
+    assert float((C - ref).abs().max()) / scale < 2e-6 * max(1.0, k / 512)
+    # fp32-representable inputs with small integer values are reproduced exactly
+    Ai = torch.randint(-8, 9, (m, k), generator=g).double().to(DEV)
+    Bi = torch.randint(-8, 9, (n, k), generator=g).double().to(DEV)
+    assert torch.equal(ops.tgemm(Ai, Bi), Ai @ Bi.T)
+
+
 # ------------------------------------------------------------------------------------------- base kernels
 FAMS = [("rbf", 2.5, 0), ("matern", 1.5, 1), ("matern", 2.5, 2)]
 
@@ -258,3 +278,30 @@ def test_nystrom_basis(bq, M, q):
     assert err(U) <= 3.0 * opt + 1e-9 * float(torch.linalg.norm(K))
     # Rayleigh quotients are the diagonal of U K U^T
     assert rel(S, torch.diagonal(U @ K @ U.T)) < 1e-9
+
+
+@pytest.mark.parametrize("M,q,d,ls", [(300, 99, 5, 2.0), (700, 200, 5, 2.0), (1500, 99, 2, 1.0), (2000, 499, 10, 2.5)])
+def test_nystrom_basis_fp32_tensor_path(bq, M, q, d, ls):
+    """fp32 kernels: the subspace iteration's K Y products run on the tensor cores (tgemm, 3xTF32);
+    the basis stays orthonormal to fp64 and captures what the reference's fp32 svd_lowrank captures
+    (d = 2: fast spectral decay, numerically rank-deficient Gram matrix)."""
+    _, _, ops = bq
+    g = torch.Generator().manual_seed(M + q)
+    Z = (math.sqrt(2.0) * torch.randn(M, d, generator=g)).float()
+    spec = _spec(bq, 0, ls, 1.0)
+    torch.manual_seed(0)
+    S, U = ops.nystrom_basis(spec, Z.to(DEV), q)
+    U = U.cpu()
+    assert U.shape == (q, M) and U.dtype == torch.float64
+    assert float((U @ U.T - torch.eye(q, dtype=torch.float64)).abs().max()) < 1e-10
+    K = ogp.base_kernel(Z.double(), Z.double(), "rbf", ls, 1.0)
+    torch.manual_seed(0)
+    _, Uref = orchq.nystrom_basis(Z, q, lambda a, b: ogp.base_kernel(a, b, "rbf", ls, 1.0))   # fp32, as BASQ runs it
+    Uref = torch.linalg.qr(Uref.double().T).Q.T
+    err = lambda B: float(torch.linalg.norm(K - K @ B.T @ B))
+    ev = torch.linalg.eigvalsh(K).flip(0)
+    opt = float(torch.sqrt((ev[q:] ** 2).sum()))
+    nK = float(torch.linalg.norm(K))
+    assert err(U) <= 1.5 * err(Uref) + 1e-6 * nK
+    assert err(U) <= 3.0 * opt + 1e-6 * nK
+    assert rel(S, torch.diagonal(U @ K @ U.T)) < 1e-5
