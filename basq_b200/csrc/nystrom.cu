@@ -285,6 +285,21 @@ __global__ void trace_kernel(const double* __restrict__ G, int q, int64_t ld, do
   if (threadIdx.x == 0) *out = sh[0];
 }
 
+// out [cols, rows] = in [rows, cols]^T (both row-major), 32 x 32 tiles through shared memory
+__global__ void transpose_kernel(const double* __restrict__ in, int rows, int cols, double* __restrict__ out) {
+  __shared__ double tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = in[(int64_t)r * cols + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[(int64_t)c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
 struct OrthWs {
   DevBuf gram, linv, tmp, prow, prow2, flags, scal;
 };
@@ -405,22 +420,24 @@ int nystrom_basis(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, in
     BASQ_TRY(blk_from_f64(ctx, Yin, q, true, &Yb));                 // Y^T as [q, M] operand
     return tgemm(ctx, Yb, Kb, 1.0, Yout, q, true);                  // (Y^T K^T)^T = K Y
   };
+  // Between products one shifted CholeskyQR pass is enough: it only has to keep the basis well
+  // enough conditioned for the next product (directions it damps by more than the working precision
+  // are lost to that product's rounding anyway); the last product is followed by sCholQR3, which
+  // returns a basis orthonormal to fp64.
   BASQ_TRY(multiply(Omega, Y.as<double>()));
-  BASQ_TRY(orthonormalise(ctx, ws, Y.as<double>(), M, q, niter > 0 ? 2 : 3));
+  BASQ_TRY(orthonormalise(ctx, ws, Y.as<double>(), M, q, niter > 0 ? 1 : 3));
   BASQ_TRY(Y2.alloc(ctx, sizeof(double) * (size_t)M * q));
   for (int it = 0; it < niter; ++it) {
     BASQ_TRY(multiply(Y.as<double>(), Y2.as<double>()));
-    BASQ_TRY(orthonormalise(ctx, ws, Y2.as<double>(), M, q, 2));
+    BASQ_TRY(orthonormalise(ctx, ws, Y2.as<double>(), M, q, 1));
     BASQ_TRY(multiply(Y2.as<double>(), Y.as<double>()));
-    BASQ_TRY(orthonormalise(ctx, ws, Y.as<double>(), M, q, it + 1 == niter ? 3 : 2));
+    BASQ_TRY(orthonormalise(ctx, ws, Y.as<double>(), M, q, it + 1 == niter ? 3 : 1));
   }
-  // U = Q^T  [q, M]  (transpose through a GEMM with the identity would waste flops: use geam-like copy)
+  // U = Q^T  [q, M]
   {
-    // ws.gram <- I (q x q), then U = I * Q^T via dgemm(NT)
-    BASQ_CUDA(cudaMemsetAsync(ws.gram.p, 0, sizeof(double) * (size_t)q * q, ctx->stream));
-    add_diag_kernel<<<ceil_div(q, 256), 256, 0, ctx->stream>>>(ws.gram.as<double>(), q, q, 1.0);
+    dim3 grid((unsigned)ceil_div(q, 32), (unsigned)ceil_div(Mi, 32));
+    transpose_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(Y.as<double>(), Mi, q, U_out);
     ctx->launches++;
-    BASQ_TRY(dgemm(ctx, false, true, q, Mi, q, 1.0, ws.gram.as<double>(), q, Y.as<double>(), q, 0.0, U_out, M));
   }
   if (S_out) {
     // Rayleigh quotients q_i^T K q_i
