@@ -3,18 +3,27 @@
 //   stage 1  Gauss-Jordan with row pivoting turns A [n, S] into [I | T]      (null-space basis)
 //   stage 2  ratio-test eliminations of the m = S - n non-basic sets          (BASQ/_rchq.py:146-171)
 //
-// B200 mapping.  One persistent cooperative kernel, 512 threads per CTA, one CTA per SM.
+// The step is a chain of n + m strictly sequential pivots: what matters is the latency of ONE pivot.
+// B200 mapping.  One persistent cooperative kernel, NT threads per CTA, one CTA per SM.
 //   * The tableau never touches shared or global memory between pivots: CTA k keeps a block of B
 //     consecutive rows (stage 1) / non-basic columns (stage 2) in REGISTERS, thread t holding the
-//     entries of columns (rows) t, t+512, t+1024, ... of each of them.
-//   * A block-step: the owner CTA performs its B pivots back to back on its own registers
-//     (pivot search = block arg-reduce; the B-1 sibling updates are register FMAs) and streams the
-//     B pivot rows to L2 as they are produced; ONE grid barrier; every other CTA replays the B
-//     rank-1 updates from L2 (pivot row entries prefetched one pivot ahead, multipliers broadcast
-//     through a double-buffered shared array - one __syncthreads per pivot).
-//   So n pivots cost ceil(n/B) grid barriers instead of n, and the per-pivot critical path is a few
-//   hundred cycles instead of several L2 round trips.
-// Limits: S <= 2048 (4 columns per thread), n <= 1024 (2 rows per thread), n, m <= 8 * #SMs.
+//     entries of columns (rows) t, t+NT, t+2NT, ... of each of them.
+//   * The owner CTA performs its B pivots back to back on its own registers: pivot search = block
+//     arg-reduce with one __syncthreads (the signed pivot travels with the reduction), multipliers
+//     of the B-1 sibling rows broadcast through a double-buffered shared array (second
+//     __syncthreads), sibling updates are register FMAs.
+//   * Publication is "the data is the flag": the pivot row (column) and a per-thread copy of the
+//     pivot index are streamed to L2 buffers that the host pre-filled with a NaN / -1 sentinel; a
+//     consumer thread simply polls the few words IT needs until they are no longer the sentinel.
+//     No fences, no flags, no grid barrier on the pivot chain (one barrier between the stages):
+//     consumers replay pivot i while the owner is already working on pivot i+1, so the chain per
+//     block is the owner's B pivots + one L2 round trip + ONE replayed pivot of the next owner.
+//   * Stage 2 hands the basic weights from owner to owner the same way; CTAs whose columns are
+//     eliminated exit.
+// Limits: S <= CPT*NT = 2048, n <= RPT*NT = 1024, n, m <= 8 * #SMs.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -24,32 +33,67 @@ namespace basq {
 
 namespace {
 
-constexpr int NT = 512;
-constexpr int CPT = 4;  // tableau columns per thread in stage 1
-constexpr int RPT = 2;  // tableau rows per thread in stage 2
+constexpr unsigned FULLMASK = 0xffffffffu;
+constexpr int SPIN_LIMIT = 1 << 22;  // polls before a consumer declares the chain dead
 
 struct Car2Dev {
   double* A;
   int n, S;
   int64_t lda;
-  double* prow;   // [n][S]   pivot rows as published
-  int* pinfo;     // [n]      pivot column of row r, -1 = row skipped (dependent)
-  double* pcol;   // [S][n]   pivot columns as published (stage 2)
-  double* sinfo;  // [S][2]   alpha, istar
-  double* omega;  // [S]
+  double* prow;     // [n][S]      pivot rows as published (NaN-sentinel filled)
+  int* prep;        // [n][NT]     per-thread copies of the row's pivot code (-1 = not yet published)
+  int* pinfo;       // [n]         pivot column of row r, -1 = row skipped (dependent)
+  double* pcol;     // [S][n]      pivot columns as published (stage 2; NaN-sentinel filled)
+  int* srep;        // [S][NT]     per-thread copies of the column's leaving-row code
+  double* muh;      // [G2][n]     basic weights handed to the owner of block k+1 (NaN-sentinel filled)
+  int* rph;         // [G2][n]     row -> set map handed over (code = set + 2)
+  double* omega;    // [S]
   unsigned* bar;
   int* status;
   double tol;
 };
 
-struct VI {
-  double v;
+// pivot codes: -1 not published, 1 = none (row skipped / no basic set leaves), c + 2 = index c
+__device__ __forceinline__ bool is_sentinel(double v) { return __double_as_longlong(v) == -1ll; }
+
+__device__ __forceinline__ double poll_f64(const double* p, int* status) {
+  double v = __ldcg(p);
+  int spins = 0;
+  while (is_sentinel(v)) {
+    if ((++spins & 255) == 0 && (*reinterpret_cast<volatile int*>(status) != 0 || spins > SPIN_LIMIT)) {
+      if (spins > SPIN_LIMIT) atomicExch(status, 2);
+      return 0.0;
+    }
+    v = __ldcg(p);
+  }
+  return v;
+}
+__device__ __forceinline__ int poll_i32(const int* p, int* status) {
+  int v = __ldcg(p);
+  int spins = 0;
+  while (v == -1) {
+    if ((++spins & 255) == 0 && (*reinterpret_cast<volatile int*>(status) != 0 || spins > SPIN_LIMIT)) {
+      if (spins > SPIN_LIMIT) atomicExch(status, 2);
+      return 1;
+    }
+    v = __ldcg(p);
+  }
+  return v;
+}
+
+struct VSI {
+  double v;  // key (|entry| or ratio)
+  double s;  // payload (signed entry)
   int i;
 };
 
-template <bool MAX>
-__device__ __forceinline__ VI block_best(VI x, VI* scratch) {
-  auto beats = [](const VI& a, const VI& b) {
+// Block-wide arg-best with ONE barrier: warp results go to a parity-alternating scratch row, every
+// warp then reduces the NT/32 candidates itself.  (Two calls can never touch the same row while a
+// thread still reads it: a thread passes the barrier of call N+1 only after all threads finished
+// reading the row of call N.)
+template <bool MAX, int NT>
+__device__ __forceinline__ VSI block_best(VSI x, VSI (*scratch)[NT / 32], int& spar) {
+  auto beats = [](const VSI& a, const VSI& b) {
     if (a.i < 0) return false;
     if (b.i < 0) return true;
     if (MAX ? (a.v > b.v) : (a.v < b.v)) return true;
@@ -57,43 +101,40 @@ __device__ __forceinline__ VI block_best(VI x, VI* scratch) {
   };
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    VI y;
-    y.v = __shfl_down_sync(0xffffffffu, x.v, o);
-    y.i = __shfl_down_sync(0xffffffffu, x.i, o);
+    VSI y;
+    y.v = __shfl_xor_sync(FULLMASK, x.v, o);
+    y.s = __shfl_xor_sync(FULLMASK, x.s, o);
+    y.i = __shfl_xor_sync(FULLMASK, x.i, o);
     if (beats(y, x)) x = y;
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) scratch[warp] = x;
+  if (lane == 0) scratch[spar][warp] = x;
   __syncthreads();
-  if (warp == 0) {
-    VI y = (lane < NT / 32) ? scratch[lane] : VI{0.0, -1};
+  VSI y = scratch[spar][lane & (NT / 32 - 1)];
+  spar ^= 1;
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-      VI z;
-      z.v = __shfl_down_sync(0xffffffffu, y.v, o);
-      z.i = __shfl_down_sync(0xffffffffu, y.i, o);
-      if (beats(z, y)) y = z;
-    }
-    if (lane == 0) scratch[16] = y;
+  for (int o = NT / 64; o > 0; o >>= 1) {
+    VSI z;
+    z.v = __shfl_xor_sync(FULLMASK, y.v, o);
+    z.s = __shfl_xor_sync(FULLMASK, y.s, o);
+    z.i = __shfl_xor_sync(FULLMASK, y.i, o);
+    if (beats(z, y)) y = z;
   }
-  __syncthreads();
-  return scratch[16];
+  return y;
 }
 
-template <int B>
+template <int B, int NT, int CPT, int RPT>
 __global__ void __launch_bounds__(NT, 1) car2_kernel(const Car2Dev a) {
-  __shared__ VI scratch[32];
+  __shared__ VSI scratch[2][NT / 32];
   __shared__ double fbuf[2][8];
-  __shared__ double pbcast;
   __shared__ int abort_sh;
-  __shared__ int scan_sh[NT];
-  __shared__ int tot_sh[CPT + 1];
   extern __shared__ int nbcol[];  // [S] non-basic column list (stage 2)
 
   const int n = a.n, S = a.S;
   const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
-  unsigned target = 0;
-  int par = 0;  // parity of the multiplier buffer (advanced once per applied pivot, CTA-uniform)
+  unsigned gen = 0;
+  int par = 0;   // parity of the multiplier buffer (advanced once per applied pivot, CTA-uniform)
+  int spar = 0;  // parity of the arg-reduce scratch
 
   for (int c = b * NT + tid; c < S; c += G * NT) a.omega[c] = 0.0;
 
@@ -117,124 +158,117 @@ __global__ void __launch_bounds__(NT, 1) car2_kernel(const Car2Dev a) {
   }
 #pragma unroll
   for (int i = 0; i < B; ++i) {
-    VI m{0.0, -1};
+    VSI m{0.0, 0.0, -1};
     if (i < rows_mine) {
 #pragma unroll
       for (int j = 0; j < CPT; ++j) {
         const double v = fabs(reg[i][j]);
-        if ((elig >> j & 1u) && (m.i < 0 || v > m.v)) m = VI{v, tid + j * NT};
+        if ((elig >> j & 1u) && (m.i < 0 || v > m.v)) m = VSI{v, 0.0, tid + j * NT};
       }
     }
-    rscale[i] = block_best<true>(m, scratch).v;  // (CTA-uniform loop: every thread calls it B times)
+    rscale[i] = block_best<true, NT>(m, scratch, spar).v;  // (CTA-uniform loop: every thread calls it B times)
   }
+
+  // rank-1 update of the own rows with pivot-row entries `pr` (pivot column cs); skip_row: the
+  // pivot row itself when it lives in this CTA
+  auto eliminate = [&](const double (&pr)[CPT], int cs, int skip_row) {
+    const int js = cs / NT;
+    if ((cs % NT) == tid) {
+      elig &= ~(1u << js);
+#pragma unroll
+      for (int i2 = 0; i2 < B; ++i2) {
+        double f = 0.0;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+          if (j == js) f = reg[i2][j];
+        fbuf[par][i2] = f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i2 = 0; i2 < B; ++i2) {
+      if (i2 != skip_row && i2 < rows_mine) {
+        const double f = fbuf[par][i2];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) reg[i2][j] = (tid + j * NT == cs) ? 0.0 : fma(-f, pr[j], reg[i2][j]);
+      }
+    }
+    par ^= 1;
+  };
 
   for (int k = 0; k < G1; ++k) {
     const int kr0 = k * B;
     const int krows = min(B, n - kr0);
     if (b == k) {
-      // ---- owner: B local pivots
+      // ---- owner: B local pivots, each published as soon as it exists
 #pragma unroll
       for (int i = 0; i < B; ++i) {
         if (i < krows) {
-          VI m{0.0, -1};
+          VSI m{0.0, 0.0, -1};
 #pragma unroll
           for (int j = 0; j < CPT; ++j) {
             const double v = fabs(reg[i][j]);
-            if ((elig >> j & 1u) && (m.i < 0 || v > m.v)) m = VI{v, tid + j * NT};
+            if ((elig >> j & 1u) && (m.i < 0 || v > m.v)) m = VSI{v, reg[i][j], tid + j * NT};
           }
-          m = block_best<true>(m, scratch);
+          m = block_best<true, NT>(m, scratch, spar);
           const bool skip = (m.i < 0) || !(m.v > a.tol * rscale[i]) || !(rscale[i] > 0.0);
+          const int row = kr0 + i;
           if (skip) {
-            if (tid == 0) a.pinfo[kr0 + i] = -1;
+            __stcg(&a.prep[(int64_t)row * NT + tid], 1);
+            if (tid == 0) a.pinfo[row] = -1;
           } else {
             const int cs = m.i;
-            const bool mine = (cs % NT) == tid;
-            const int js = cs / NT;
-            if (mine) {
-              double p = 0.0;
-#pragma unroll
-              for (int j = 0; j < CPT; ++j)
-                if (j == js) p = reg[i][j];
-              pbcast = p;
-            }
-            __syncthreads();
-            const double inv = 1.0 / pbcast;
+            const double inv = 1.0 / m.s;
+            // the multipliers of the sibling rows are the PRE-scaling entries of column cs: grab them
+            // (eliminate reads reg[i2][js] for i2 != i) after the pivot row has been scaled
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
               const int c = tid + j * NT;
               reg[i][j] = (c == cs) ? 1.0 : reg[i][j] * inv;
-              if (c < S) __stcg(&a.prow[(int64_t)(kr0 + i) * S + c], reg[i][j]);
+              if (c < S) __stcg(&a.prow[(int64_t)row * S + c], reg[i][j]);
             }
-            if (mine) {
-              elig &= ~(1u << js);
-#pragma unroll
-              for (int i2 = 0; i2 < B; ++i2) {
-                double f = 0.0;
-#pragma unroll
-                for (int j = 0; j < CPT; ++j)
-                  if (j == js) f = reg[i2][j];
-                fbuf[par][i2] = f;
-              }
-            }
-            if (tid == 0) a.pinfo[kr0 + i] = cs;
-            __syncthreads();
-#pragma unroll
-            for (int i2 = 0; i2 < B; ++i2) {
-              if (i2 != i && i2 < krows) {
-                const double f = fbuf[par][i2];
-#pragma unroll
-                for (int j = 0; j < CPT; ++j)
-                  reg[i2][j] = (tid + j * NT == cs) ? 0.0 : fma(-f, reg[i][j], reg[i2][j]);
-              }
-            }
-            par ^= 1;
+            __stcg(&a.prep[(int64_t)row * NT + tid], cs + 2);
+            if (tid == 0) a.pinfo[row] = cs;
+            eliminate(reg[i], cs, i);
           }
         }
       }
-    }
-    if (grid_barrier(a.bar, target, a.status, &abort_sh)) return;
-    if (b != k) {
-      // ---- everyone else: replay the B rank-1 updates
-      double cur[CPT], nxt[CPT];
+    } else {
+      // ---- everyone else: replay the block's rank-1 updates as the pivots appear in L2 (codes of the
+      // whole block and a rolling window of pivot-row entries are requested ahead of use)
+      int code[B];
 #pragma unroll
-      for (int j = 0; j < CPT; ++j) {
-        const int c = tid + j * NT;
-        cur[j] = (c < S) ? __ldcg(&a.prow[(int64_t)kr0 * S + c]) : 0.0;
-      }
-      for (int i = 0; i < krows; ++i) {
-        const int cs = __ldcg(&a.pinfo[kr0 + i]);
+      for (int i = 0; i < B; ++i) code[i] = (i < krows) ? __ldcg(&a.prep[(int64_t)(kr0 + i) * NT + tid]) : 1;
+      constexpr int PF = (B < 3) ? B : 3;
+      double win[PF][CPT];
+#pragma unroll
+      for (int i = 0; i < PF; ++i)
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
           const int c = tid + j * NT;
-          nxt[j] = (i + 1 < krows && c < S) ? __ldcg(&a.prow[(int64_t)(kr0 + i + 1) * S + c]) : 0.0;
-        }
-        if (cs >= 0) {
-          const int js = cs / NT;
-          if ((cs % NT) == tid) {
-            elig &= ~(1u << js);
-#pragma unroll
-            for (int i2 = 0; i2 < B; ++i2) {
-              double f = 0.0;
-#pragma unroll
-              for (int j = 0; j < CPT; ++j)
-                if (j == js) f = reg[i2][j];
-              fbuf[par][i2] = f;
-            }
-          }
-          __syncthreads();
-#pragma unroll
-          for (int i2 = 0; i2 < B; ++i2) {
-            if (i2 < rows_mine) {
-              const double f = fbuf[par][i2];
-#pragma unroll
-              for (int j = 0; j < CPT; ++j)
-                reg[i2][j] = (tid + j * NT == cs) ? 0.0 : fma(-f, cur[j], reg[i2][j]);
-            }
-          }
-          par ^= 1;
+          win[i][j] = (i < krows && c < S) ? __ldcg(&a.prow[(int64_t)(kr0 + i) * S + c]) : 0.0;
         }
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) cur[j] = nxt[j];
+      for (int i = 0; i < B; ++i) {
+        if (i < krows) {
+          int cd = code[i];
+          if (cd == -1) cd = poll_i32(&a.prep[(int64_t)(kr0 + i) * NT + tid], a.status);
+          double cur[CPT];
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) {
+            cur[j] = win[i % PF][j];
+            const int c = tid + j * NT;
+            if (i + PF < B) win[i % PF][j] = (i + PF < krows && c < S) ? __ldcg(&a.prow[(int64_t)(kr0 + i + PF) * S + c]) : 0.0;
+          }
+          if (cd >= 2) {
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+              const int c = tid + j * NT;
+              if (c < S && is_sentinel(cur[j])) cur[j] = poll_f64(&a.prow[(int64_t)(kr0 + i) * S + c], a.status);
+            }
+            eliminate(cur, cd - 2, -1);
+          }
+        }
       }
     }
   }
@@ -249,37 +283,45 @@ __global__ void __launch_bounds__(NT, 1) car2_kernel(const Car2Dev a) {
         if (c < S) __stcg(&a.A[(int64_t)(r0 + i) * a.lda + c], reg[i][j]);
       }
     }
-  // ascending list of still-eligible (= non-basic) columns: one block scan per column group
-  int base = 0;
+  // ascending list of still-eligible (= non-basic) columns: warp ballots + a scan over the warp counts
+  __shared__ int wcnt[CPT][NT / 32];
+  __shared__ int m_sh;
+  {
+    const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
-  for (int j = 0; j < CPT; ++j) {
-    const int bit = (elig >> j) & 1u;
-    __syncthreads();
-    scan_sh[tid] = bit;
-    __syncthreads();
-    for (int o = 1; o < NT; o <<= 1) {
-      int t = 0;
-      if (tid >= o) t = scan_sh[tid - o];
-      __syncthreads();
-      scan_sh[tid] += t;
-      __syncthreads();
+    for (int j = 0; j < CPT; ++j) {
+      const unsigned mask = __ballot_sync(FULLMASK, (elig >> j) & 1u);
+      if (lane == 0) wcnt[j][warp] = __popc(mask);
     }
-    if (bit) nbcol[base + scan_sh[tid] - 1] = tid + j * NT;
-    if (tid == NT - 1) tot_sh[j] = scan_sh[tid];
     __syncthreads();
-    base += tot_sh[j];
+    int base = 0;
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      int before = 0, total = 0;
+      for (int w = 0; w < NT / 32; ++w) {
+        const int cnt = wcnt[j][w];
+        if (w < warp) before += cnt;
+        total += cnt;
+      }
+      const unsigned mask = __ballot_sync(FULLMASK, (elig >> j) & 1u);
+      if ((elig >> j) & 1u) nbcol[base + before + __popc(mask & ((1u << lane) - 1u))] = tid + j * NT;
+      base += total;
+    }
+    if (tid == 0) m_sh = base;
+    __syncthreads();
   }
-  const int m = base;
+  const int m = m_sh;
   if ((m + B - 1) / B > G) {
     // more non-basic sets than this launch can hold in registers (rank-deficient system):
     // tell the host to redo the step with the general kernel.  Uniform over the grid.
     if (b == 0 && tid == 0) atomicExch(a.status, 3);
     return;
   }
-  if (grid_barrier(a.bar, target, a.status, &abort_sh)) return;
+  if (grid_barrier(a.bar, gen, a.status, &abort_sh)) return;
 
   // ------------------------------------------------------------------ stage 2: own non-basic columns -> registers
   const int G2 = (m + B - 1) / B;
+  if (b >= G2) return;  // no columns here; nobody waits for this CTA
   const int c0 = b * B;
   const int cols_mine = max(0, min(B, m - c0));
   double tc[B][RPT];
@@ -300,164 +342,202 @@ __global__ void __launch_bounds__(NT, 1) car2_kernel(const Car2Dev a) {
     }
   }
 
-  // weights move along the null vector of one non-basic set; pv = its tableau column
-  auto apply = [&](const double (&pv)[RPT], double alpha, int istar, int entering, int first) {
+  // pivot the own columns [first, cols_mine) on basic row istar of the published column pv
+  auto col_update = [&](const double (&pv)[RPT], int istar, int first) {
+    const int js = istar / NT;
+    if ((istar % NT) == tid) {
+      double p = 0.0;
 #pragma unroll
-    for (int jj = 0; jj < RPT; ++jj) {
-      if (rowpt[jj] >= 0) {
-        const double v = fma(alpha, pv[jj], muB[jj]);
-        muB[jj] = v > 0.0 ? v : 0.0;
-      }
-    }
-    if (istar >= 0) {
-      const int js = istar / NT;
-      if ((istar % NT) == tid) {
-        double p = 0.0;
-#pragma unroll
-        for (int jj = 0; jj < RPT; ++jj)
-          if (jj == js) p = pv[jj];
-#pragma unroll
-        for (int l2 = 0; l2 < B; ++l2) {
-          double t = 0.0;
-#pragma unroll
-          for (int jj = 0; jj < RPT; ++jj)
-            if (jj == js) t = tc[l2][jj];
-          fbuf[par][l2] = t / p;
-        }
-#pragma unroll
-        for (int jj = 0; jj < RPT; ++jj)
-          if (jj == js) {
-            muB[jj] = 1.0 - alpha;  // the entering set keeps what is left of its unit weight
-            rowpt[jj] = entering;
-          }
-      }
-      __syncthreads();
+      for (int jj = 0; jj < RPT; ++jj)
+        if (jj == js) p = pv[jj];
+      const double invp = 1.0 / p;
 #pragma unroll
       for (int l2 = 0; l2 < B; ++l2) {
-        if (l2 >= first && l2 < cols_mine) {
-          const double t = fbuf[par][l2];
+        double t = 0.0;
 #pragma unroll
-          for (int jj = 0; jj < RPT; ++jj)
-            tc[l2][jj] = (tid + jj * NT == istar) ? t : fma(-pv[jj], t, tc[l2][jj]);
-        }
+        for (int jj = 0; jj < RPT; ++jj)
+          if (jj == js) t = tc[l2][jj];
+        fbuf[par][l2] = t * invp;
       }
-      par ^= 1;
     }
+    __syncthreads();
+#pragma unroll
+    for (int l2 = 0; l2 < B; ++l2) {
+      if (l2 >= first && l2 < cols_mine) {
+        const double t = fbuf[par][l2];
+#pragma unroll
+        for (int jj = 0; jj < RPT; ++jj)
+          tc[l2][jj] = (tid + jj * NT == istar) ? t : fma(-pv[jj], t, tc[l2][jj]);
+      }
+    }
+    par ^= 1;
   };
 
-  for (int k = 0; k < G2; ++k) {
+  for (int k = 0; k <= b; ++k) {
     const int kc0 = k * B;
     const int kcols = min(B, m - kc0);
-    if (b == k) {
+    if (k < b) {
+      // ---- replay the block's pivots on the own columns as they appear
+      int code[B];
+      double pvs[B][RPT];
+#pragma unroll
+      for (int l = 0; l < B; ++l) {
+        code[l] = (l < kcols) ? __ldcg(&a.srep[(int64_t)(kc0 + l) * NT + tid]) : 1;
+#pragma unroll
+        for (int jj = 0; jj < RPT; ++jj) {
+          const int i = tid + jj * NT;
+          pvs[l][jj] = (l < kcols && i < n) ? __ldcg(&a.pcol[(int64_t)(kc0 + l) * n + i]) : 0.0;
+        }
+      }
 #pragma unroll
       for (int l = 0; l < B; ++l) {
         if (l < kcols) {
-          VI best{0.0, -1};
+          int cd = code[l];
+          if (cd == -1) cd = poll_i32(&a.srep[(int64_t)(kc0 + l) * NT + tid], a.status);
+          if (cd >= 2) {
+#pragma unroll
+            for (int jj = 0; jj < RPT; ++jj) {
+              const int i = tid + jj * NT;
+              if (i < n && is_sentinel(pvs[l][jj])) pvs[l][jj] = poll_f64(&a.pcol[(int64_t)(kc0 + l) * n + i], a.status);
+            }
+            col_update(pvs[l], cd - 2, 0);
+          }
+        }
+      }
+    } else {
+      // ---- owner: take over the basic weights, then its columns' ratio tests (reference :148-159)
+      if (k > 0) {
+#pragma unroll
+        for (int jj = 0; jj < RPT; ++jj) {
+          const int i = tid + jj * NT;
+          if (i < n) {
+            rowpt[jj] = poll_i32(&a.rph[(int64_t)(k - 1) * n + i], a.status) - 2;
+            muB[jj] = poll_f64(&a.muh[(int64_t)(k - 1) * n + i], a.status);
+          }
+        }
+      }
+#pragma unroll
+      for (int l = 0; l < B; ++l) {
+        if (l < kcols) {
+          VSI best{0.0, 0.0, -1};
 #pragma unroll
           for (int jj = 0; jj < RPT; ++jj) {
             const double t = tc[l][jj];
             if (rowpt[jj] >= 0 && t < 0.0) {
               const double ratio = muB[jj] / (-t);
-              if (best.i < 0 || ratio < best.v) best = VI{ratio, tid + jj * NT};
+              if (best.i < 0 || ratio < best.v) best = VSI{ratio, 0.0, tid + jj * NT};
             }
           }
-          best = block_best<false>(best, scratch);
+          best = block_best<false, NT>(best, scratch, spar);
           // the non-basic set itself has +1 in its null vector and weight 1: ratio 1
           const bool self = (best.i < 0) || !(best.v < 1.0);
           const double alpha = self ? 1.0 : best.v;
           const int istar = self ? -1 : best.i;
           const int jn = kc0 + l;
+          double pv[RPT];
 #pragma unroll
           for (int jj = 0; jj < RPT; ++jj) {
             const int i = tid + jj * NT;
-            if (i < n) __stcg(&a.pcol[(int64_t)jn * n + i], tc[l][jj]);
+            pv[jj] = tc[l][jj];
+            if (i < n && istar >= 0) __stcg(&a.pcol[(int64_t)jn * n + i], pv[jj]);
+            if (rowpt[jj] >= 0) {
+              const double v = fma(alpha, pv[jj], muB[jj]);
+              muB[jj] = v > 0.0 ? v : 0.0;
+            }
+            if (istar >= 0 && i == istar) {
+              muB[jj] = 1.0 - alpha;  // the entering set keeps what is left of its unit weight
+              rowpt[jj] = nbcol[jn];
+            }
           }
-          if (tid == 0) {
-            __stcg(&a.sinfo[2 * jn + 0], alpha);
-            __stcg(&a.sinfo[2 * jn + 1], (double)istar);
-          }
-          double pv[RPT];
-#pragma unroll
-          for (int jj = 0; jj < RPT; ++jj) pv[jj] = tc[l][jj];
-          apply(pv, alpha, istar, nbcol[jn], l + 1);
+          __stcg(&a.srep[(int64_t)jn * NT + tid], istar >= 0 ? istar + 2 : 1);
+          if (istar >= 0) col_update(pv, istar, l + 1);
         }
       }
-    }
-    if (grid_barrier(a.bar, target, a.status, &abort_sh)) return;
-    if (b != k) {
-      for (int l = 0; l < kcols; ++l) {
-        const int jn = kc0 + l;
-        const double alpha = __ldcg(&a.sinfo[2 * jn + 0]);
-        const int istar = (int)__ldcg(&a.sinfo[2 * jn + 1]);
-        double pv[RPT];
+      if (k == G2 - 1) {
+#pragma unroll
+        for (int jj = 0; jj < RPT; ++jj)
+          if (rowpt[jj] >= 0 && muB[jj] > 0.0) a.omega[rowpt[jj]] = muB[jj];
+      } else {
 #pragma unroll
         for (int jj = 0; jj < RPT; ++jj) {
           const int i = tid + jj * NT;
-          pv[jj] = (i < n) ? __ldcg(&a.pcol[(int64_t)jn * n + i]) : 0.0;
+          if (i < n) {
+            __stcg(&a.rph[(int64_t)k * n + i], rowpt[jj] + 2);
+            __stcg(&a.muh[(int64_t)k * n + i], muB[jj]);
+          }
         }
-        // CTAs whose columns are already eliminated (b < k) only track the weights
-        apply(pv, alpha, istar, nbcol[jn], b > k ? 0 : B);
       }
     }
   }
-  if (b == 0) {
-#pragma unroll
-    for (int jj = 0; jj < RPT; ++jj)
-      if (rowpt[jj] >= 0 && muB[jj] > 0.0) a.omega[rowpt[jj]] = muB[jj];
-  }
 }
 
-template <int B>
+template <int B, int NT, int CPT, int RPT>
 int launch_car2(basq_ctx* ctx, const Car2Dev& d, int grid, size_t smem) {
-  BASQ_CUDA(cudaFuncSetAttribute(car2_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BASQ_CUDA(cudaFuncSetAttribute(car2_kernel<B, NT, CPT, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* args[] = {(void*)&d};
-  BASQ_CUDA(cudaLaunchCooperativeKernel((const void*)car2_kernel<B>, dim3(grid), dim3(NT), args, smem, ctx->stream));
+  BASQ_CUDA(cudaLaunchCooperativeKernel((const void*)car2_kernel<B, NT, CPT, RPT>, dim3(grid), dim3(NT), args, smem,
+                                        ctx->stream));
   return BASQ_OK;
 }
+
+constexpr int C2_NT = 512, C2_CPT = 4, C2_RPT = 2;
 
 }  // namespace
 
 bool caratheodory_fast_supported(const basq_ctx* ctx, int n, int S) {
   const int m = S - n;
-  return S <= CPT * NT && n <= RPT * NT && n <= 8 * ctx->num_sms && m <= 8 * ctx->num_sms && m >= 1;
+  return S <= C2_CPT * C2_NT && n <= C2_RPT * C2_NT && n <= 8 * ctx->num_sms && m <= 8 * ctx->num_sms && m >= 1;
 }
 
 // status_out: 0 ok, 3 = more non-basic sets than fit (A holds the stage-1 result; caller must redo)
 int caratheodory_fast(basq_ctx* ctx, double* A, int n, int S, int lda, double* omega_out, int* status_out) {
+  constexpr int NT = C2_NT;
   const int m_max = S;  // non-basic sets: S - rank; S - n for a full-rank system
   int B = 1;
   while (B < 8 && ((n + B - 1) / B > ctx->num_sms || (m_max + B - 1) / B > ctx->num_sms)) B *= 2;
   const int grid = std::min(ctx->num_sms, std::max((n + B - 1) / B, (m_max + B - 1) / B));
+  const int G2max = grid;
   DevBuf ws;
-  const size_t sz_prow = sizeof(double) * (size_t)n * S, sz_pcol = sizeof(double) * (size_t)S * n,
-               sz_sinfo = sizeof(double) * 2 * S, sz_int = sizeof(int) * ((size_t)n + 8);
-  BASQ_TRY(ws.alloc(ctx, 512 + sz_prow + sz_pcol + sz_sinfo + sz_int + 64));
+  auto r256 = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t sz_head = 512;
+  // sentinel-filled region (0xFF bytes: NaN doubles, -1 ints)
+  const size_t sz_prow = r256(sizeof(double) * (size_t)n * S), sz_pcol = r256(sizeof(double) * (size_t)S * n),
+               sz_prep = r256(sizeof(int) * (size_t)n * NT), sz_srep = r256(sizeof(int) * (size_t)S * NT),
+               sz_muh = r256(sizeof(double) * (size_t)G2max * n), sz_rph = r256(sizeof(int) * (size_t)G2max * n);
+  const size_t sz_sent = sz_prow + sz_pcol + sz_prep + sz_srep + sz_muh + sz_rph;
+  const size_t sz_pinfo = r256(sizeof(int) * (size_t)n);
+  BASQ_TRY(ws.alloc(ctx, sz_head + sz_sent + sz_pinfo));
   unsigned char* w = ws.as<unsigned char>();
   Car2Dev d;
   d.A = A; d.n = n; d.S = S; d.lda = lda;
   d.bar = reinterpret_cast<unsigned*>(w);            // 256 B: arrival counter + flag line
   d.status = reinterpret_cast<int*>(w + 256);
-  w += 512;
+  w += sz_head;
+  unsigned char* sent0 = w;
   d.prow = reinterpret_cast<double*>(w); w += sz_prow;
   d.pcol = reinterpret_cast<double*>(w); w += sz_pcol;
-  d.sinfo = reinterpret_cast<double*>(w); w += sz_sinfo;
+  d.muh = reinterpret_cast<double*>(w); w += sz_muh;
+  d.prep = reinterpret_cast<int*>(w); w += sz_prep;
+  d.srep = reinterpret_cast<int*>(w); w += sz_srep;
+  d.rph = reinterpret_cast<int*>(w); w += sz_rph;
   d.pinfo = reinterpret_cast<int*>(w);
   d.omega = omega_out;
   d.tol = 1e-13;
-  BASQ_CUDA(cudaMemsetAsync(ws.p, 0, 512, ctx->stream));
+  BASQ_CUDA(cudaMemsetAsync(ws.p, 0, sz_head, ctx->stream));
+  BASQ_CUDA(cudaMemsetAsync(sent0, 0xFF, sz_sent, ctx->stream));
   const size_t smem = sizeof(int) * (size_t)S;
   switch (B) {
-    case 1: BASQ_TRY(launch_car2<1>(ctx, d, grid, smem)); break;
-    case 2: BASQ_TRY(launch_car2<2>(ctx, d, grid, smem)); break;
-    case 4: BASQ_TRY(launch_car2<4>(ctx, d, grid, smem)); break;
-    default: BASQ_TRY(launch_car2<8>(ctx, d, grid, smem)); break;
+    case 1: BASQ_TRY((launch_car2<1, C2_NT, C2_CPT, C2_RPT>(ctx, d, grid, smem))); break;
+    case 2: BASQ_TRY((launch_car2<2, C2_NT, C2_CPT, C2_RPT>(ctx, d, grid, smem))); break;
+    case 4: BASQ_TRY((launch_car2<4, C2_NT, C2_CPT, C2_RPT>(ctx, d, grid, smem))); break;
+    default: BASQ_TRY((launch_car2<8, C2_NT, C2_CPT, C2_RPT>(ctx, d, grid, smem))); break;
   }
   ctx->launches++;
   int status = 0;
   BASQ_CUDA(cudaMemcpyAsync(&status, d.status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
   *status_out = status;
-  BASQ_CHECK(status == 0 || status == 3, BASQ_ERR_NUMERIC, "caratheodory: grid barrier watchdog fired (status %d)",
+  BASQ_CHECK(status == 0 || status == 3, BASQ_ERR_NUMERIC, "caratheodory: pivot chain watchdog fired (status %d)",
              status);
   return BASQ_OK;
 }
