@@ -81,51 +81,79 @@ __device__ __forceinline__ int poll_i32(const int* p, int* status) {
   return v;
 }
 
-struct VSI {
-  double v;  // key (|entry| or ratio)
-  double s;  // payload (signed entry)
-  int i;
+// ---------------------------------------------------------------------------------------------
+// Block-wide arg-max / arg-min with ONE barrier and two shuffles per butterfly round.
+// The key is a non-negative double, so its bit pattern orders like an unsigned integer; the low 12
+// mantissa bits are replaced by the candidate's index (complemented for the maximum), which makes
+// every candidate unique and breaks ties (keys equal to 2^-40 relative) towards the smaller index.
+// The winner's exact payload (signed pivot / exact ratio) travels through the scratch row: the lane
+// that recognises its own packed key as the warp's best writes it, and after the barrier every warp
+// reduces the NT/32 warp results itself.  (Two calls never touch the same scratch row while a thread
+// still reads it: a thread passes the barrier of call N+1 only after all threads finished reading
+// the row of call N.)
+// ---------------------------------------------------------------------------------------------
+struct Slot {
+  unsigned long long key;
+  double val;
+};
+struct Best {
+  int idx;     // -1: no candidate
+  double val;  // exact payload of the winner
 };
 
-// Block-wide arg-best with ONE barrier: warp results go to a parity-alternating scratch row, every
-// warp then reduces the NT/32 candidates itself.  (Two calls can never touch the same row while a
-// thread still reads it: a thread passes the barrier of call N+1 only after all threads finished
-// reading the row of call N.)
+__device__ __forceinline__ unsigned long long pack_max(double key, int idx) {
+  return ((unsigned long long)__double_as_longlong(key) & ~0xFFFull) | (unsigned long long)(0xFFF - idx);
+}
+__device__ __forceinline__ unsigned long long pack_min(double key, int idx) {
+  return ((unsigned long long)__double_as_longlong(key) & ~0xFFFull) | (unsigned long long)idx;
+}
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long x, int o) {
+  const unsigned lo = __shfl_xor_sync(FULLMASK, (unsigned)x, o);
+  const unsigned hi = __shfl_xor_sync(FULLMASK, (unsigned)(x >> 32), o);
+  return ((unsigned long long)hi << 32) | lo;
+}
+
+// MAX: `none` = 0 ; MIN: `none` = ~0
 template <bool MAX, int NT>
-__device__ __forceinline__ VSI block_best(VSI x, VSI (*scratch)[NT / 32], int& spar) {
-  auto beats = [](const VSI& a, const VSI& b) {
-    if (a.i < 0) return false;
-    if (b.i < 0) return true;
-    if (MAX ? (a.v > b.v) : (a.v < b.v)) return true;
-    return a.v == b.v && a.i < b.i;
-  };
+__device__ __forceinline__ Best block_best(unsigned long long mine, double payload, Slot (*scratch)[NT / 32], int& spar) {
+  constexpr unsigned long long NONE = MAX ? 0ull : ~0ull;
+  unsigned long long x = mine;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    VSI y;
-    y.v = __shfl_xor_sync(FULLMASK, x.v, o);
-    y.s = __shfl_xor_sync(FULLMASK, x.s, o);
-    y.i = __shfl_xor_sync(FULLMASK, x.i, o);
-    if (beats(y, x)) x = y;
+    const unsigned long long y = shfl_xor_u64(x, o);
+    x = MAX ? (y > x ? y : x) : (y < x ? y : x);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) scratch[spar][warp] = x;
+  if (x == NONE) {
+    if (lane == 0) scratch[spar][warp] = Slot{NONE, 0.0};
+  } else if (mine == x) {
+    scratch[spar][warp] = Slot{x, payload};
+  }
   __syncthreads();
-  VSI y = scratch[spar][lane & (NT / 32 - 1)];
+  const Slot* row = scratch[spar];
   spar ^= 1;
+  const unsigned long long w = row[lane & (NT / 32 - 1)].key;
+  unsigned long long y = w;
 #pragma unroll
   for (int o = NT / 64; o > 0; o >>= 1) {
-    VSI z;
-    z.v = __shfl_xor_sync(FULLMASK, y.v, o);
-    z.s = __shfl_xor_sync(FULLMASK, y.s, o);
-    z.i = __shfl_xor_sync(FULLMASK, y.i, o);
-    if (beats(z, y)) y = z;
+    const unsigned long long z = shfl_xor_u64(y, o);
+    y = MAX ? (z > y ? z : y) : (z < y ? z : y);
   }
-  return y;
+  Best r;
+  if (y == NONE) {
+    r.idx = -1;
+    r.val = 0.0;
+    return r;
+  }
+  const unsigned hit = __ballot_sync(FULLMASK, w == y);
+  r.val = row[(__ffs(hit) - 1) & (NT / 32 - 1)].val;
+  r.idx = MAX ? (0xFFF - (int)(y & 0xFFFull)) : (int)(y & 0xFFFull);
+  return r;
 }
 
 template <int B, int NT, int CPT, int RPT>
 __global__ void __launch_bounds__(NT, 1) car2_kernel(const Car2Dev a) {
-  __shared__ VSI scratch[2][NT / 32];
+  __shared__ Slot scratch[2][NT / 32];
   __shared__ double fbuf[2][8];
   __shared__ int abort_sh;
   extern __shared__ int nbcol[];  // [S] non-basic column list (stage 2)
@@ -158,15 +186,16 @@ __global__ void __launch_bounds__(NT, 1) car2_kernel(const Car2Dev a) {
   }
 #pragma unroll
   for (int i = 0; i < B; ++i) {
-    VSI m{0.0, 0.0, -1};
+    unsigned long long mk = 0ull;
+    double mv = 0.0;
     if (i < rows_mine) {
 #pragma unroll
       for (int j = 0; j < CPT; ++j) {
-        const double v = fabs(reg[i][j]);
-        if ((elig >> j & 1u) && (m.i < 0 || v > m.v)) m = VSI{v, 0.0, tid + j * NT};
+        const unsigned long long pk = pack_max(fabs(reg[i][j]), tid + j * NT);
+        if ((elig >> j & 1u) && pk > mk) { mk = pk; mv = reg[i][j]; }
       }
     }
-    rscale[i] = block_best<true, NT>(m, scratch, spar).v;  // (CTA-uniform loop: every thread calls it B times)
+    rscale[i] = fabs(block_best<true, NT>(mk, mv, scratch, spar).val);  // (CTA-uniform loop: every thread calls it B times)
   }
 
   // rank-1 update of the own rows with pivot-row entries `pr` (pivot column cs); skip_row: the
@@ -190,8 +219,15 @@ __global__ void __launch_bounds__(NT, 1) car2_kernel(const Car2Dev a) {
       if (i2 != skip_row && i2 < rows_mine) {
         const double f = fbuf[par][i2];
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) reg[i2][j] = (tid + j * NT == cs) ? 0.0 : fma(-f, pr[j], reg[i2][j]);
+        for (int j = 0; j < CPT; ++j) reg[i2][j] = fma(-f, pr[j], reg[i2][j]);
       }
+    }
+    if ((cs % NT) == tid) {  // the eliminated column is exactly zero in every other row
+#pragma unroll
+      for (int i2 = 0; i2 < B; ++i2)
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+          if (j == js && i2 != skip_row) reg[i2][j] = 0.0;
     }
     par ^= 1;
   };
@@ -204,21 +240,22 @@ __global__ void __launch_bounds__(NT, 1) car2_kernel(const Car2Dev a) {
 #pragma unroll
       for (int i = 0; i < B; ++i) {
         if (i < krows) {
-          VSI m{0.0, 0.0, -1};
+          unsigned long long mk = 0ull;
+          double mv = 0.0;
 #pragma unroll
           for (int j = 0; j < CPT; ++j) {
-            const double v = fabs(reg[i][j]);
-            if ((elig >> j & 1u) && (m.i < 0 || v > m.v)) m = VSI{v, reg[i][j], tid + j * NT};
+            const unsigned long long pk = pack_max(fabs(reg[i][j]), tid + j * NT);
+            if ((elig >> j & 1u) && pk > mk) { mk = pk; mv = reg[i][j]; }
           }
-          m = block_best<true, NT>(m, scratch, spar);
-          const bool skip = (m.i < 0) || !(m.v > a.tol * rscale[i]) || !(rscale[i] > 0.0);
+          const Best m = block_best<true, NT>(mk, mv, scratch, spar);
+          const bool skip = (m.idx < 0) || !(fabs(m.val) > a.tol * rscale[i]) || !(rscale[i] > 0.0);
           const int row = kr0 + i;
           if (skip) {
             __stcg(&a.prep[(int64_t)row * NT + tid], 1);
             if (tid == 0) a.pinfo[row] = -1;
           } else {
-            const int cs = m.i;
-            const double inv = 1.0 / m.s;
+            const int cs = m.idx;
+            const double inv = 1.0 / m.val;
             // the multipliers of the sibling rows are the PRE-scaling entries of column cs: grab them
             // (eliminate reads reg[i2][js] for i2 != i) after the pivot row has been scaled
 #pragma unroll
@@ -366,9 +403,15 @@ __global__ void __launch_bounds__(NT, 1) car2_kernel(const Car2Dev a) {
       if (l2 >= first && l2 < cols_mine) {
         const double t = fbuf[par][l2];
 #pragma unroll
-        for (int jj = 0; jj < RPT; ++jj)
-          tc[l2][jj] = (tid + jj * NT == istar) ? t : fma(-pv[jj], t, tc[l2][jj]);
+        for (int jj = 0; jj < RPT; ++jj) tc[l2][jj] = fma(-pv[jj], t, tc[l2][jj]);
       }
+    }
+    if ((istar % NT) == tid) {  // the leaving row holds the multiplier itself
+#pragma unroll
+      for (int l2 = 0; l2 < B; ++l2)
+#pragma unroll
+        for (int jj = 0; jj < RPT; ++jj)
+          if (jj == js && l2 >= first && l2 < cols_mine) tc[l2][jj] = fbuf[par][l2];
     }
     par ^= 1;
   };
@@ -419,20 +462,22 @@ __global__ void __launch_bounds__(NT, 1) car2_kernel(const Car2Dev a) {
 #pragma unroll
       for (int l = 0; l < B; ++l) {
         if (l < kcols) {
-          VSI best{0.0, 0.0, -1};
+          unsigned long long bk = ~0ull;
+          double bv = 0.0;
 #pragma unroll
           for (int jj = 0; jj < RPT; ++jj) {
             const double t = tc[l][jj];
             if (rowpt[jj] >= 0 && t < 0.0) {
               const double ratio = muB[jj] / (-t);
-              if (best.i < 0 || ratio < best.v) best = VSI{ratio, 0.0, tid + jj * NT};
+              const unsigned long long pk = pack_min(ratio, tid + jj * NT);
+              if (pk < bk) { bk = pk; bv = ratio; }
             }
           }
-          best = block_best<false, NT>(best, scratch, spar);
+          const Best best = block_best<false, NT>(bk, bv, scratch, spar);
           // the non-basic set itself has +1 in its null vector and weight 1: ratio 1
-          const bool self = (best.i < 0) || !(best.v < 1.0);
-          const double alpha = self ? 1.0 : best.v;
-          const int istar = self ? -1 : best.i;
+          const bool self = (best.idx < 0) || !(best.val < 1.0);
+          const double alpha = self ? 1.0 : best.val;
+          const int istar = self ? -1 : best.idx;
           const int jn = kc0 + l;
           double pv[RPT];
 #pragma unroll
