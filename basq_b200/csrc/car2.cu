@@ -34,7 +34,6 @@ namespace basq {
 namespace {
 
 constexpr unsigned FULLMASK = 0xffffffffu;
-constexpr int SPIN_LIMIT = 1 << 22;  // polls before a consumer declares the chain dead
 
 struct Car2Dev {
   double* A;
@@ -54,32 +53,7 @@ struct Car2Dev {
 };
 
 // pivot codes: -1 not published, 1 = none (row skipped / no basic set leaves), c + 2 = index c
-__device__ __forceinline__ bool is_sentinel(double v) { return __double_as_longlong(v) == -1ll; }
-
-__device__ __forceinline__ double poll_f64(const double* p, int* status) {
-  double v = __ldcg(p);
-  int spins = 0;
-  while (is_sentinel(v)) {
-    if ((++spins & 255) == 0 && (*reinterpret_cast<volatile int*>(status) != 0 || spins > SPIN_LIMIT)) {
-      if (spins > SPIN_LIMIT) atomicExch(status, 2);
-      return 0.0;
-    }
-    v = __ldcg(p);
-  }
-  return v;
-}
-__device__ __forceinline__ int poll_i32(const int* p, int* status) {
-  int v = __ldcg(p);
-  int spins = 0;
-  while (v == -1) {
-    if ((++spins & 255) == 0 && (*reinterpret_cast<volatile int*>(status) != 0 || spins > SPIN_LIMIT)) {
-      if (spins > SPIN_LIMIT) atomicExch(status, 2);
-      return 1;
-    }
-    v = __ldcg(p);
-  }
-  return v;
-}
+// (is_sentinel / poll_f64 / poll_i32: gridsync.cuh)
 
 // ---------------------------------------------------------------------------------------------
 // Block-wide arg-max / arg-min with ONE barrier and two shuffles per butterfly round.

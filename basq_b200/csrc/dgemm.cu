@@ -25,7 +25,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 template <bool TA, bool TB, int MF>
 __global__ void __launch_bounds__(256) dgemm_kernel(int M, int N, int K, double alpha, const double* __restrict__ A,
                                                     int64_t lda, const double* __restrict__ B, int64_t ldb, double beta,
-                                                    double* __restrict__ C, int64_t ldc) {
+                                                    double* __restrict__ C, int64_t ldc, int tri_k) {
   constexpr int BM = 16 * MF;
   constexpr int AV = BM * BK / 256;  // A elements staged per thread
   constexpr int BV = BN * BK / 256;  // B elements staged per thread
@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(256) dgemm_kernel(int M, int N, int K, double 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 2, wn = warp & 3;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // tri_k: op(B)[k][n] is zero for k > n (B lower triangular, used transposed): stop at the tile's last column
+  if (tri_k) K = min(K, n0 + BN);
 
   // staging maps: consecutive threads walk the contiguous index of each operand
   int a_m[AV], a_k[AV], b_n[BV], b_k[BV];
@@ -126,27 +128,28 @@ __global__ void __launch_bounds__(256) dgemm_kernel(int M, int N, int K, double 
 
 template <bool TA, bool TB>
 void launch(basq_ctx* ctx, int m, int n, int k, double alpha, const double* A, int64_t lda, const double* B,
-            int64_t ldb, double beta, double* C, int64_t ldc) {
+            int64_t ldb, double beta, double* C, int64_t ldc, int tri_k) {
   const int64_t tiles128 = (int64_t)ceil_div(m, 128) * ceil_div(n, BN);
   if (tiles128 >= ctx->num_sms / 2) {
     dim3 grid((unsigned)ceil_div(n, BN), (unsigned)ceil_div(m, 128));
-    dgemm_kernel<TA, TB, 8><<<grid, 256, 0, ctx->stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    dgemm_kernel<TA, TB, 8><<<grid, 256, 0, ctx->stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k);
   } else {
     dim3 grid((unsigned)ceil_div(n, BN), (unsigned)ceil_div(m, 64));
-    dgemm_kernel<TA, TB, 4><<<grid, 256, 0, ctx->stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    dgemm_kernel<TA, TB, 4><<<grid, 256, 0, ctx->stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k);
   }
 }
 }  // namespace
 
 int dgemm(basq_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const double* A, int64_t lda,
-          const double* B, int64_t ldb, double beta, double* C, int64_t ldc) {
+          const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool b_lower_tri) {
+  const int tri_k = (b_lower_tri && tb) ? 1 : 0;
   if (m <= 0 || n <= 0) return BASQ_OK;
   BASQ_CHECK(k >= 0, BASQ_ERR_INVALID, "dgemm: negative k");
   BASQ_CHECK(ceil_div(m, 64) <= 65535, BASQ_ERR_UNSUPPORTED, "dgemm: m=%d too large for one launch", m);
-  if (!ta && !tb) launch<false, false>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
-  else if (ta && !tb) launch<true, false>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
-  else if (!ta && tb) launch<false, true>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
-  else launch<true, true>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+  if (!ta && !tb) launch<false, false>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k);
+  else if (ta && !tb) launch<true, false>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k);
+  else if (!ta && tb) launch<false, true>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k);
+  else launch<true, true>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k);
   ctx->launches++;
   BASQ_CUDA(cudaGetLastError());
   return BASQ_OK;

@@ -125,12 +125,9 @@ struct Chol2Dev {
 template <int B>
 __global__ void __launch_bounds__(C2_NT, 1) chol2_kernel(const Chol2Dev a) {
   __shared__ double fbuf[2][8];
-  __shared__ double pbcast;
-  __shared__ int abort_sh;
+  __shared__ double pbcast[2];
   const int q = a.q, W2 = 2 * a.q, b = blockIdx.x, tid = threadIdx.x;
-  unsigned gen = 0;
   int par = 0;
-  const int G1 = (q + B - 1) / B;
   const int r0 = b * B;
   const int rows_mine = max(0, min(B, q - r0));
   double reg[B][C2_CPT];
@@ -144,7 +141,9 @@ __global__ void __launch_bounds__(C2_NT, 1) chol2_kernel(const Chol2Dev a) {
       reg[i][j] = v;
     }
 
-  for (int k = 0; k < G1; ++k) {
+  // rows of the blocks above arrive through L2 ("the data is the flag", gridsync.cuh); a CTA is done
+  // after its own block, so the loop ends at k == b
+  for (int k = 0; k <= b; ++k) {
     const int kr0 = k * B;
     const int krows = min(B, q - kr0);
     if (b == k) {
@@ -152,39 +151,33 @@ __global__ void __launch_bounds__(C2_NT, 1) chol2_kernel(const Chol2Dev a) {
       for (int i = 0; i < B; ++i) {
         if (i < krows) {
           const int r = kr0 + i;
-          const bool mine = (r % C2_NT) == tid;
           const int js = r / C2_NT;
-          if (mine) {
+          if ((r % C2_NT) == tid) {
             double p = 0.0;
 #pragma unroll
             for (int j = 0; j < C2_CPT; ++j)
               if (j == js) p = reg[i][j];
             if (!(p > a.floor)) p = a.floor;
-            pbcast = 1.0 / sqrt(p);
-          }
-          __syncthreads();
-          const double inv = pbcast;
-#pragma unroll
-          for (int j = 0; j < C2_CPT; ++j) {
-            const int c = tid + j * C2_NT;
-            reg[i][j] *= inv;
-            if (c < W2) __stcg(&a.prow[(int64_t)r * W2 + c], reg[i][j]);
-          }
-          if (mine) {
-            double d = 1.0;
-#pragma unroll
-            for (int j = 0; j < C2_CPT; ++j)
-              if (j == js) d = reg[i][j];
+            const double inv = 1.0 / sqrt(p);
+            pbcast[par] = inv;
+            // multiplier of sibling row i2: g_i2r / d with d = p * inv the scaled diagonal
 #pragma unroll
             for (int i2 = 0; i2 < B; ++i2) {
               double f = 0.0;
 #pragma unroll
               for (int j = 0; j < C2_CPT; ++j)
                 if (j == js) f = reg[i2][j];
-              fbuf[par][i2] = f / d;
+              fbuf[par][i2] = f / (p * inv);
             }
           }
           __syncthreads();
+          const double inv = pbcast[par];
+#pragma unroll
+          for (int j = 0; j < C2_CPT; ++j) {
+            const int c = tid + j * C2_NT;
+            reg[i][j] *= inv;
+            if (c < W2) __stcg(&a.prow[(int64_t)r * W2 + c], reg[i][j]);
+          }
 #pragma unroll
           for (int i2 = 0; i2 < B; ++i2) {
             if (i2 > i && i2 < krows) {
@@ -197,50 +190,56 @@ __global__ void __launch_bounds__(C2_NT, 1) chol2_kernel(const Chol2Dev a) {
           par ^= 1;
         }
       }
-    }
-    if (grid_barrier(a.bar, gen, a.status, &abort_sh)) return;
-    if (b > k) {
-      double cur[C2_CPT], nxt[C2_CPT];
+    } else {
+      constexpr int PF = (B < 3) ? B : 3;
+      double win[PF][C2_CPT];
 #pragma unroll
-      for (int j = 0; j < C2_CPT; ++j) {
-        const int c = tid + j * C2_NT;
-        cur[j] = (c < W2) ? __ldcg(&a.prow[(int64_t)kr0 * W2 + c]) : 0.0;
-      }
-      for (int i = 0; i < krows; ++i) {
-        const int r = kr0 + i;
+      for (int i = 0; i < PF; ++i)
 #pragma unroll
         for (int j = 0; j < C2_CPT; ++j) {
           const int c = tid + j * C2_NT;
-          nxt[j] = (i + 1 < krows && c < W2) ? __ldcg(&a.prow[(int64_t)(r + 1) * W2 + c]) : 0.0;
+          win[i][j] = (i < krows && c < W2) ? __ldcg(&a.prow[(int64_t)(kr0 + i) * W2 + c]) : 0.0;
         }
-        const int js = r / C2_NT;
-        if ((r % C2_NT) == tid) {
-          double d = 1.0;
 #pragma unroll
-          for (int j = 0; j < C2_CPT; ++j)
-            if (j == js) d = cur[j];
+      for (int i = 0; i < B; ++i) {
+        if (i < krows) {
+          const int r = kr0 + i;
+          double cur[C2_CPT];
+#pragma unroll
+          for (int j = 0; j < C2_CPT; ++j) {
+            const int c = tid + j * C2_NT;
+            cur[j] = win[i % PF][j];
+            if (i + PF < B) win[i % PF][j] = (i + PF < krows && c < W2) ? __ldcg(&a.prow[(int64_t)(r + PF) * W2 + c]) : 0.0;
+            if (c < W2 && is_sentinel(cur[j])) cur[j] = poll_f64(&a.prow[(int64_t)r * W2 + c], a.status);
+          }
+          const int js = r / C2_NT;
+          if ((r % C2_NT) == tid) {
+            double d = 1.0;
+#pragma unroll
+            for (int j = 0; j < C2_CPT; ++j)
+              if (j == js) d = cur[j];
+            const double invd = 1.0 / d;
+#pragma unroll
+            for (int i2 = 0; i2 < B; ++i2) {
+              double f = 0.0;
+#pragma unroll
+              for (int j = 0; j < C2_CPT; ++j)
+                if (j == js) f = reg[i2][j];
+              fbuf[par][i2] = f * invd;
+            }
+          }
+          __syncthreads();
 #pragma unroll
           for (int i2 = 0; i2 < B; ++i2) {
-            double f = 0.0;
+            if (i2 < rows_mine) {
+              const double f = fbuf[par][i2];
 #pragma unroll
-            for (int j = 0; j < C2_CPT; ++j)
-              if (j == js) f = reg[i2][j];
-            fbuf[par][i2] = f / d;
+              for (int j = 0; j < C2_CPT; ++j)
+                reg[i2][j] = (tid + j * C2_NT == r) ? 0.0 : fma(-f, cur[j], reg[i2][j]);
+            }
           }
+          par ^= 1;
         }
-        __syncthreads();
-#pragma unroll
-        for (int i2 = 0; i2 < B; ++i2) {
-          if (i2 < rows_mine) {
-            const double f = fbuf[par][i2];
-#pragma unroll
-            for (int j = 0; j < C2_CPT; ++j)
-              reg[i2][j] = (tid + j * C2_NT == r) ? 0.0 : fma(-f, cur[j], reg[i2][j]);
-          }
-        }
-        par ^= 1;
-#pragma unroll
-        for (int j = 0; j < C2_CPT; ++j) cur[j] = nxt[j];
       }
     }
   }
@@ -317,6 +316,7 @@ int chol_inverse(basq_ctx* ctx, OrthWs& ws, int q, double floor_val) {
     d2.bar = ws.flags.as<unsigned>();
     d2.status = ws.flags.as<int>() + 64;
     BASQ_CUDA(cudaMemsetAsync(ws.flags.p, 0, 256, ctx->stream));
+    BASQ_CUDA(cudaMemsetAsync(ws.prow2.p, 0xFF, sizeof(double) * 2 * (size_t)q * q, ctx->stream));  // sentinel
     const int grid = (q + B - 1) / B;
     switch (B) {
       case 1: BASQ_TRY(launch_chol2<1>(ctx, d2, grid)); break;
@@ -371,7 +371,8 @@ int orthonormalise(basq_ctx* ctx, OrthWs& ws, double* Y, int64_t M, int q, int p
     }
     BASQ_TRY(chol_inverse(ctx, ws, q, tr * 1e-30));
     // Y <- Y L^-T
-    BASQ_TRY(dgemm(ctx, false, true, (int)M, q, q, 1.0, Y, q, ws.linv.as<double>(), q, 0.0, ws.tmp.as<double>(), q));
+    BASQ_TRY(dgemm(ctx, false, true, (int)M, q, q, 1.0, Y, q, ws.linv.as<double>(), q, 0.0, ws.tmp.as<double>(), q,
+                   /*b_lower_tri=*/true));
     BASQ_CUDA(cudaMemcpyAsync(Y, ws.tmp.p, sizeof(double) * (size_t)M * q, cudaMemcpyDeviceToDevice, ctx->stream));
   }
   int status = 0;
