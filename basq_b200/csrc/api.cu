@@ -54,6 +54,20 @@ __global__ void model_space_kernel(int mode, double offset, int64_t n, double* _
   if (write_var) var[p] = vo;
 }
 
+// W[r, i] = fpar[i] * sum_{k < cnt} Acell[r, node[i] + k * stride]: the column of a tree node of the
+// cell hierarchy (car_levels) from the projected cell columns, in a fixed summation order
+__global__ void gather_nodes_kernel(const double* __restrict__ Acell, int64_t ldc, int n, int C,
+                                    const int* __restrict__ node, const double* __restrict__ fpar, int stride,
+                                    int cnt, double* __restrict__ W, int64_t ldw) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)n * C) return;
+  const int r = (int)(t / C), i = (int)(t % C);
+  const double* src = Acell + (int64_t)r * ldc + node[i];
+  double s = 0.0;
+  for (int k = 0; k < cnt; ++k) s += src[(int64_t)k * stride];
+  W[(int64_t)r * ldw + i] = fpar[i] * s;
+}
+
 int check_finite_host(const double* v, int64_t n, const char* what) {
   for (int64_t i = 0; i < n; ++i)
     BASQ_CHECK(isfinite(v[i]), BASQ_ERR_NUMERIC, "%s contains a non-finite value at %lld", what, (long long)i);
@@ -80,9 +94,9 @@ struct basq_session {
   DevBuf sz;        // [M] per-landmark factor
   DevBuf Az;        // [M, n_obs] = K(Z, Xobs) W          (non-linear modes)
   RecPool pool;
-  DevBuf G;         // [Mtot, ldg]
+  DevBuf G;         // [Mtot, ldg]   (ldg = cells of the widest pass so far)
   int64_t ldg = 0;
-  DevBuf rank;      // int [S]
+  DevBuf rank;      // int [cells]
   DevBuf V, corrT;  // chunk buffers of the non-linear modes
   int64_t chunkP = 0;
   int64_t idx_base = 0;
@@ -204,9 +218,7 @@ int session_create_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
   BASQ_TRY(build_records(ctx, s->kp, desc->dtype, X, N_loc, uniform_w, mu, has_factor ? sx.as<double>() : nullptr,
                          !nonlin, &s->pool));
 
-  s->ldg = s->S;
-  BASQ_TRY(s->G.alloc(ctx, sizeof(double) * (size_t)s->Mtot * s->ldg));
-  BASQ_TRY(s->rank.alloc(ctx, sizeof(int) * s->S));
+  s->ldg = 0;  // G and the rank table are sized by the first pass (session_reserve_cells)
   if (nonlin) {
     int64_t P = (int64_t)(96ll << 20) / (8ll * std::max<int64_t>(M, n_obs));
     P = std::max<int64_t>(1024, std::min<int64_t>(P, 65536));
@@ -214,61 +226,177 @@ int session_create_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
     BASQ_TRY(s->V.alloc(ctx, sizeof(double) * (size_t)n_obs * P));
     BASQ_TRY(s->corrT.alloc(ctx, sizeof(double) * (size_t)M * P));
   }
-  s->omega_host.resize(s->S);
-  s->rank_host.resize(s->S);
   BASQ_CUDA(cudaStreamSynchronize(ctx->stream));  // sx goes out of scope
   return BASQ_OK;
 }
 
-int session_partial_impl(basq_session* s, int64_t R_glob, int64_t off, double* A_out) {
+// buffers that scale with the number of cells (F * S) of a pass
+int session_reserve_cells(basq_session* s, int cells) {
+  if (cells <= s->ldg) return BASQ_OK;
   basq_ctx* ctx = s->ctx;
-  const int S = s->S, n = s->n;
-  const int S_eff = (int)std::min<int64_t>(S, R_glob);
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  s->G.release();
+  s->rank.release();
+  s->ldg = cells;
+  BASQ_TRY(s->G.alloc(ctx, sizeof(double) * (size_t)s->Mtot * s->ldg));
+  BASQ_TRY(s->rank.alloc(ctx, sizeof(int) * (size_t)cells));
+  s->omega_host.resize(cells);
+  s->rank_host.resize(cells);
+  return BASQ_OK;
+}
+
+// Local part of a pass: A_out[n, F * S] (ld = F * S), column c = numerators / mass of CELL c, the
+// points whose global position = c (mod F * S).  F = 1 is the reference's round (S sets); F > 1
+// refines every set j into the F cells j, j + S, ..., so that ONE pass of kernel evaluations serves
+// log2(F) + 1 Caratheodory levels (car_levels).
+int session_partial_impl(basq_session* s, int64_t R_glob, int64_t off, int F, double* A_out) {
+  basq_ctx* ctx = s->ctx;
+  const int n = s->n;
+  const int cells = F * s->S;
+  const int c_eff = (int)std::min<int64_t>(cells, R_glob);
+  BASQ_CHECK(F >= 1 && F <= BASQ_MAX_CELL_FACTOR && (F & (F - 1)) == 0, BASQ_ERR_INVALID,
+             "partial: the cell factor must be a power of two <= %d (got %d)", BASQ_MAX_CELL_FACTOR, F);
   BASQ_CHECK(off >= 0 && off + s->pool.count <= R_glob, BASQ_ERR_INVALID,
              "partial: offset %lld + local %lld exceeds global %lld", (long long)off, (long long)s->pool.count,
              (long long)R_glob);
-  BASQ_CUDA(cudaMemsetAsync(A_out, 0, sizeof(double) * (size_t)n * S, ctx->stream));
+  BASQ_TRY(session_reserve_cells(s, cells));
+  BASQ_CUDA(cudaMemsetAsync(A_out, 0, sizeof(double) * (size_t)n * cells, ctx->stream));
   {
     PhaseTimer t(ctx, PH_SETSUM);
-    BASQ_TRY(set_masses(ctx, s->pool, off, S, S_eff, A_out));
-    BASQ_TRY(session_set_sums(s, off, S, 0, s->pool.count, s->G.as<double>(), s->ldg));
+    BASQ_TRY(set_masses(ctx, s->pool, off, cells, c_eff, A_out));
+    BASQ_TRY(session_set_sums(s, off, cells, 0, s->pool.count, s->G.as<double>(), s->ldg));
   }
   {
     PhaseTimer t(ctx, PH_PROJ);
     // rows 1..q : U' @ G   (reference: U_svd @ X_for_nys, BASQ/_rchq.py:88)
-    BASQ_TRY(dgemm(ctx, false, false, s->q, S_eff, s->Mtot, 1.0, s->Uprime.as<double>(), s->Mtot, s->G.as<double>(),
-                   s->ldg, 0.0, A_out + S, S));
+    BASQ_TRY(dgemm(ctx, false, false, s->q, c_eff, s->Mtot, 1.0, s->Uprime.as<double>(), s->Mtot, s->G.as<double>(),
+                   s->ldg, 0.0, A_out + cells, cells));
   }
   return BASQ_OK;
 }
 
-int session_apply_impl(basq_session* s, int64_t R_glob, int64_t off, const double* omega, int64_t* R_loc_new) {
+// Caratheodory over the cell hierarchy of one pass.  Acell[n, F * S] (ld = F * S) holds the summed
+// cell columns.  Level 0 reduces the S sets (set j = cells j + S t, t < F) to <= n; level l + 1
+// splits every surviving node into its two halves (t = r and t = r + 2^l modulo 2^(l+1)), scales
+// them by the parent's factor and reduces those <= 2n columns to <= n again.  After the last level
+// at most n CELLS survive: factor_host[c] is the product of the factors along the path of cell c
+// (0 = dropped).  Every level is the reference's step (BASQ/_rchq.py:103-105) on a finer partition.
+int car_levels(basq_ctx* ctx, const double* Acell, int n, int S, int F, int64_t R_glob, double* factor_host) {
+  const int cells = F * S;
+  int L = 0;
+  while ((1 << L) < F) ++L;
+  const int c_eff = (int)std::min<int64_t>(cells, R_glob);
+  BASQ_CHECK(F == 1 || R_glob >= cells, BASQ_ERR_INVALID, "car_levels: refined passes need R >= F * S");
+  std::vector<int> act;
+  std::vector<double> fac;
+  const int S0 = std::min(S, c_eff);
+  act.resize(S0);
+  fac.assign(S0, 1.0);
+  for (int j = 0; j < S0; ++j) act[j] = j;
+  for (int c = 0; c < cells; ++c) factor_host[c] = 0.0;
+  DevBuf W, dnode, dfpar, omega;
+  BASQ_TRY(W.alloc(ctx, sizeof(double) * (size_t)n * S));
+  BASQ_TRY(dnode.alloc(ctx, sizeof(int) * S));
+  BASQ_TRY(dfpar.alloc(ctx, sizeof(double) * S));
+  BASQ_TRY(omega.alloc(ctx, sizeof(double) * S));
+  std::vector<double> om(S);
+  for (int lvl = 0; lvl <= L; ++lvl) {
+    const int C = (int)act.size();
+    BASQ_CHECK(C >= 1 && C <= S, BASQ_ERR_NUMERIC, "car_levels: %d active nodes at level %d", C, lvl);
+    const int stride = S << lvl, cnt = F >> lvl;
+    if (C > n) {
+      {
+        PhaseTimer t(ctx, PH_CAR);
+        BASQ_CUDA(cudaMemcpyAsync(dnode.p, act.data(), sizeof(int) * C, cudaMemcpyHostToDevice, ctx->stream));
+        BASQ_CUDA(cudaMemcpyAsync(dfpar.p, fac.data(), sizeof(double) * C, cudaMemcpyHostToDevice, ctx->stream));
+        gather_nodes_kernel<<<(unsigned)ceil_div64((int64_t)n * C, 256), 256, 0, ctx->stream>>>(
+            Acell, cells, n, C, dnode.as<int>(), dfpar.as<double>(), stride, cnt, W.as<double>(), S);
+        ctx->launches++;
+        BASQ_CUDA(cudaGetLastError());
+      }
+      BASQ_TRY(caratheodory(ctx, W.as<double>(), n, C, S, omega.as<double>()));
+      BASQ_CUDA(cudaMemcpyAsync(om.data(), omega.p, sizeof(double) * C, cudaMemcpyDeviceToHost, ctx->stream));
+      BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+      BASQ_TRY(check_finite_host(om.data(), C, "omega"));
+    } else {
+      for (int i = 0; i < C; ++i) om[i] = 1.0;
+    }
+    std::vector<int> nact;
+    std::vector<double> nfac;
+    int kept = 0;
+    for (int half = 0; half < (lvl < L ? 2 : 1); ++half)
+      for (int i = 0; i < C; ++i) {
+        const double f = fac[i] * om[i];
+        if (!(om[i] > 0.0) || !(f > 0.0)) continue;
+        if (half == 0) ++kept;
+        if (lvl < L) {
+          nact.push_back(act[i] + half * stride);
+          nfac.push_back(f);
+        } else {
+          factor_host[act[i]] = f;
+        }
+      }
+    BASQ_CHECK(kept >= 1, BASQ_ERR_NUMERIC, "car_levels: the Caratheodory step kept no set (level %d)", lvl);
+    act.swap(nact);
+    fac.swap(nfac);
+  }
+  return BASQ_OK;
+}
+
+// Rescale the kept cells by factor_host[F * S] (0 = dropped), drop the rest, compact in order.
+int session_apply_impl(basq_session* s, int64_t R_glob, int64_t off, int F, const double* factor_host,
+                       int64_t* R_loc_new) {
   basq_ctx* ctx = s->ctx;
   PhaseTimer t(ctx, PH_APPLY);
-  const int S = s->S;
-  const int S_eff = (int)std::min<int64_t>(S, R_glob);
-  BASQ_CUDA(cudaMemcpyAsync(s->omega_host.data(), omega, sizeof(double) * S_eff, cudaMemcpyDeviceToHost, ctx->stream));
-  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
-  BASQ_TRY(check_finite_host(s->omega_host.data(), S_eff, "omega"));
+  const int cells = F * s->S;
+  const int c_eff = (int)std::min<int64_t>(cells, R_glob);
+  BASQ_TRY(session_reserve_cells(s, cells));
+  BASQ_TRY(check_finite_host(factor_host, c_eff, "omega"));
   int K = 0;
-  for (int j = 0; j < S; ++j) {
+  for (int j = 0; j < cells; ++j) {
     s->rank_host[j] = K;
-    if (j < S_eff && s->omega_host[j] > 0.0) ++K;
+    s->omega_host[j] = (j < c_eff && factor_host[j] > 0.0) ? factor_host[j] : 0.0;
+    if (s->omega_host[j] > 0.0) ++K;
   }
   BASQ_CHECK(K >= 1, BASQ_ERR_NUMERIC, "apply: the Caratheodory step kept no set");
   auto D = [&](int64_t g) {  // kept points among global positions < g
-    const int64_t e = g / S;
-    const int j = (int)(g % S);
+    const int64_t e = g / cells;
+    const int j = (int)(g % cells);
     return e * (int64_t)K + s->rank_host[j];
   };
   const int64_t dest_base = D(off);
   const int64_t new_count = D(off + s->pool.count) - dest_base;
-  BASQ_CUDA(cudaMemcpyAsync(s->rank.p, s->rank_host.data(), sizeof(int) * S, cudaMemcpyHostToDevice, ctx->stream));
-  BASQ_TRY(apply_round(ctx, &s->pool, off, S, omega, s->rank.as<int>(), K, s->scale_wf, dest_base, new_count));
-  // rank_host is reused next round: make sure the H2D copy has consumed it
+  DevBuf dom;
+  BASQ_TRY(dom.alloc(ctx, sizeof(double) * (size_t)cells));
+  BASQ_CUDA(cudaMemcpyAsync(dom.p, s->omega_host.data(), sizeof(double) * cells, cudaMemcpyHostToDevice, ctx->stream));
+  BASQ_CUDA(cudaMemcpyAsync(s->rank.p, s->rank_host.data(), sizeof(int) * cells, cudaMemcpyHostToDevice, ctx->stream));
+  BASQ_TRY(apply_round(ctx, &s->pool, off, cells, dom.as<double>(), s->rank.as<int>(), K, s->scale_wf, dest_base,
+                       new_count));
+  // the host tables are reused by the next pass: make sure the H2D copies have consumed them
   BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
   if (R_loc_new) *R_loc_new = new_count;
   return BASQ_OK;
+}
+
+// Cell factor of a pass over R_loc local points (R_glob in total): refining costs one projection
+// column per extra cell and saves the kernel evaluations of the rounds it replaces, so it pays
+// while the local set-sum work (Mtot * R_loc evaluations) dominates the projection (2 q Mtot S F flop).
+int choose_cell_factor(const basq_session* s, int64_t R_glob, int64_t R_loc_max) {
+  static const int forced = [] { const char* e = getenv("BASQ_CELL_FACTOR"); return e ? atoi(e) : 0; }();
+  const int64_t S = s->S, qS = (int64_t)s->q * s->S;
+  auto fits = [&](int f) { return R_glob >= (int64_t)4 * f * S; };
+  int F = 1;
+  if (forced >= 1) {
+    while (F * 2 <= forced && F * 2 <= BASQ_MAX_CELL_FACTOR && fits(F * 2)) F *= 2;
+  } else {
+    // one evaluation costs about 4.4 fp64-GEMM flop at the measured rates: going from F/2 to F saves
+    // R_loc Mtot / F evaluations and adds (F/2 - 1) projections of 2 q Mtot S flop
+    if (fits(2)) F = 2;
+    if (fits(4) && R_loc_max > qS) F = 4;
+    if (fits(8) && R_loc_max > 6 * qS) F = 8;
+  }
+  if (s->nl != NL_LIN) F = 1;  // the chunked non-linear path keeps the plain round
+  return F;
 }
 
 // Phi[p_lo..p_hi, q] for the session's live records
@@ -298,22 +426,29 @@ int recombine_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, i
   BASQ_TRY(session_create_impl(ctx, desc, X, N, N, 0, Z, M, U, q, mu, 0, s.get()));
   trace_point(ctx, "recombine: session created");
   const int n = s->n, S = s->S;
-  DevBuf A, omega;
-  BASQ_TRY(A.alloc(ctx, sizeof(double) * (size_t)n * S));
-  BASQ_TRY(omega.alloc(ctx, sizeof(double) * S));
+  DevBuf A;
   int64_t R = s->pool.count;
-  int rounds = 0;
+  std::vector<double> factor;
+  int rounds = 0, a_cells = 0;
   while (R > n) {
     BASQ_CHECK(++rounds <= 256, BASQ_ERR_NUMERIC, "recombine: no convergence after 256 rounds");
-    BASQ_TRY(session_partial_impl(s.get(), R, 0, A.as<double>()));
-    trace_point(ctx, "  round: partial");
-    const int S_eff = (int)std::min<int64_t>(S, R);
-    BASQ_TRY(caratheodory(ctx, A.as<double>(), n, S_eff, S, omega.as<double>()));
-    trace_point(ctx, "  round: caratheodory");
+    const int F = choose_cell_factor(s.get(), R, R);
+    const int cells = F * S;
+    if (cells > a_cells) {
+      BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+      A.release();
+      BASQ_TRY(A.alloc(ctx, sizeof(double) * (size_t)n * cells));
+      a_cells = cells;
+      factor.resize(cells);
+    }
+    BASQ_TRY(session_partial_impl(s.get(), R, 0, F, A.as<double>()));
+    trace_point(ctx, "  pass: partial");
+    BASQ_TRY(car_levels(ctx, A.as<double>(), n, S, F, R, factor.data()));
+    trace_point(ctx, "  pass: caratheodory levels");
     int64_t Rn = 0;
-    BASQ_TRY(session_apply_impl(s.get(), R, 0, omega.as<double>(), &Rn));
-    trace_point(ctx, "  round: apply");
-    BASQ_CHECK(Rn < R, BASQ_ERR_NUMERIC, "recombine: round %d made no progress (%lld points)", rounds, (long long)R);
+    BASQ_TRY(session_apply_impl(s.get(), R, 0, F, factor.data(), &Rn));
+    trace_point(ctx, "  pass: apply");
+    BASQ_CHECK(Rn < R, BASQ_ERR_NUMERIC, "recombine: pass %d made no progress (%lld points)", rounds, (long long)R);
     R = Rn;
   }
   trace_point(ctx, "recombine: rounds done");
@@ -632,14 +767,46 @@ int basq_session_count(const basq_session* s, int64_t* R_loc_host) {
 int basq_session_partial(basq_session* s, int64_t R_glob, int64_t off_glob, double* A_out) {
   BASQ_CHECK(s && A_out, BASQ_ERR_INVALID, "NULL argument");
   BASQ_CUDA(cudaSetDevice(s->ctx->device));
-  return session_partial_impl(s, R_glob, off_glob, A_out);
+  return session_partial_impl(s, R_glob, off_glob, 1, A_out);
+}
+
+int basq_session_partial_cells(basq_session* s, int64_t R_glob, int64_t off_glob, int F, double* A_out) {
+  BASQ_CHECK(s && A_out, BASQ_ERR_INVALID, "NULL argument");
+  BASQ_CUDA(cudaSetDevice(s->ctx->device));
+  return session_partial_impl(s, R_glob, off_glob, F, A_out);
+}
+
+int basq_session_cell_factor(const basq_session* s, int64_t R_glob, int64_t R_loc_max, int* F_out_host) {
+  BASQ_CHECK(s && F_out_host, BASQ_ERR_INVALID, "NULL argument");
+  *F_out_host = choose_cell_factor(s, R_glob, R_loc_max);
+  return BASQ_OK;
+}
+
+int basq_car_levels(basq_ctx* ctx, const double* A_cells, int n, int S, int F, int64_t R_glob,
+                    double* factor_out_host) {
+  BASQ_CHECK(ctx && A_cells && factor_out_host, BASQ_ERR_INVALID, "basq_car_levels: NULL argument");
+  BASQ_CHECK(n >= 1 && S >= 1 && F >= 1 && F <= BASQ_MAX_CELL_FACTOR && (F & (F - 1)) == 0, BASQ_ERR_INVALID,
+             "basq_car_levels: bad shape n=%d S=%d F=%d", n, S, F);
+  BASQ_CUDA(cudaSetDevice(ctx->device));
+  return car_levels(ctx, A_cells, n, S, F, R_glob, factor_out_host);
 }
 
 int basq_session_apply(basq_session* s, int64_t R_glob, int64_t off_glob, const double* omega,
                        int64_t* R_loc_new_host) {
   BASQ_CHECK(s && omega, BASQ_ERR_INVALID, "NULL argument");
   BASQ_CUDA(cudaSetDevice(s->ctx->device));
-  return session_apply_impl(s, R_glob, off_glob, omega, R_loc_new_host);
+  std::vector<double> h((size_t)s->S);
+  BASQ_CUDA(cudaMemcpyAsync(h.data(), omega, sizeof(double) * s->S, cudaMemcpyDeviceToHost, s->ctx->stream));
+  BASQ_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  return session_apply_impl(s, R_glob, off_glob, 1, h.data(), R_loc_new_host);
+}
+
+int basq_session_apply_cells(basq_session* s, int64_t R_glob, int64_t off_glob, int F, const double* factor_host,
+                             int64_t* R_loc_new_host) {
+  BASQ_CHECK(s && factor_host, BASQ_ERR_INVALID, "NULL argument");
+  BASQ_CHECK(F >= 1 && F <= BASQ_MAX_CELL_FACTOR && (F & (F - 1)) == 0, BASQ_ERR_INVALID, "apply: bad cell factor %d", F);
+  BASQ_CUDA(cudaSetDevice(s->ctx->device));
+  return session_apply_impl(s, R_glob, off_glob, F, factor_host, R_loc_new_host);
 }
 
 int basq_session_result(basq_session* s, int64_t* idx_out, double* w_out, int cap, int* n_out_host) {

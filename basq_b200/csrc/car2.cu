@@ -49,8 +49,17 @@ struct Car2Dev {
   double* omega;    // [S]
   unsigned* bar;
   int* status;
+  unsigned long long* stamps;  // optional [4] globaltimer stamps (BASQ_CAR_TIMING=1): start, stage 1 done, barrier passed, end
   double tol;
 };
+
+__device__ __forceinline__ void stamp(unsigned long long* stamps, int i) {
+  if (stamps) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    stamps[i] = t;
+  }
+}
 
 // pivot codes: -1 not published, 1 = none (row skipped / no basic set leaves), c + 2 = index c
 // (is_sentinel / poll_f64 / poll_i32: gridsync.cuh)
@@ -139,6 +148,7 @@ __global__ void __launch_bounds__(NT, 1) car2_kernel(const Car2Dev a) {
   int spar = 0;  // parity of the arg-reduce scratch
 
   for (int c = b * NT + tid; c < S; c += G * NT) a.omega[c] = 0.0;
+  if (b == 0 && tid == 0) stamp(a.stamps, 0);
 
   // ------------------------------------------------------------------ stage 1: own rows -> registers
   const int G1 = (n + B - 1) / B;
@@ -284,6 +294,7 @@ __global__ void __launch_bounds__(NT, 1) car2_kernel(const Car2Dev a) {
     }
   }
 
+  if (b == G1 - 1 && tid == 0) stamp(a.stamps, 1);
   // ------------------------------------------------------------------ write [I | T] back, list the non-basic sets
 #pragma unroll
   for (int i = 0; i < B; ++i)
@@ -329,6 +340,7 @@ __global__ void __launch_bounds__(NT, 1) car2_kernel(const Car2Dev a) {
     return;
   }
   if (grid_barrier(a.bar, gen, a.status, &abort_sh)) return;
+  if (b == 0 && tid == 0) stamp(a.stamps, 2);
 
   // ------------------------------------------------------------------ stage 2: own non-basic columns -> registers
   const int G2 = (m + B - 1) / B;
@@ -473,6 +485,7 @@ __global__ void __launch_bounds__(NT, 1) car2_kernel(const Car2Dev a) {
         }
       }
       if (k == G2 - 1) {
+        if (tid == 0) stamp(a.stamps, 3);
 #pragma unroll
         for (int jj = 0; jj < RPT; ++jj)
           if (rowpt[jj] >= 0 && muB[jj] > 0.0) a.omega[rowpt[jj]] = muB[jj];
@@ -542,6 +555,8 @@ int caratheodory_fast(basq_ctx* ctx, double* A, int n, int S, int lda, double* o
   d.pinfo = reinterpret_cast<int*>(w);
   d.omega = omega_out;
   d.tol = 1e-13;
+  static const bool timing = [] { const char* e = getenv("BASQ_CAR_TIMING"); return e && e[0] == '1'; }();
+  d.stamps = timing ? reinterpret_cast<unsigned long long*>(ws.as<unsigned char>() + 256 + 64) : nullptr;
   BASQ_CUDA(cudaMemsetAsync(ws.p, 0, sz_head, ctx->stream));
   BASQ_CUDA(cudaMemsetAsync(sent0, 0xFF, sz_sent, ctx->stream));
   const size_t smem = sizeof(int) * (size_t)S;
@@ -555,6 +570,12 @@ int caratheodory_fast(basq_ctx* ctx, double* A, int n, int S, int lda, double* o
   int status = 0;
   BASQ_CUDA(cudaMemcpyAsync(&status, d.status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (timing) {
+    unsigned long long t[4];
+    BASQ_CUDA(cudaMemcpy(t, d.stamps, sizeof(t), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[car2] n=%d S=%d B=%d grid=%d: stage1 %.1f us, barrier+list %.1f us, stage2 %.1f us\n", n, S, B, grid,
+            (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3);
+  }
   *status_out = status;
   BASQ_CHECK(status == 0 || status == 3, BASQ_ERR_NUMERIC, "caratheodory: pivot chain watchdog fired (status %d)",
              status);

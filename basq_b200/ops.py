@@ -197,16 +197,30 @@ class Session:
         _lib.check(_lib.lib.basq_session_count(self.handle, C.byref(c)))
         return int(c.value)
 
-    def partial(self, R_glob, off_glob, A: torch.Tensor):
-        assert A.dtype == torch.float64 and A.is_contiguous() and A.shape == (self.n, self.S)
-        _lib.check(_lib.lib.basq_session_partial(self.handle, int(R_glob), int(off_glob), A.data_ptr()))
+    def cell_factor(self, R_glob, R_loc_max) -> int:
+        """Cells per set (1, 2, 4, 8) the library picks for a pass over R_glob live points."""
+        f = C.c_int(1)
+        _lib.check(_lib.lib.basq_session_cell_factor(self.handle, int(R_glob), int(R_loc_max), C.byref(f)))
+        return int(f.value)
 
-    def car(self, A: torch.Tensor, S_eff: int, omega: torch.Tensor):
-        _lib.check(_lib.lib.basq_car(self.ctx.handle, A.data_ptr(), self.n, int(S_eff), self.S, omega.data_ptr(), None))
+    def partial(self, R_glob, off_glob, F, A: torch.Tensor):
+        """Local part of the pass's cell system A [n, F*S] (sum over ranks before car_levels)."""
+        assert A.dtype == torch.float64 and A.is_contiguous() and A.shape == (self.n, F * self.S)
+        _lib.check(_lib.lib.basq_session_partial_cells(self.handle, int(R_glob), int(off_glob), int(F), A.data_ptr()))
 
-    def apply(self, R_glob, off_glob, omega: torch.Tensor) -> int:
+    def car_levels(self, A: torch.Tensor, F, R_glob) -> torch.Tensor:
+        """Per-cell factors (HOST fp64 [F*S], 0 = dropped) of the pass's Caratheodory levels."""
+        factor = torch.zeros(F * self.S, dtype=torch.float64)
+        _lib.check(_lib.lib.basq_car_levels(self.ctx.handle, A.data_ptr(), self.n, self.S, int(F), int(R_glob),
+                                            factor.data_ptr()))
+        return factor
+
+    def apply(self, R_glob, off_glob, F, factor: torch.Tensor) -> int:
         c = C.c_int64(0)
-        _lib.check(_lib.lib.basq_session_apply(self.handle, int(R_glob), int(off_glob), omega.data_ptr(), C.byref(c)))
+        assert factor.device.type == "cpu" and factor.dtype == torch.float64 and factor.numel() == F * self.S
+        factor = factor.contiguous()
+        _lib.check(_lib.lib.basq_session_apply_cells(self.handle, int(R_glob), int(off_glob), int(F),
+                                                     factor.data_ptr(), C.byref(c)))
         return int(c.value)
 
     def result(self):

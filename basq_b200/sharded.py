@@ -1,8 +1,8 @@
 """Recombination of a candidate set sharded over ranks (one process per GPU).
 
-Per Tchernychova-Lyons round every rank forms the barycentre numerators of ITS points
-(set = global position mod S), one all-reduce sums the small [n, S] system over NVLink, every rank
-runs the same deterministic Caratheodory kernel on the identical reduced system, and rescales /
+Per Tchernychova-Lyons pass every rank forms the barycentre numerators of ITS points
+(cell = global position mod F*S), one all-reduce sums the small [n, F*S] system over NVLink, every
+rank runs the same deterministic Caratheodory levels on the identical reduced system, and rescales /
 compacts its own shard.  Counts and offsets after a round follow analytically from the kept sets,
 so the only collective on the data path is that all-reduce.
 
@@ -30,8 +30,12 @@ def kept_before(g, S, keep_prefix, K):
 
 
 def recombine_sharded(engine, n, S, group=None, device=None, max_rounds=256):
-    """Run the round loop on `engine` (count/partial/car/apply/result).  Returns this rank's
-    surviving (idx, w); concatenate over ranks (gather_result) for the full rule."""
+    """Run the pass loop on `engine` (count/cell_factor/partial/car_levels/apply/result).  Returns
+    this rank's surviving (idx, w); concatenate over ranks (gather_result) for the full rule.
+
+    A pass over F*S cells (cell = global position mod F*S, set j = cells j, j+S, ...) costs ONE
+    sweep of kernel evaluations and ONE all-reduce of the [n, F*S] cell system; its log2(F)+1
+    Caratheodory levels (engine.car_levels) shrink the candidates by 2F."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     device = device if device is not None else getattr(engine, "device", "cpu")
@@ -40,8 +44,7 @@ def recombine_sharded(engine, n, S, group=None, device=None, max_rounds=256):
     if world > 1:
         dist.all_reduce(counts, group=group)
     counts = counts.cpu().tolist()
-    A = torch.zeros(n, S, dtype=torch.float64, device=device)
-    omega = torch.zeros(S, dtype=torch.float64, device=device)
+    bufs = {}
     rounds = 0
     while sum(counts) > n:
         rounds += 1
@@ -49,27 +52,31 @@ def recombine_sharded(engine, n, S, group=None, device=None, max_rounds=256):
             raise RuntimeError("recombine_sharded: no convergence")
         R = sum(counts)
         off = sum(counts[:rank])
-        engine.partial(R, off, A)
+        F = engine.cell_factor(R, max(counts))          # same inputs on every rank -> same F
+        cells = F * S
+        A = bufs.get(F)
+        if A is None:
+            A = bufs[F] = torch.zeros(n, cells, dtype=torch.float64, device=device)
+        engine.partial(R, off, F, A)
         if world > 1:
             dist.all_reduce(A, group=group)
-        S_eff = min(S, R)
-        omega.zero_()
-        engine.car(A, S_eff, omega)
-        new_local = engine.apply(R, off, omega)
-        # every rank derives every rank's new count from the kept sets: no extra collective
-        keep = (omega[:S_eff] > 0).to(torch.int64).cpu()
-        prefix = torch.zeros(S + 1, dtype=torch.int64)
-        prefix[1:S_eff + 1] = torch.cumsum(keep, 0)
-        prefix[S_eff + 1:] = prefix[S_eff]
-        K = int(prefix[S])
+        factor = engine.car_levels(A, F, R)              # host [cells]; identical on every rank
+        new_local = engine.apply(R, off, F, factor)
+        # every rank derives every rank's new count from the kept cells: no extra collective
+        c_eff = min(cells, R)
+        keep = (factor[:c_eff] > 0).to(torch.int64)
+        prefix = torch.zeros(cells + 1, dtype=torch.int64)
+        prefix[1:c_eff + 1] = torch.cumsum(keep, 0)
+        prefix[c_eff + 1:] = prefix[c_eff]
+        K = int(prefix[cells])
         new_counts, o = [], 0
         for c in counts:
-            new_counts.append(kept_before(o + c, S, prefix, K) - kept_before(o, S, prefix, K))
+            new_counts.append(kept_before(o + c, cells, prefix, K) - kept_before(o, cells, prefix, K))
             o += c
         if new_counts[rank] != new_local:
             raise RuntimeError(f"rank {rank}: survivor count mismatch {new_counts[rank]} != {new_local}")
         if sum(new_counts) >= R:
-            raise RuntimeError("recombine_sharded: round made no progress")
+            raise RuntimeError("recombine_sharded: pass made no progress")
         counts = new_counts
     return engine.result()
 

@@ -40,7 +40,7 @@ ctx.profile(False)
 # Caratheodory on the first-round system of this workload vs a random system of the same shape
 sess = ops.Session(kern, X[: min(N, 2_000_000)], Z, U, min(N, 2_000_000), 0)
 A = torch.zeros(sess.n, sess.S, dtype=torch.float64, device=dev)
-sess.partial(sess.count(), 0, A)
+sess.partial(sess.count(), 0, 1, A)
 Ar = torch.randn(n, 2 * n, generator=torch.Generator(device=dev).manual_seed(3), device=dev, dtype=torch.float64)
 Ar[0] = Ar[0].abs() + 0.1
 for name, mat in (("round-1 system", A), ("random system", Ar)):

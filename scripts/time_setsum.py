@@ -17,7 +17,7 @@ sess = ops.Session(spec, X, Z, U, N, 0)
 A = torch.zeros(sess.n, sess.S, dtype=torch.float64, device=dev)
 ctx = _lib.context_for(dev)
 for _ in range(2):
-    sess.partial(N, 0, A)
+    sess.partial(N, 0, 1, A)
 ctx.profile(True); ctx.profile_read(True)
 reps = int(os.environ.get("REPS", "3"))
 import subprocess, threading
@@ -29,7 +29,7 @@ def sample():
 th = threading.Thread(target=sample, daemon=True)
 if reps > 5: th.start()
 for _ in range(reps):
-    sess.partial(N, 0, A)
+    sess.partial(N, 0, 1, A)
 torch.cuda.synchronize()
 stop.set()
 if reps > 5:

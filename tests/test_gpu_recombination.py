@@ -224,18 +224,34 @@ def test_staged_session_two_shards_one_gpu(bq):
     s0 = ops.Session(cov.forward, X[:cut].to(DEV), Z.to(DEV), U.to(DEV), N, 0)
     s1 = ops.Session(cov.forward, X[cut:].to(DEV), Z.to(DEV), U.to(DEV), N, cut)
     S = s0.S
-    A0 = torch.zeros(n, S, dtype=torch.float64, device=DEV); A1 = torch.zeros_like(A0)
-    omega = torch.zeros(S, dtype=torch.float64, device=DEV)
     c0, c1 = s0.count(), s1.count()
-    rounds = 0
+    rounds, factors_used = 0, set()
     while c0 + c1 > n:
         R = c0 + c1
-        s0.partial(R, 0, A0); s1.partial(R, c0, A1)
+        F = s0.cell_factor(R, max(c0, c1))
+        assert F == s1.cell_factor(R, max(c0, c1)) and (F == 1 or R >= F * S)
+        if rounds == 0:
+            F = 4                                        # exercise the refined pass whatever the policy says
+        factors_used.add(F)
+        A0 = torch.zeros(n, F * S, dtype=torch.float64, device=DEV); A1 = torch.zeros_like(A0)
+        s0.partial(R, 0, F, A0); s1.partial(R, c0, F, A1)
         A = (A0 + A1).contiguous()
-        s0.car(A, min(S, R), omega)
-        c0, c1 = s0.apply(R, 0, omega), s1.apply(R, c0, omega)
+        # the cell columns refine the set columns: folding them gives the reference's round system
+        if F > 1:
+            B0 = torch.zeros(n, S, dtype=torch.float64, device=DEV); B1 = torch.zeros_like(B0)
+            s0.partial(R, 0, 1, B0); s1.partial(R, c0, 1, B1)
+            fold = A.view(n, F, S).sum(1)
+            assert torch.allclose(fold, B0 + B1, rtol=1e-12, atol=1e-18)
+        factor = s0.car_levels(A, F, R)
+        assert int((factor > 0).sum()) <= n
+        # every level preserves the moments: sum_c factor_c A[:, c] = sum_c A[:, c]
+        lhs, rhs = A.cpu() @ factor, A.cpu().sum(1)
+        assert float(torch.linalg.norm(lhs - rhs) / torch.linalg.norm(rhs)) < 1e-11
+        c0, c1 = s0.apply(R, 0, F, factor), s1.apply(R, c0, F, factor)
+        assert c0 + c1 <= -(-R // (F * S)) * n
         rounds += 1
         assert rounds < 64
+    assert 4 in factors_used
     i0, w0 = s0.result(); i1, w1 = s1.result()
     idx, w = torch.cat([i0, i1]), torch.cat([w0, w1])
     _check_rule(idx, w, N, n)

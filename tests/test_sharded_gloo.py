@@ -32,28 +32,60 @@ class OracleEngine:
     def count(self):
         return len(self.mu)
 
-    def _sets(self, off):
-        return (off + torch.arange(len(self.mu))) % self.S
+    def cell_factor(self, R, R_loc_max):
+        F = 1
+        while F < 4 and R >= 4 * (2 * F) * self.S:
+            F *= 2
+        return F
 
-    def partial(self, R, off, A):
+    def _cells(self, off, F):
+        return (off + torch.arange(len(self.mu))) % (F * self.S)
+
+    def partial(self, R, off, F, A):
         A.zero_()
         if len(self.mu) == 0:
             return
-        sets = self._sets(off)
+        cells = self._cells(off, F)
         feats = (self.U @ self.kernel(self.Z, self.X)) * self.mu.unsqueeze(0)       # [q, R_loc]
-        A[0].index_add_(0, sets, self.mu)
-        A[1:].index_add_(1, sets, feats)
+        A[0].index_add_(0, cells, self.mu)
+        A[1:].index_add_(1, cells, feats)
 
-    def car(self, A, S_eff, omega):
-        mass = A[0, :S_eff]
-        bary = (A[1:, :S_eff] / mass.unsqueeze(0)).T
+    def _car(self, A):
+        """omega >= 0 with A omega = A 1 and <= n non-zeros (oracle Caratheodory on barycentres)."""
+        mass = A[0]
+        bary = (A[1:] / mass.unsqueeze(0)).T
         w, keep = orchq.caratheodory(bary, mass.clone())
-        omega.zero_()
+        omega = torch.zeros(A.shape[1], dtype=torch.float64)
         omega[keep] = w / mass[keep]
+        return omega
 
-    def apply(self, R, off, omega):
-        sets = self._sets(off)
-        scale = omega[sets]
+    def car_levels(self, A, F, R):
+        """The cell hierarchy of one pass (include/basq_b200.h: basq_car_levels) with the oracle's
+        Caratheodory step at every level."""
+        S, n = self.S, self.n
+        cells = F * S
+        L = F.bit_length() - 1
+        factor = torch.zeros(cells, dtype=torch.float64)
+        act = list(range(min(S, R)))
+        fac = [1.0] * len(act)
+        for lvl in range(L + 1):
+            stride, cnt = S << lvl, F >> lvl
+            cols = torch.stack([f * sum(A[:, u + k * stride] for k in range(cnt)) for u, f in zip(act, fac)], 1)
+            om = self._car(cols) if len(act) > n else torch.ones(len(act), dtype=torch.float64)
+            nact, nfac = [], []
+            for half in range(2 if lvl < L else 1):
+                for u, f, o in zip(act, fac, om.tolist()):
+                    if o > 0:
+                        if lvl < L:
+                            nact.append(u + half * stride)
+                            nfac.append(f * o)
+                        else:
+                            factor[u] = f * o
+            act, fac = nact, nfac
+        return factor
+
+    def apply(self, R, off, F, factor):
+        scale = factor[self._cells(off, F)]
         live = scale > 0
         self.X, self.mu, self.idx = self.X[live], (self.mu * scale)[live], self.idx[live]
         return len(self.mu)
