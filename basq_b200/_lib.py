@@ -67,8 +67,8 @@ def _load():
         "basq_session_apply": (I, [P, L, L, P, C.POINTER(L)]),
         "basq_session_result": (I, [P, P, P, I, C.POINTER(I)]),
         "basq_session_cell_factor": (I, [P, L, L, C.POINTER(I)]),
-        "basq_session_partial_cells": (I, [P, L, L, I, P]),
-        "basq_car_levels": (I, [P, P, I, I, I, L, P]),
+        "basq_session_pass_begin": (I, [P, L, L, I]),
+        "basq_session_level": (I, [P, I, I, P, P, P, P]),
         "basq_session_apply_cells": (I, [P, L, L, I, P, C.POINTER(L)]),
         "basq_dgemm": (I, [P, I, I, I, I, I, D, P, I, P, I, D, P, I]),
         "basq_tgemm": (I, [P, I, I, I, P, I, P, I, P, I]),

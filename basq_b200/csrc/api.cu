@@ -54,18 +54,38 @@ __global__ void model_space_kernel(int mode, double offset, int64_t n, double* _
   if (write_var) var[p] = vo;
 }
 
-// W[r, i] = fpar[i] * sum_{k < cnt} Acell[r, node[i] + k * stride]: the column of a tree node of the
-// cell hierarchy (car_levels) from the projected cell columns, in a fixed summation order
-__global__ void gather_nodes_kernel(const double* __restrict__ Acell, int64_t ldc, int n, int C,
-                                    const int* __restrict__ node, const double* __restrict__ fpar, int stride,
-                                    int cnt, double* __restrict__ W, int64_t ldw) {
+// out[m, i] = sum_{k < cnt} G[m, node[i] + k * stride]: the set-sum column of a tree node of the
+// pass's cell hierarchy (a node = every stride-th cell from node[i]) in a fixed summation order
+__global__ void fold_cols_kernel(const double* __restrict__ G, int64_t ldg, int rows, int K,
+                                 const int* __restrict__ node, int stride, int cnt, double* __restrict__ out,
+                                 int64_t ldo) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (int64_t)n * C) return;
-  const int r = (int)(t / C), i = (int)(t % C);
-  const double* src = Acell + (int64_t)r * ldc + node[i];
+  if (t >= (int64_t)rows * K) return;
+  const int m = (int)(t / K), i = (int)(t % K);
+  const double* src = G + (int64_t)m * ldg + node[i];
   double s = 0.0;
   for (int k = 0; k < cnt; ++k) s += src[(int64_t)k * stride];
-  W[(int64_t)r * ldw + i] = fpar[i] * s;
+  out[(int64_t)m * ldo + i] = s;
+}
+
+// raw[:, 0..K) holds the projected columns of the K nodes just folded.  Below level 0 they are the
+// LOW halves of the K surviving parents and the HIGH halves follow by linearity,
+// hi = parent - lo (parent = column ppos[i] of the previous level), so only half of a level's columns
+// are ever projected.  A_out = columns scaled by the parents' factors fpar.
+__global__ void level_finish_kernel(double* __restrict__ raw, const double* __restrict__ prev, int n, int K,
+                                    int below0, const int* __restrict__ ppos, const double* __restrict__ fpar,
+                                    double* __restrict__ A_out, int64_t ld) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)n * K) return;
+  const int r = (int)(t / K), i = (int)(t % K);
+  const double f = fpar[i];
+  const double lo = raw[(int64_t)r * ld + i];
+  A_out[(int64_t)r * ld + i] = f * lo;
+  if (below0) {
+    const double hi = prev[(int64_t)r * ld + ppos[i]] - lo;
+    raw[(int64_t)r * ld + K + i] = hi;
+    A_out[(int64_t)r * ld + K + i] = f * hi;
+  }
 }
 
 int check_finite_host(const double* v, int64_t n, const char* what) {
@@ -97,6 +117,14 @@ struct basq_session {
   DevBuf G;         // [Mtot, ldg]   (ldg = cells of the widest pass so far)
   int64_t ldg = 0;
   DevBuf rank;      // int [cells]
+  // state of the current pass (session_pass_begin / session_level)
+  int pass_F = 0;
+  int64_t pass_R = 0, pass_off = 0;
+  DevBuf cellmass;  // [cells] mass of every cell
+  DevBuf Gf;        // [Mtot, S] folded set-sum columns of a level
+  DevBuf raw[2];    // [n, S] unscaled local columns of the current / previous level
+  int raw_cur = 0;
+  DevBuf lnode, lppos, lfpar;  // device copies of a level's node ids, parent positions, parent factors
   DevBuf V, corrT;  // chunk buffers of the non-linear modes
   int64_t chunkP = 0;
   int64_t idx_base = 0;
@@ -240,105 +268,168 @@ int session_reserve_cells(basq_session* s, int cells) {
   s->ldg = cells;
   BASQ_TRY(s->G.alloc(ctx, sizeof(double) * (size_t)s->Mtot * s->ldg));
   BASQ_TRY(s->rank.alloc(ctx, sizeof(int) * (size_t)cells));
+  s->cellmass.release();
+  BASQ_TRY(s->cellmass.alloc(ctx, sizeof(double) * (size_t)cells));
   s->omega_host.resize(cells);
   s->rank_host.resize(cells);
   return BASQ_OK;
 }
 
-// Local part of a pass: A_out[n, F * S] (ld = F * S), column c = numerators / mass of CELL c, the
-// points whose global position = c (mod F * S).  F = 1 is the reference's round (S sets); F > 1
-// refines every set j into the F cells j, j + S, ..., so that ONE pass of kernel evaluations serves
-// log2(F) + 1 Caratheodory levels (car_levels).
-int session_partial_impl(basq_session* s, int64_t R_glob, int64_t off, int F, double* A_out) {
+// Begin a pass over F * S cells (cell of a point = global position mod F * S; set j = cells j,
+// j + S, ..., j + (F-1) S).  ONE sweep of kernel evaluations fills G[:, c] = sum over cell c of
+// w_p k(z, x_p); the log2(F) + 1 Caratheodory levels of the pass (session_level) then only fold and
+// project columns of G.  F = 1 is the reference's round (BASQ/_rchq.py:81-101).
+int session_pass_begin(basq_session* s, int64_t R_glob, int64_t off, int F) {
   basq_ctx* ctx = s->ctx;
-  const int n = s->n;
-  const int cells = F * s->S;
-  const int c_eff = (int)std::min<int64_t>(cells, R_glob);
   BASQ_CHECK(F >= 1 && F <= BASQ_MAX_CELL_FACTOR && (F & (F - 1)) == 0, BASQ_ERR_INVALID,
-             "partial: the cell factor must be a power of two <= %d (got %d)", BASQ_MAX_CELL_FACTOR, F);
+             "pass: the cell factor must be a power of two <= %d (got %d)", BASQ_MAX_CELL_FACTOR, F);
+  const int cells = F * s->S;
+  BASQ_CHECK(F == 1 || R_glob >= cells, BASQ_ERR_INVALID, "pass: refined passes need R >= F * S");
   BASQ_CHECK(off >= 0 && off + s->pool.count <= R_glob, BASQ_ERR_INVALID,
-             "partial: offset %lld + local %lld exceeds global %lld", (long long)off, (long long)s->pool.count,
+             "pass: offset %lld + local %lld exceeds global %lld", (long long)off, (long long)s->pool.count,
              (long long)R_glob);
+  BASQ_CHECK(F == 1 || s->nl == NL_LIN, BASQ_ERR_UNSUPPORTED, "pass: the non-linear modes use plain rounds (F = 1)");
+  const int c_eff = (int)std::min<int64_t>(cells, R_glob);
   BASQ_TRY(session_reserve_cells(s, cells));
-  BASQ_CUDA(cudaMemsetAsync(A_out, 0, sizeof(double) * (size_t)n * cells, ctx->stream));
-  {
-    PhaseTimer t(ctx, PH_SETSUM);
-    BASQ_TRY(set_masses(ctx, s->pool, off, cells, c_eff, A_out));
-    BASQ_TRY(session_set_sums(s, off, cells, 0, s->pool.count, s->G.as<double>(), s->ldg));
+  if (!s->Gf.p) {
+    BASQ_TRY(s->Gf.alloc(ctx, sizeof(double) * (size_t)s->Mtot * s->S));
+    for (int i = 0; i < 2; ++i) BASQ_TRY(s->raw[i].alloc(ctx, sizeof(double) * (size_t)s->n * s->S));
+    BASQ_TRY(s->lnode.alloc(ctx, sizeof(int) * s->S));
+    BASQ_TRY(s->lppos.alloc(ctx, sizeof(int) * s->S));
+    BASQ_TRY(s->lfpar.alloc(ctx, sizeof(double) * s->S));
   }
-  {
-    PhaseTimer t(ctx, PH_PROJ);
-    // rows 1..q : U' @ G   (reference: U_svd @ X_for_nys, BASQ/_rchq.py:88)
-    BASQ_TRY(dgemm(ctx, false, false, s->q, c_eff, s->Mtot, 1.0, s->Uprime.as<double>(), s->Mtot, s->G.as<double>(),
-                   s->ldg, 0.0, A_out + cells, cells));
-  }
+  s->pass_F = F;
+  s->pass_R = R_glob;
+  s->pass_off = off;
+  PhaseTimer t(ctx, PH_SETSUM);
+  BASQ_TRY(set_masses(ctx, s->pool, off, cells, c_eff, s->cellmass.as<double>()));
+  BASQ_TRY(session_set_sums(s, off, cells, 0, s->pool.count, s->G.as<double>(), s->ldg));
   return BASQ_OK;
 }
 
-// Caratheodory over the cell hierarchy of one pass.  Acell[n, F * S] (ld = F * S) holds the summed
-// cell columns.  Level 0 reduces the S sets (set j = cells j + S t, t < F) to <= n; level l + 1
-// splits every surviving node into its two halves (t = r and t = r + 2^l modulo 2^(l+1)), scales
-// them by the parent's factor and reduces those <= 2n columns to <= n again.  After the last level
-// at most n CELLS survive: factor_host[c] is the product of the factors along the path of cell c
-// (0 = dropped).  Every level is the reference's step (BASQ/_rchq.py:103-105) on a finer partition.
-int car_levels(basq_ctx* ctx, const double* Acell, int n, int S, int F, int64_t R_glob, double* factor_host) {
-  const int cells = F * S;
-  int L = 0;
-  while ((1 << L) < F) ++L;
-  const int c_eff = (int)std::min<int64_t>(cells, R_glob);
-  BASQ_CHECK(F == 1 || R_glob >= cells, BASQ_ERR_INVALID, "car_levels: refined passes need R >= F * S");
-  std::vector<int> act;
-  std::vector<double> fac;
-  const int S0 = std::min(S, c_eff);
-  act.resize(S0);
-  fac.assign(S0, 1.0);
-  for (int j = 0; j < S0; ++j) act[j] = j;
-  for (int c = 0; c < cells; ++c) factor_host[c] = 0.0;
-  DevBuf W, dnode, dfpar, omega;
-  BASQ_TRY(W.alloc(ctx, sizeof(double) * (size_t)n * S));
-  BASQ_TRY(dnode.alloc(ctx, sizeof(int) * S));
-  BASQ_TRY(dfpar.alloc(ctx, sizeof(double) * S));
-  BASQ_TRY(omega.alloc(ctx, sizeof(double) * S));
+// Local part of level `lvl` of the current pass: A_out[n, S] (ld = S, columns beyond the level's
+// count zero), row 0 = masses, rows 1..q = U' G (reference: U_svd @ X_for_nys, BASQ/_rchq.py:88).
+//   lvl 0: K columns, column i = set node[i] (all F cells of it), scaled by fpar[i].
+//   lvl > 0: 2 K columns [low halves | high halves] of the K surviving nodes of the previous level;
+//            node[i] = id of the low half (cells node[i] + k (S << lvl)), ppos[i] = the parent's column
+//            in the previous level, fpar[i] = the parent's factor; high half = parent - low half.
+int session_level(basq_session* s, int lvl, int K, const int* node_host, const int* ppos_host,
+                  const double* fpar_host, double* A_out) {
+  basq_ctx* ctx = s->ctx;
+  const int n = s->n, S = s->S, F = s->pass_F;
+  BASQ_CHECK(F >= 1 && lvl >= 0 && (1 << lvl) <= F, BASQ_ERR_INVALID, "level %d outside the pass (F = %d)", lvl, F);
+  const int C = lvl == 0 ? K : 2 * K;
+  BASQ_CHECK(K >= 1 && C <= S, BASQ_ERR_INVALID, "level %d: %d columns exceed S = %d", lvl, C, S);
+  const int stride = S << lvl, cnt = F >> lvl;
+  for (int i = 0; i < K; ++i)
+    BASQ_CHECK(node_host[i] >= 0 && node_host[i] < stride && (lvl == 0 || (ppos_host[i] >= 0 && ppos_host[i] < S)),
+               BASQ_ERR_INVALID, "level %d: bad node %d", lvl, i);
+  PhaseTimer t(ctx, PH_PROJ);
+  BASQ_CUDA(cudaMemcpyAsync(s->lnode.p, node_host, sizeof(int) * K, cudaMemcpyHostToDevice, ctx->stream));
+  if (lvl > 0) BASQ_CUDA(cudaMemcpyAsync(s->lppos.p, ppos_host, sizeof(int) * K, cudaMemcpyHostToDevice, ctx->stream));
+  BASQ_CUDA(cudaMemcpyAsync(s->lfpar.p, fpar_host, sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
+  BASQ_CUDA(cudaMemsetAsync(A_out, 0, sizeof(double) * (size_t)n * S, ctx->stream));
+  double* raw = s->raw[s->raw_cur].as<double>();
+  const double* prev = s->raw[s->raw_cur ^ 1].as<double>();
+  const double* Gsrc = s->G.as<double>();
+  int64_t ldsrc = s->ldg;
+  bool identity = (cnt == 1 && lvl == 0);  // plain round: the sets ARE the cells, project G as it is
+  for (int i = 0; identity && i < K; ++i) identity = node_host[i] == i;
+  if (!identity) {
+    fold_cols_kernel<<<(unsigned)ceil_div64((int64_t)s->Mtot * K, 256), 256, 0, ctx->stream>>>(
+        s->G.as<double>(), s->ldg, s->Mtot, K, s->lnode.as<int>(), stride, cnt, s->Gf.as<double>(), S);
+    ctx->launches++;
+    Gsrc = s->Gf.as<double>();
+    ldsrc = S;
+  }
+  fold_cols_kernel<<<(unsigned)ceil_div64(K, 256), 256, 0, ctx->stream>>>(s->cellmass.as<double>(), 0, 1, K,
+                                                                          s->lnode.as<int>(), stride, cnt, raw, S);
+  ctx->launches++;
+  BASQ_CUDA(cudaGetLastError());
+  BASQ_TRY(dgemm(ctx, false, false, s->q, K, s->Mtot, 1.0, s->Uprime.as<double>(), s->Mtot, Gsrc, ldsrc, 0.0, raw + S, S));
+  level_finish_kernel<<<(unsigned)ceil_div64((int64_t)n * K, 256), 256, 0, ctx->stream>>>(
+      raw, prev, n, K, lvl > 0 ? 1 : 0, s->lppos.as<int>(), s->lfpar.as<double>(), A_out, S);
+  ctx->launches++;
+  BASQ_CUDA(cudaGetLastError());
+  // the host arrays may be reused by the caller as soon as we return
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  s->raw_cur ^= 1;
+  return BASQ_OK;
+}
+
+// Host bookkeeping of a pass's level tree, shared by the single-call loop (recombine_impl) and
+// mirrored by basq_b200/sharded.py: which nodes are presented to the next Caratheodory level.
+struct LevelTree {
+  int S = 0, F = 1, L = 0, lvl = 0;
+  std::vector<int> act;      // node id of every column of the current level
+  std::vector<double> fac;   // factor of every column's parent (1 at level 0)
+  std::vector<int> node, ppos;
+  std::vector<double> fpar;  // arguments of session_level for the current level
+  void begin(int S_, int F_, int64_t R_glob) {
+    S = S_; F = F_; lvl = 0; L = 0;
+    while ((1 << L) < F) ++L;
+    const int S0 = (int)std::min<int64_t>(S, R_glob);
+    node.resize(S0); ppos.assign(S0, 0); fpar.assign(S0, 1.0);
+    for (int j = 0; j < S0; ++j) node[j] = j;
+    act = node; fac = fpar;
+  }
+  int columns() const { return (int)act.size(); }
+  // consume the level's factors om[columns()] (1 = untouched); returns false after the last level,
+  // when factor_host[F * S] has received the product of the factors along every surviving path
+  bool advance(const double* om, double* factor_host, int* kept_out) {
+    const int C = columns();
+    const int stride = S << lvl;
+    std::vector<int> nnode, nppos;
+    std::vector<double> nfpar;
+    for (int i = 0; i < C; ++i) {
+      const double f = fac[i] * om[i];
+      if (!(om[i] > 0.0) || !(f > 0.0)) continue;
+      if (lvl < L) { nnode.push_back(act[i]); nppos.push_back(i); nfpar.push_back(f); }
+      else factor_host[act[i]] = f;
+      ++*kept_out;
+    }
+    if (lvl == L) return false;
+    node.swap(nnode); ppos.swap(nppos); fpar.swap(nfpar);
+    const int K = (int)node.size();
+    act.resize(2 * K); fac.resize(2 * K);
+    for (int i = 0; i < K; ++i) {
+      act[i] = node[i]; act[K + i] = node[i] + stride;
+      fac[i] = fac[K + i] = fpar[i];
+    }
+    ++lvl;
+    return true;
+  }
+};
+
+// All levels of the current pass for a single rank: factor_host[F * S] out.
+int session_pass_levels(basq_session* s, double* A, double* omega_dev, double* factor_host) {
+  basq_ctx* ctx = s->ctx;
+  const int n = s->n, S = s->S, F = s->pass_F;
+  for (int c = 0; c < F * S; ++c) factor_host[c] = 0.0;
+  LevelTree tree;
+  tree.begin(S, F, s->pass_R);
   std::vector<double> om(S);
-  for (int lvl = 0; lvl <= L; ++lvl) {
-    const int C = (int)act.size();
-    BASQ_CHECK(C >= 1 && C <= S, BASQ_ERR_NUMERIC, "car_levels: %d active nodes at level %d", C, lvl);
-    const int stride = S << lvl, cnt = F >> lvl;
+  for (;;) {
+    const int K = (int)tree.node.size();
+    BASQ_CHECK(K >= 1, BASQ_ERR_NUMERIC, "pass: no active node at level %d", tree.lvl);
+    const int C = tree.columns();
     if (C > n) {
-      {
-        PhaseTimer t(ctx, PH_CAR);
-        BASQ_CUDA(cudaMemcpyAsync(dnode.p, act.data(), sizeof(int) * C, cudaMemcpyHostToDevice, ctx->stream));
-        BASQ_CUDA(cudaMemcpyAsync(dfpar.p, fac.data(), sizeof(double) * C, cudaMemcpyHostToDevice, ctx->stream));
-        gather_nodes_kernel<<<(unsigned)ceil_div64((int64_t)n * C, 256), 256, 0, ctx->stream>>>(
-            Acell, cells, n, C, dnode.as<int>(), dfpar.as<double>(), stride, cnt, W.as<double>(), S);
-        ctx->launches++;
-        BASQ_CUDA(cudaGetLastError());
-      }
-      BASQ_TRY(caratheodory(ctx, W.as<double>(), n, C, S, omega.as<double>()));
-      BASQ_CUDA(cudaMemcpyAsync(om.data(), omega.p, sizeof(double) * C, cudaMemcpyDeviceToHost, ctx->stream));
+      BASQ_TRY(session_level(s, tree.lvl, K, tree.node.data(), tree.ppos.data(), tree.fpar.data(), A));
+      BASQ_TRY(caratheodory(ctx, A, n, C, S, omega_dev));
+      BASQ_CUDA(cudaMemcpyAsync(om.data(), omega_dev, sizeof(double) * C, cudaMemcpyDeviceToHost, ctx->stream));
       BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
       BASQ_TRY(check_finite_host(om.data(), C, "omega"));
     } else {
+      // nothing to eliminate at this level; deeper levels still need this level's raw columns
+      if (tree.lvl < tree.L)
+        BASQ_TRY(session_level(s, tree.lvl, K, tree.node.data(), tree.ppos.data(), tree.fpar.data(), A));
       for (int i = 0; i < C; ++i) om[i] = 1.0;
     }
-    std::vector<int> nact;
-    std::vector<double> nfac;
     int kept = 0;
-    for (int half = 0; half < (lvl < L ? 2 : 1); ++half)
-      for (int i = 0; i < C; ++i) {
-        const double f = fac[i] * om[i];
-        if (!(om[i] > 0.0) || !(f > 0.0)) continue;
-        if (half == 0) ++kept;
-        if (lvl < L) {
-          nact.push_back(act[i] + half * stride);
-          nfac.push_back(f);
-        } else {
-          factor_host[act[i]] = f;
-        }
-      }
-    BASQ_CHECK(kept >= 1, BASQ_ERR_NUMERIC, "car_levels: the Caratheodory step kept no set (level %d)", lvl);
-    act.swap(nact);
-    fac.swap(nfac);
+    const int lvl = tree.lvl;
+    const bool more = tree.advance(om.data(), factor_host, &kept);
+    BASQ_CHECK(kept >= 1, BASQ_ERR_NUMERIC, "pass: the Caratheodory step kept no set (level %d)", lvl);
+    if (!more) break;
   }
   return BASQ_OK;
 }
@@ -378,25 +469,31 @@ int session_apply_impl(basq_session* s, int64_t R_glob, int64_t off, int F, cons
   return BASQ_OK;
 }
 
-// Cell factor of a pass over R_loc local points (R_glob in total): refining costs one projection
-// column per extra cell and saves the kernel evaluations of the rounds it replaces, so it pays
-// while the local set-sum work (Mtot * R_loc evaluations) dominates the projection (2 q Mtot S F flop).
+// Cell factor of a pass over R_glob points (at most R_loc_max on one rank).  A pass with F = 2^L
+// costs one sweep of Mtot * R_loc kernel evaluations (tiles of 32 members per cell: short cells
+// waste slots) plus (1 + L/2) projections of S columns, and replaces L + 1 rounds: pick the F with
+// the lowest cost per level.  One evaluation ~ 4.4 fp64-GEMM flop at the measured kernel rates.
 int choose_cell_factor(const basq_session* s, int64_t R_glob, int64_t R_loc_max) {
   static const int forced = [] { const char* e = getenv("BASQ_CELL_FACTOR"); return e ? atoi(e) : 0; }();
-  const int64_t S = s->S, qS = (int64_t)s->q * s->S;
+  if (s->nl != NL_LIN) return 1;  // the chunked non-linear path keeps the plain round
+  const int64_t S = s->S;
   auto fits = [&](int f) { return R_glob >= (int64_t)4 * f * S; };
-  int F = 1;
   if (forced >= 1) {
+    int F = 1;
     while (F * 2 <= forced && F * 2 <= BASQ_MAX_CELL_FACTOR && fits(F * 2)) F *= 2;
-  } else {
-    // one evaluation costs about 4.4 fp64-GEMM flop at the measured rates: going from F/2 to F saves
-    // R_loc Mtot / F evaluations and adds (F/2 - 1) projections of 2 q Mtot S flop
-    if (fits(2)) F = 2;
-    if (fits(4) && R_loc_max > qS) F = 4;
-    if (fits(8) && R_loc_max > 6 * qS) F = 8;
+    return F;
   }
-  if (s->nl != NL_LIN) F = 1;  // the chunked non-linear path keeps the plain round
-  return F;
+  const double proj = 2.0 * s->q * (double)S / 4.4;  // one projection of S columns, in evaluations per landmark
+  int best = 1;
+  double best_cost = 0.0;
+  for (int F = 1, L = 0; F <= BASQ_MAX_CELL_FACTOR; F *= 2, ++L) {
+    if (F > 1 && !fits(F)) break;
+    const double members = (double)R_loc_max / ((double)F * S);          // local members per cell
+    const double slots = 32.0 * ceil(std::max(members, 1e-9) / 32.0);    // tile slots they occupy
+    const double cost = ((double)R_loc_max * (slots / std::max(members, 1e-9)) + proj * (1.0 + 0.5 * L)) / (L + 1);
+    if (F == 1 || cost < best_cost) { best = F; best_cost = cost; }
+  }
+  return best;
 }
 
 // Phi[p_lo..p_hi, q] for the session's live records
@@ -426,24 +523,19 @@ int recombine_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, i
   BASQ_TRY(session_create_impl(ctx, desc, X, N, N, 0, Z, M, U, q, mu, 0, s.get()));
   trace_point(ctx, "recombine: session created");
   const int n = s->n, S = s->S;
-  DevBuf A;
+  DevBuf A, omega;
+  BASQ_TRY(A.alloc(ctx, sizeof(double) * (size_t)n * S));
+  BASQ_TRY(omega.alloc(ctx, sizeof(double) * S));
   int64_t R = s->pool.count;
   std::vector<double> factor;
-  int rounds = 0, a_cells = 0;
+  int rounds = 0;
   while (R > n) {
-    BASQ_CHECK(++rounds <= 256, BASQ_ERR_NUMERIC, "recombine: no convergence after 256 rounds");
+    BASQ_CHECK(++rounds <= 256, BASQ_ERR_NUMERIC, "recombine: no convergence after 256 passes");
     const int F = choose_cell_factor(s.get(), R, R);
-    const int cells = F * S;
-    if (cells > a_cells) {
-      BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
-      A.release();
-      BASQ_TRY(A.alloc(ctx, sizeof(double) * (size_t)n * cells));
-      a_cells = cells;
-      factor.resize(cells);
-    }
-    BASQ_TRY(session_partial_impl(s.get(), R, 0, F, A.as<double>()));
-    trace_point(ctx, "  pass: partial");
-    BASQ_TRY(car_levels(ctx, A.as<double>(), n, S, F, R, factor.data()));
+    factor.resize((size_t)F * S);
+    BASQ_TRY(session_pass_begin(s.get(), R, 0, F));
+    trace_point(ctx, "  pass: set sums");
+    BASQ_TRY(session_pass_levels(s.get(), A.as<double>(), omega.as<double>(), factor.data()));
     trace_point(ctx, "  pass: caratheodory levels");
     int64_t Rn = 0;
     BASQ_TRY(session_apply_impl(s.get(), R, 0, F, factor.data(), &Rn));
@@ -573,6 +665,17 @@ int basq_gram(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_
   BASQ_CHECK(ctx && desc && X && Y && out, BASQ_ERR_INVALID, "basq_gram: NULL argument");
   BASQ_CHECK(a >= 1 && b >= 1, BASQ_ERR_INVALID, "basq_gram: empty operand");
   BASQ_CUDA(cudaSetDevice(ctx->device));
+  return basq::gram_matrix(ctx, desc, X, a, Y, b, out, false);
+}
+
+}  // extern "C"
+
+// kernel(X, Y) [a, b] in fp64.  tensor_correction: the posterior-covariance correction
+// (K_xX W) K_Xy - an [a, n_obs] x [n_obs, b] product - runs on the tensor cores with fp32 accuracy
+// (tgemm.cu).  Only the Nystrom range finder asks for that: its products with this matrix are
+// 3xTF32 as well, and only the span of the resulting basis matters.
+int basq::gram_matrix(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t a, const void* Y, int64_t b,
+                      double* out, bool tensor_correction) {
   KParams kp;
   BASQ_TRY(make_kparams(desc, &kp));
   BASQ_TRY(compute_center(ctx, desc, X, a, &kp));
@@ -593,8 +696,18 @@ int basq_gram(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_
     BASQ_CHECK(a < (1ll << 31) && b < (1ll << 31), BASQ_ERR_UNSUPPORTED, "basq_gram: operand too large");
     BASQ_TRY(dgemm(ctx, false, false, (int)a, n_obs, n_obs, 1.0, KxX.as<double>(), n_obs, desc->W, n_obs, 0.0,
                    T.as<double>(), n_obs));
-    BASQ_TRY(dgemm(ctx, false, false, (int)a, (int)b, n_obs, -1.0, T.as<double>(), n_obs, KXy.as<double>(), b, 1.0,
-                   out, b));
+    if (tensor_correction && desc->dtype == BASQ_F32) {
+      BlkOperand Tb, Yb;
+      BASQ_TRY(Tb.alloc(ctx, (int)a, n_obs));
+      BASQ_TRY(Yb.alloc(ctx, (int)b, n_obs));
+      BASQ_TRY(blk_from_f64(ctx, T.as<double>(), n_obs, false, &Tb));
+      BASQ_TRY(blk_from_f64(ctx, KXy.as<double>(), b, true, &Yb));   // K_Xy^T as [b, n_obs] operand
+      BASQ_TRY(tgemm(ctx, Tb, Yb, -1.0, out, b, false, /*accumulate=*/true));
+      BASQ_CUDA(cudaStreamSynchronize(ctx->stream));                 // operands go out of scope
+    } else {
+      BASQ_TRY(dgemm(ctx, false, false, (int)a, (int)b, n_obs, -1.0, T.as<double>(), n_obs, KXy.as<double>(), b, 1.0,
+                     out, b));
+    }
     const bool warped = (mode == BASQ_WSABI_L || mode == BASQ_WSABI_M || mode == BASQ_MMLT_G);
     if (warped) {
       BASQ_TRY(fx.alloc(ctx, sizeof(double) * a));
@@ -620,6 +733,8 @@ int basq_gram(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_
   BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
   return BASQ_OK;
 }
+
+extern "C" {
 
 int basq_gp_predict(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t N, int space, double offset,
                     double* mean_out, double* var_out) {
@@ -767,13 +882,10 @@ int basq_session_count(const basq_session* s, int64_t* R_loc_host) {
 int basq_session_partial(basq_session* s, int64_t R_glob, int64_t off_glob, double* A_out) {
   BASQ_CHECK(s && A_out, BASQ_ERR_INVALID, "NULL argument");
   BASQ_CUDA(cudaSetDevice(s->ctx->device));
-  return session_partial_impl(s, R_glob, off_glob, 1, A_out);
-}
-
-int basq_session_partial_cells(basq_session* s, int64_t R_glob, int64_t off_glob, int F, double* A_out) {
-  BASQ_CHECK(s && A_out, BASQ_ERR_INVALID, "NULL argument");
-  BASQ_CUDA(cudaSetDevice(s->ctx->device));
-  return session_partial_impl(s, R_glob, off_glob, F, A_out);
+  BASQ_TRY(session_pass_begin(s, R_glob, off_glob, 1));
+  LevelTree tree;
+  tree.begin(s->S, 1, R_glob);
+  return session_level(s, 0, (int)tree.node.size(), tree.node.data(), tree.ppos.data(), tree.fpar.data(), A_out);
 }
 
 int basq_session_cell_factor(const basq_session* s, int64_t R_glob, int64_t R_loc_max, int* F_out_host) {
@@ -782,13 +894,17 @@ int basq_session_cell_factor(const basq_session* s, int64_t R_glob, int64_t R_lo
   return BASQ_OK;
 }
 
-int basq_car_levels(basq_ctx* ctx, const double* A_cells, int n, int S, int F, int64_t R_glob,
-                    double* factor_out_host) {
-  BASQ_CHECK(ctx && A_cells && factor_out_host, BASQ_ERR_INVALID, "basq_car_levels: NULL argument");
-  BASQ_CHECK(n >= 1 && S >= 1 && F >= 1 && F <= BASQ_MAX_CELL_FACTOR && (F & (F - 1)) == 0, BASQ_ERR_INVALID,
-             "basq_car_levels: bad shape n=%d S=%d F=%d", n, S, F);
-  BASQ_CUDA(cudaSetDevice(ctx->device));
-  return car_levels(ctx, A_cells, n, S, F, R_glob, factor_out_host);
+int basq_session_pass_begin(basq_session* s, int64_t R_glob, int64_t off_glob, int F) {
+  BASQ_CHECK(s, BASQ_ERR_INVALID, "NULL argument");
+  BASQ_CUDA(cudaSetDevice(s->ctx->device));
+  return session_pass_begin(s, R_glob, off_glob, F);
+}
+
+int basq_session_level(basq_session* s, int lvl, int K, const int* node_host, const int* ppos_host,
+                       const double* fpar_host, double* A_out) {
+  BASQ_CHECK(s && node_host && fpar_host && A_out && (lvl == 0 || ppos_host), BASQ_ERR_INVALID, "NULL argument");
+  BASQ_CUDA(cudaSetDevice(s->ctx->device));
+  return session_level(s, lvl, K, node_host, ppos_host, fpar_host, A_out);
 }
 
 int basq_session_apply(basq_session* s, int64_t R_glob, int64_t off_glob, const double* omega,

@@ -390,6 +390,10 @@ int dgemm(basq_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, co
 // car.cu
 int caratheodory(basq_ctx* ctx, double* A, int n, int S, int lda, double* omega_out);
 
+// api.cu: kernel(X, Y) [a, b] in fp64 (the body of basq_gram)
+int gram_matrix(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t a, const void* Y, int64_t b,
+                double* out, bool tensor_correction);
+
 // nystrom.cu
 int nystrom_basis(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, int64_t M, int q,
                   const double* Omega, int niter, double* U_out, double* S_out);

@@ -42,6 +42,7 @@ struct TgDev {
   int64_t ldo;
   int transposed;  // 0: out[i * ldo + j] ; 1: out[j * ldo + i]
   double alpha;
+  int accumulate;  // out += alpha * A B^T instead of out = ...
 };
 
 __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const TgDev a) {
@@ -159,12 +160,19 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_kernel(const TgDev a) {
           if (a.transposed) {
 #pragma unroll
             for (int c = 0; c < 32; ++c)
-              if (j0 + c < a.J) a.out[(int64_t)(j0 + c) * a.ldo + i] = a.alpha * (double)__uint_as_float(v[c]);
+              if (j0 + c < a.J) {
+                double* dst = a.out + (int64_t)(j0 + c) * a.ldo + i;
+                const double val = a.alpha * (double)__uint_as_float(v[c]);
+                *dst = a.accumulate ? *dst + val : val;
+              }
           } else {
             double* dst = a.out + (int64_t)i * a.ldo + j0;
 #pragma unroll
             for (int c = 0; c < 32; ++c)
-              if (j0 + c < a.J) dst[c] = a.alpha * (double)__uint_as_float(v[c]);
+              if (j0 + c < a.J) {
+                const double val = a.alpha * (double)__uint_as_float(v[c]);
+                dst[c] = a.accumulate ? dst[c] + val : val;
+              }
           }
         }
       }
@@ -236,7 +244,7 @@ int blk_from_f64(basq_ctx* ctx, const double* src, int64_t ld, bool transposed, 
 }
 
 int tgemm(basq_ctx* ctx, const BlkOperand& A, const BlkOperand& B, double alpha, double* out, int64_t ldo,
-          bool transposed) {
+          bool transposed, bool accumulate) {
   BASQ_CHECK(A.kdim == B.kdim && A.KC == B.KC, BASQ_ERR_INVALID, "tgemm: inner dimensions differ (%d vs %d)", A.kdim,
              B.kdim);
   BASQ_CHECK((size_t)TG_SMEM <= ctx->smem_optin, BASQ_ERR_UNSUPPORTED, "tgemm: needs %d B shared memory", TG_SMEM);
@@ -250,6 +258,7 @@ int tgemm(basq_ctx* ctx, const BlkOperand& A, const BlkOperand& B, double alpha,
   d.out = out; d.ldo = ldo;
   d.transposed = transposed ? 1 : 0;
   d.alpha = alpha;
+  d.accumulate = accumulate ? 1 : 0;
   const int n_items = A.RT * ((B.RT + 1) / 2);
   BASQ_CUDA(cudaFuncSetAttribute(tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
   const int grid = std::min(ctx->num_sms, n_items);

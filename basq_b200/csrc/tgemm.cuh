@@ -19,8 +19,8 @@ struct BlkOperand {
 int blk_from_f64(basq_ctx* ctx, const double* src, int64_t ld, bool transposed, BlkOperand* op);
 
 // out = alpha * A B^T  ([A.rows, B.rows], fp64, row-major with leading dimension ldo), or its
-// transpose ([B.rows, A.rows]) when `transposed`.
+// transpose ([B.rows, A.rows]) when `transposed`; `accumulate` adds to out instead of overwriting it.
 int tgemm(basq_ctx* ctx, const BlkOperand& A, const BlkOperand& B, double alpha, double* out, int64_t ldo,
-          bool transposed);
+          bool transposed, bool accumulate = false);
 
 }  // namespace basq

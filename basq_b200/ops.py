@@ -203,17 +203,26 @@ class Session:
         _lib.check(_lib.lib.basq_session_cell_factor(self.handle, int(R_glob), int(R_loc_max), C.byref(f)))
         return int(f.value)
 
-    def partial(self, R_glob, off_glob, F, A: torch.Tensor):
-        """Local part of the pass's cell system A [n, F*S] (sum over ranks before car_levels)."""
-        assert A.dtype == torch.float64 and A.is_contiguous() and A.shape == (self.n, F * self.S)
-        _lib.check(_lib.lib.basq_session_partial_cells(self.handle, int(R_glob), int(off_glob), int(F), A.data_ptr()))
+    def partial(self, R_glob, off_glob, A: torch.Tensor):
+        """The reference's round: local part of the [n, S] barycentre system (pass with F = 1)."""
+        assert A.dtype == torch.float64 and A.is_contiguous() and A.shape == (self.n, self.S)
+        _lib.check(_lib.lib.basq_session_partial(self.handle, int(R_glob), int(off_glob), A.data_ptr()))
 
-    def car_levels(self, A: torch.Tensor, F, R_glob) -> torch.Tensor:
-        """Per-cell factors (HOST fp64 [F*S], 0 = dropped) of the pass's Caratheodory levels."""
-        factor = torch.zeros(F * self.S, dtype=torch.float64)
-        _lib.check(_lib.lib.basq_car_levels(self.ctx.handle, A.data_ptr(), self.n, self.S, int(F), int(R_glob),
-                                            factor.data_ptr()))
-        return factor
+    def pass_begin(self, R_glob, off_glob, F):
+        """The sweep of a pass: cell sums of this rank's live points over F*S cells."""
+        _lib.check(_lib.lib.basq_session_pass_begin(self.handle, int(R_glob), int(off_glob), int(F)))
+
+    def level(self, lvl, node, ppos, fpar, A: torch.Tensor):
+        """Local part of level `lvl` of the current pass into A [n, S] (see basq_session_level)."""
+        assert A.dtype == torch.float64 and A.is_contiguous() and A.shape == (self.n, self.S)
+        K = len(node)
+        nd = (C.c_int * K)(*node)
+        pp = (C.c_int * K)(*(ppos if lvl > 0 else [0] * K))
+        fp = (C.c_double * K)(*fpar)
+        _lib.check(_lib.lib.basq_session_level(self.handle, int(lvl), K, nd, pp, fp, A.data_ptr()))
+
+    def car(self, A: torch.Tensor, C_cols: int, omega: torch.Tensor):
+        _lib.check(_lib.lib.basq_car(self.ctx.handle, A.data_ptr(), self.n, int(C_cols), self.S, omega.data_ptr(), None))
 
     def apply(self, R_glob, off_glob, F, factor: torch.Tensor) -> int:
         c = C.c_int64(0)

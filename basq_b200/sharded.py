@@ -1,9 +1,10 @@
 """Recombination of a candidate set sharded over ranks (one process per GPU).
 
 Per Tchernychova-Lyons pass every rank forms the barycentre numerators of ITS points
-(cell = global position mod F*S), one all-reduce sums the small [n, F*S] system over NVLink, every
-rank runs the same deterministic Caratheodory levels on the identical reduced system, and rescales /
-compacts its own shard.  Counts and offsets after a round follow analytically from the kept sets,
+(cell = global position mod F*S) in one sweep of kernel evaluations; for each of the pass's
+Caratheodory levels one all-reduce sums the small [n, S] system over NVLink, every rank runs the
+same deterministic Caratheodory kernel on the identical reduced system, and at the end of the pass
+rescales / compacts its own shard.  Counts and offsets after a round follow analytically from the kept sets,
 so the only collective on the data path is that all-reduce.
 
 The loop is written against a tiny engine interface so the host logic can be exercised on CPU with
@@ -29,13 +30,50 @@ def kept_before(g, S, keep_prefix, K):
     return e * K + int(keep_prefix[j])
 
 
+class LevelTree:
+    """Host bookkeeping of one pass (mirror of LevelTree in csrc/api.cu): which nodes of the cell
+    hierarchy are presented to the next Caratheodory level.  Node u of level l = cells
+    u + k * S * 2^l; its children are u (low half) and u + S * 2^l (high half)."""
+
+    def __init__(self, S, F, R_glob):
+        self.S, self.F, self.L, self.lvl = S, F, F.bit_length() - 1, 0
+        S0 = min(S, R_glob)
+        self.node, self.ppos, self.fpar = list(range(S0)), [0] * S0, [1.0] * S0
+        self.act, self.fac = list(self.node), list(self.fpar)
+
+    def columns(self):
+        return len(self.act)
+
+    def advance(self, om, factor):
+        """Consume the level's factors om (1 = untouched).  Returns (more_levels, kept); after the
+        last level `factor` [F*S] holds the product of the factors along every surviving path."""
+        stride = self.S << self.lvl
+        node, ppos, fpar, kept = [], [], [], 0
+        for i, (u, f0, o) in enumerate(zip(self.act, self.fac, om)):
+            f = f0 * o
+            if not (o > 0.0 and f > 0.0):
+                continue
+            kept += 1
+            if self.lvl < self.L:
+                node.append(u); ppos.append(i); fpar.append(f)
+            else:
+                factor[u] = f
+        if self.lvl == self.L:
+            return False, kept
+        self.node, self.ppos, self.fpar = node, ppos, fpar
+        self.act = node + [u + stride for u in node]
+        self.fac = fpar + fpar
+        self.lvl += 1
+        return True, kept
+
+
 def recombine_sharded(engine, n, S, group=None, device=None, max_rounds=256):
-    """Run the pass loop on `engine` (count/cell_factor/partial/car_levels/apply/result).  Returns
-    this rank's surviving (idx, w); concatenate over ranks (gather_result) for the full rule.
+    """Run the pass loop on `engine` (count/cell_factor/pass_begin/level/car/apply/result).
+    Returns this rank's surviving (idx, w); concatenate over ranks (gather_result) for the full rule.
 
     A pass over F*S cells (cell = global position mod F*S, set j = cells j, j+S, ...) costs ONE
-    sweep of kernel evaluations and ONE all-reduce of the [n, F*S] cell system; its log2(F)+1
-    Caratheodory levels (engine.car_levels) shrink the candidates by 2F."""
+    sweep of kernel evaluations; each of its log2(F)+1 Caratheodory levels all-reduces one small
+    [n, S] system, and the candidates shrink by 2F."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     device = device if device is not None else getattr(engine, "device", "cpu")
@@ -44,7 +82,8 @@ def recombine_sharded(engine, n, S, group=None, device=None, max_rounds=256):
     if world > 1:
         dist.all_reduce(counts, group=group)
     counts = counts.cpu().tolist()
-    bufs = {}
+    A = torch.zeros(n, S, dtype=torch.float64, device=device)
+    omega = torch.zeros(S, dtype=torch.float64, device=device)
     rounds = 0
     while sum(counts) > n:
         rounds += 1
@@ -54,13 +93,25 @@ def recombine_sharded(engine, n, S, group=None, device=None, max_rounds=256):
         off = sum(counts[:rank])
         F = engine.cell_factor(R, max(counts))          # same inputs on every rank -> same F
         cells = F * S
-        A = bufs.get(F)
-        if A is None:
-            A = bufs[F] = torch.zeros(n, cells, dtype=torch.float64, device=device)
-        engine.partial(R, off, F, A)
-        if world > 1:
-            dist.all_reduce(A, group=group)
-        factor = engine.car_levels(A, F, R)              # host [cells]; identical on every rank
+        engine.pass_begin(R, off, F)
+        factor = torch.zeros(cells, dtype=torch.float64)
+        tree = LevelTree(S, F, R)
+        while True:
+            C = tree.columns()
+            if C > n or tree.lvl < tree.L:
+                engine.level(tree.lvl, tree.node, tree.ppos, tree.fpar, A)
+            if C > n:
+                if world > 1:
+                    dist.all_reduce(A, group=group)
+                engine.car(A, C, omega)                   # identical system -> identical factors on every rank
+                om = omega[:C].cpu().tolist()
+            else:
+                om = [1.0] * C
+            more, kept = tree.advance(om, factor)
+            if kept < 1:
+                raise RuntimeError("recombine_sharded: the Caratheodory step kept no set")
+            if not more:
+                break
         new_local = engine.apply(R, off, F, factor)
         # every rank derives every rank's new count from the kept cells: no extra collective
         c_eff = min(cells, R)

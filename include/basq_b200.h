@@ -26,7 +26,7 @@ extern "C" {
 
 #define BASQ_ABI_VERSION 1
 #define BASQ_MAX_DIM 32
-#define BASQ_MAX_CELL_FACTOR 8 /* cells per set in a refined pass (basq_session_partial_cells) */
+#define BASQ_MAX_CELL_FACTOR 16 /* cells per set in a refined pass (basq_session_partial_cells) */
 
 enum basq_status {
   BASQ_OK = 0,
@@ -149,22 +149,27 @@ int basq_session_apply(basq_session* s, int64_t R_glob, int64_t off_glob, const 
 /* surviving local points: global indices (ascending) and weights; cap = capacity of the outputs */
 int basq_session_result(basq_session* s, int64_t* idx_out, double* w_out, int cap, int* n_out_host);
 
-/* ---- refined passes: one pass of kernel evaluations, log2(F) + 1 Caratheodory levels -------- */
+/* ---- refined passes: one sweep of kernel evaluations, log2(F) + 1 Caratheodory levels ------- */
 /* A pass may refine every set j into the F cells j, j + S, ..., j + (F-1) S (cell of a point =
-   global position mod F*S; F a power of two <= BASQ_MAX_CELL_FACTOR, R_glob >= F*S).  The cell
-   columns are linear in the points, so the set columns of the reference's round (BASQ/_rchq.py:81-101)
-   are their sums, and after the round the two halves of every surviving set form the next round's
-   sets WITHOUT new kernel evaluations: the candidates shrink by 2F per pass instead of 2. */
+   global position mod F*S; F a power of two <= BASQ_MAX_CELL_FACTOR, R_glob >= F*S).  The cell sums
+   G[:, c] = sum_{p in c} w_p k(Z, x_p) are linear in the points, so the set columns of the reference's
+   round (BASQ/_rchq.py:81-101) are sums of cell columns, and after the round the two halves of every
+   surviving set form the next round's sets WITHOUT new kernel evaluations: the candidates shrink by
+   2F per sweep instead of 2.  Level l works on NODES: node u < S * 2^l = cells u + k * S * 2^l;
+   its children at level l + 1 are u (low half) and u + S * 2^l (high half). */
 /* F the library would pick for a pass over R_glob live points, R_loc_max = largest rank-local count */
 int basq_session_cell_factor(const basq_session* s, int64_t R_glob, int64_t R_loc_max, int* F_out_host);
-/* A_out[n, F*S] (ld = F*S): local part of the cell system.  Sum over ranks before basq_car_levels. */
-int basq_session_partial_cells(basq_session* s, int64_t R_glob, int64_t off_glob, int F, double* A_out);
-/* The Caratheodory levels of one pass on the summed cell system (device, not modified).
-   factor_out_host[F*S] (HOST): product of the per-level factors of each cell, 0 = dropped; at most n
-   cells survive.  Deterministic: identical inputs give identical factors on every rank. */
-int basq_car_levels(basq_ctx* ctx, const double* A_cells, int n, int S, int F, int64_t R_glob,
-                    double* factor_out_host);
-/* Rescale the kept cells by factor_host[F*S] (HOST), drop the rest, compact.  New local count out. */
+/* The sweep: cell sums and cell masses of this rank's live points (kept inside the session). */
+int basq_session_pass_begin(basq_session* s, int64_t R_glob, int64_t off_glob, int F);
+/* Local part of level lvl's system, A_out[n, S] (device, ld = S, unused columns zero): row 0 = masses,
+   rows 1..q = U' G.  lvl 0: K columns, column i = set node_host[i] scaled by fpar_host[i] (ppos unused).
+   lvl > 0: 2K columns [low halves | high halves] of the K survivors of level lvl - 1: node_host[i] =
+   low child id, ppos_host[i] = the parent's column in level lvl - 1, fpar_host[i] = the parent's
+   accumulated factor.  Levels must be requested in order.  Sum A over ranks, then basq_car. */
+int basq_session_level(basq_session* s, int lvl, int K, const int* node_host, const int* ppos_host,
+                       const double* fpar_host, double* A_out);
+/* Rescale the kept cells by factor_host[F*S] (HOST; product of the level factors along each cell's
+   path, 0 = dropped), drop the rest, compact.  New local count out. */
 int basq_session_apply_cells(basq_session* s, int64_t R_glob, int64_t off_glob, int F,
                              const double* factor_host, int64_t* R_loc_new_host);
 /* ---- small dense helper exposed for tests ---------------------------------------------------- */

@@ -225,6 +225,8 @@ def test_staged_session_two_shards_one_gpu(bq):
     s1 = ops.Session(cov.forward, X[cut:].to(DEV), Z.to(DEV), U.to(DEV), N, cut)
     S = s0.S
     c0, c1 = s0.count(), s1.count()
+    A0 = torch.zeros(n, S, dtype=torch.float64, device=DEV); A1 = torch.zeros_like(A0)
+    omega = torch.zeros(S, dtype=torch.float64, device=DEV)
     rounds, factors_used = 0, set()
     while c0 + c1 > n:
         R = c0 + c1
@@ -233,20 +235,36 @@ def test_staged_session_two_shards_one_gpu(bq):
         if rounds == 0:
             F = 4                                        # exercise the refined pass whatever the policy says
         factors_used.add(F)
-        A0 = torch.zeros(n, F * S, dtype=torch.float64, device=DEV); A1 = torch.zeros_like(A0)
-        s0.partial(R, 0, F, A0); s1.partial(R, c0, F, A1)
-        A = (A0 + A1).contiguous()
-        # the cell columns refine the set columns: folding them gives the reference's round system
-        if F > 1:
-            B0 = torch.zeros(n, S, dtype=torch.float64, device=DEV); B1 = torch.zeros_like(B0)
-            s0.partial(R, 0, 1, B0); s1.partial(R, c0, 1, B1)
-            fold = A.view(n, F, S).sum(1)
-            assert torch.allclose(fold, B0 + B1, rtol=1e-12, atol=1e-18)
-        factor = s0.car_levels(A, F, R)
+        # the reference's round system (F = 1) before the refined sweep overwrites the pass state
+        B0 = torch.zeros_like(A0); B1 = torch.zeros_like(A0)
+        s0.partial(R, 0, B0); s1.partial(R, c0, B1)
+        s0.pass_begin(R, 0, F); s1.pass_begin(R, c0, F)
+        factor = torch.zeros(F * S, dtype=torch.float64)
+        tree = sharded.LevelTree(S, F, R)
+        while True:
+            C = tree.columns()
+            s0.level(tree.lvl, tree.node, tree.ppos, tree.fpar, A0)
+            s1.level(tree.lvl, tree.node, tree.ppos, tree.fpar, A1)
+            A = (A0 + A1).contiguous()
+            if tree.lvl == 0:
+                # level 0 of a refined pass is the reference's round: cell columns fold to set columns
+                assert float(torch.linalg.norm(A - (B0 + B1)) / torch.linalg.norm(B0 + B1)) < 1e-13
+            total = A[:, :C].sum(1).cpu()
+            if C > n:
+                s0.car(A, C, omega)
+                om = omega[:C].cpu()
+                # every level preserves its system's moments with at most n columns
+                kept_cols = (A0 + A1)[:, :C].cpu() @ om
+                assert float(torch.linalg.norm(kept_cols - total) / torch.linalg.norm(total)) < 1e-11
+                assert int((om > 0).sum()) <= n
+                om = om.tolist()
+            else:
+                om = [1.0] * C
+            more, kept = tree.advance(om, factor)
+            assert kept >= 1
+            if not more:
+                break
         assert int((factor > 0).sum()) <= n
-        # every level preserves the moments: sum_c factor_c A[:, c] = sum_c A[:, c]
-        lhs, rhs = A.cpu() @ factor, A.cpu().sum(1)
-        assert float(torch.linalg.norm(lhs - rhs) / torch.linalg.norm(rhs)) < 1e-11
         c0, c1 = s0.apply(R, 0, F, factor), s1.apply(R, c0, F, factor)
         assert c0 + c1 <= -(-R // (F * S)) * n
         rounds += 1

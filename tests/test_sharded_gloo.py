@@ -41,48 +41,32 @@ class OracleEngine:
     def _cells(self, off, F):
         return (off + torch.arange(len(self.mu))) % (F * self.S)
 
-    def partial(self, R, off, F, A):
-        A.zero_()
+    def pass_begin(self, R, off, F):
+        self.F = F
+        self.cellA = torch.zeros(self.n, F * self.S, dtype=torch.float64)
         if len(self.mu) == 0:
             return
         cells = self._cells(off, F)
         feats = (self.U @ self.kernel(self.Z, self.X)) * self.mu.unsqueeze(0)       # [q, R_loc]
-        A[0].index_add_(0, cells, self.mu)
-        A[1:].index_add_(1, cells, feats)
+        self.cellA[0].index_add_(0, cells, self.mu)
+        self.cellA[1:].index_add_(1, cells, feats)
 
-    def _car(self, A):
-        """omega >= 0 with A omega = A 1 and <= n non-zeros (oracle Caratheodory on barycentres)."""
-        mass = A[0]
-        bary = (A[1:] / mass.unsqueeze(0)).T
+    def level(self, lvl, node, ppos, fpar, A):
+        """Columns of the level's nodes, every one folded directly from the cell columns (the
+        library derives the high halves as parent - low half; the two must agree)."""
+        stride, cnt = self.S << lvl, self.F >> lvl
+        ids = list(node) + ([u + (self.S << (lvl - 1)) for u in node] if lvl > 0 else [])
+        fs = list(fpar) + (list(fpar) if lvl > 0 else [])
+        A.zero_()
+        for i, (u, f) in enumerate(zip(ids, fs)):
+            A[:, i] = f * sum(self.cellA[:, u + k * stride] for k in range(cnt))
+
+    def car(self, A, C, omega):
+        mass = A[0, :C]
+        bary = (A[1:, :C] / mass.unsqueeze(0)).T
         w, keep = orchq.caratheodory(bary, mass.clone())
-        omega = torch.zeros(A.shape[1], dtype=torch.float64)
+        omega.zero_()
         omega[keep] = w / mass[keep]
-        return omega
-
-    def car_levels(self, A, F, R):
-        """The cell hierarchy of one pass (include/basq_b200.h: basq_car_levels) with the oracle's
-        Caratheodory step at every level."""
-        S, n = self.S, self.n
-        cells = F * S
-        L = F.bit_length() - 1
-        factor = torch.zeros(cells, dtype=torch.float64)
-        act = list(range(min(S, R)))
-        fac = [1.0] * len(act)
-        for lvl in range(L + 1):
-            stride, cnt = S << lvl, F >> lvl
-            cols = torch.stack([f * sum(A[:, u + k * stride] for k in range(cnt)) for u, f in zip(act, fac)], 1)
-            om = self._car(cols) if len(act) > n else torch.ones(len(act), dtype=torch.float64)
-            nact, nfac = [], []
-            for half in range(2 if lvl < L else 1):
-                for u, f, o in zip(act, fac, om.tolist()):
-                    if o > 0:
-                        if lvl < L:
-                            nact.append(u + half * stride)
-                            nfac.append(f * o)
-                        else:
-                            factor[u] = f * o
-            act, fac = nact, nfac
-        return factor
 
     def apply(self, R, off, F, factor):
         scale = factor[self._cells(off, F)]
