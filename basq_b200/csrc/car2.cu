@@ -90,22 +90,27 @@ __device__ __forceinline__ unsigned long long pack_max(double key, int idx) {
 __device__ __forceinline__ unsigned long long pack_min(double key, int idx) {
   return ((unsigned long long)__double_as_longlong(key) & ~0xFFFull) | (unsigned long long)idx;
 }
-__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long x, int o) {
-  const unsigned lo = __shfl_xor_sync(FULLMASK, (unsigned)x, o);
-  const unsigned hi = __shfl_xor_sync(FULLMASK, (unsigned)(x >> 32), o);
-  return ((unsigned long long)hi << 32) | lo;
+// 64-bit max / min over a warp with the integer reduction unit: two REDUX (high words, then the low
+// words of the lanes that tie on the high word) instead of a five-round 64-bit shuffle butterfly.
+template <bool MAX>
+__device__ __forceinline__ unsigned long long warp_best_u64(unsigned long long x) {
+  const unsigned hi = (unsigned)(x >> 32), lo = (unsigned)x;
+  if (MAX) {
+    const unsigned mhi = __reduce_max_sync(FULLMASK, hi);
+    const unsigned mlo = __reduce_max_sync(FULLMASK, hi == mhi ? lo : 0u);
+    return ((unsigned long long)mhi << 32) | mlo;
+  } else {
+    const unsigned mhi = __reduce_min_sync(FULLMASK, hi);
+    const unsigned mlo = __reduce_min_sync(FULLMASK, hi == mhi ? lo : 0xFFFFFFFFu);
+    return ((unsigned long long)mhi << 32) | mlo;
+  }
 }
 
 // MAX: `none` = 0 ; MIN: `none` = ~0
 template <bool MAX, int NT>
 __device__ __forceinline__ Best block_best(unsigned long long mine, double payload, Slot (*scratch)[NT / 32], int& spar) {
   constexpr unsigned long long NONE = MAX ? 0ull : ~0ull;
-  unsigned long long x = mine;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long y = shfl_xor_u64(x, o);
-    x = MAX ? (y > x ? y : x) : (y < x ? y : x);
-  }
+  const unsigned long long x = warp_best_u64<MAX>(mine);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (x == NONE) {
     if (lane == 0) scratch[spar][warp] = Slot{NONE, 0.0};
@@ -116,12 +121,7 @@ __device__ __forceinline__ Best block_best(unsigned long long mine, double paylo
   const Slot* row = scratch[spar];
   spar ^= 1;
   const unsigned long long w = row[lane & (NT / 32 - 1)].key;
-  unsigned long long y = w;
-#pragma unroll
-  for (int o = NT / 64; o > 0; o >>= 1) {
-    const unsigned long long z = shfl_xor_u64(y, o);
-    y = MAX ? (z > y ? z : y) : (z < y ? z : y);
-  }
+  const unsigned long long y = warp_best_u64<MAX>(w);
   Best r;
   if (y == NONE) {
     r.idx = -1;
@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(NT, 1) car2_kernel(const Car2Dev a) {
     const int krows = min(B, n - kr0);
     if (b == k) {
       // ---- owner: B local pivots, each published as soon as it exists
+      if (tid == 0 && (b == 10 || b == 11)) stamp(a.stamps, b == 10 ? 4 : 6);
 #pragma unroll
       for (int i = 0; i < B; ++i) {
         if (i < krows) {
@@ -254,6 +255,7 @@ __global__ void __launch_bounds__(NT, 1) car2_kernel(const Car2Dev a) {
           }
         }
       }
+      if (tid == 0 && b == 10) stamp(a.stamps, 5);
     } else {
       // ---- everyone else: replay the block's rank-1 updates as the pivots appear in L2 (codes of the
       // whole block and a rolling window of pivot-row entries are requested ahead of use)
@@ -272,8 +274,36 @@ __global__ void __launch_bounds__(NT, 1) car2_kernel(const Car2Dev a) {
 #pragma unroll
       for (int i = 0; i < B; ++i) {
         if (i < krows) {
-          int cd = code[i];
-          if (cd == -1) cd = poll_i32(&a.prep[(int64_t)(kr0 + i) * NT + tid], a.status);
+          // Wait until pivot i is complete in registers.  Every missing word of pivots i .. i+PF-1 is
+          // re-requested in ONE batch of independent loads per round trip (a chain of dependent
+          // polls would cost one L2 round trip per word).
+          for (int spins = 0;; ++spins) {
+            bool ok = code[i] != -1;
+            if (code[i] >= 2) {
+#pragma unroll
+              for (int j = 0; j < CPT; ++j)
+                if (tid + j * NT < S && is_sentinel(win[i % PF][j])) ok = false;
+            }
+            if (ok) break;
+            if ((spins & 63) == 63 && (*reinterpret_cast<volatile int*>(a.status) != 0 || spins > BASQ_SPIN_LIMIT)) {
+              if (spins > BASQ_SPIN_LIMIT) atomicExch(a.status, 2);
+              code[i] = 1;
+              break;
+            }
+#pragma unroll
+            for (int w = 0; w < PF; ++w) {
+              if (i + w < B && i + w < krows) {
+                if (code[i + w] == -1) code[i + w] = __ldcg(&a.prep[(int64_t)(kr0 + i + w) * NT + tid]);
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                  const int c = tid + j * NT;
+                  if (c < S && is_sentinel(win[(i + w) % PF][j]))
+                    win[(i + w) % PF][j] = __ldcg(&a.prow[(int64_t)(kr0 + i + w) * S + c]);
+                }
+              }
+            }
+          }
+          const int cd = code[i];
           double cur[CPT];
 #pragma unroll
           for (int j = 0; j < CPT; ++j) {
@@ -281,14 +311,7 @@ __global__ void __launch_bounds__(NT, 1) car2_kernel(const Car2Dev a) {
             const int c = tid + j * NT;
             if (i + PF < B) win[i % PF][j] = (i + PF < krows && c < S) ? __ldcg(&a.prow[(int64_t)(kr0 + i + PF) * S + c]) : 0.0;
           }
-          if (cd >= 2) {
-#pragma unroll
-            for (int j = 0; j < CPT; ++j) {
-              const int c = tid + j * NT;
-              if (c < S && is_sentinel(cur[j])) cur[j] = poll_f64(&a.prow[(int64_t)(kr0 + i) * S + c], a.status);
-            }
-            eliminate(cur, cd - 2, -1);
-          }
+          if (cd >= 2) eliminate(cur, cd - 2, -1);
         }
       }
     }
@@ -421,16 +444,33 @@ __global__ void __launch_bounds__(NT, 1) car2_kernel(const Car2Dev a) {
 #pragma unroll
       for (int l = 0; l < B; ++l) {
         if (l < kcols) {
-          int cd = code[l];
-          if (cd == -1) cd = poll_i32(&a.srep[(int64_t)(kc0 + l) * NT + tid], a.status);
-          if (cd >= 2) {
+          // as in stage 1: all missing words of pivots l .. B-1 in one batch of loads per round trip
+          for (int spins = 0;; ++spins) {
+            bool ok = code[l] != -1;
+            if (code[l] >= 2) {
 #pragma unroll
-            for (int jj = 0; jj < RPT; ++jj) {
-              const int i = tid + jj * NT;
-              if (i < n && is_sentinel(pvs[l][jj])) pvs[l][jj] = poll_f64(&a.pcol[(int64_t)(kc0 + l) * n + i], a.status);
+              for (int jj = 0; jj < RPT; ++jj)
+                if (tid + jj * NT < n && is_sentinel(pvs[l][jj])) ok = false;
             }
-            col_update(pvs[l], cd - 2, 0);
+            if (ok) break;
+            if ((spins & 63) == 63 && (*reinterpret_cast<volatile int*>(a.status) != 0 || spins > BASQ_SPIN_LIMIT)) {
+              if (spins > BASQ_SPIN_LIMIT) atomicExch(a.status, 2);
+              code[l] = 1;
+              break;
+            }
+#pragma unroll
+            for (int l2 = l; l2 < B; ++l2) {
+              if (l2 < kcols) {
+                if (code[l2] == -1) code[l2] = __ldcg(&a.srep[(int64_t)(kc0 + l2) * NT + tid]);
+#pragma unroll
+                for (int jj = 0; jj < RPT; ++jj) {
+                  const int i = tid + jj * NT;
+                  if (i < n && is_sentinel(pvs[l2][jj])) pvs[l2][jj] = __ldcg(&a.pcol[(int64_t)(kc0 + l2) * n + i]);
+                }
+              }
+            }
           }
+          if (code[l] >= 2) col_update(pvs[l], code[l] - 2, 0);
         }
       }
     } else {
@@ -512,7 +552,10 @@ int launch_car2(basq_ctx* ctx, const Car2Dev& d, int grid, size_t smem) {
   return BASQ_OK;
 }
 
-constexpr int C2_NT = 512, C2_CPT = 4, C2_RPT = 2;
+#ifndef BASQ_CAR2_NT
+#define BASQ_CAR2_NT 512
+#endif
+constexpr int C2_NT = BASQ_CAR2_NT, C2_CPT = 2048 / C2_NT, C2_RPT = 1024 / C2_NT;
 
 }  // namespace
 
@@ -571,10 +614,10 @@ int caratheodory_fast(basq_ctx* ctx, double* A, int n, int S, int lda, double* o
   BASQ_CUDA(cudaMemcpyAsync(&status, d.status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
   if (timing) {
-    unsigned long long t[4];
+    unsigned long long t[8];
     BASQ_CUDA(cudaMemcpy(t, d.stamps, sizeof(t), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[car2] n=%d S=%d B=%d grid=%d: stage1 %.1f us, barrier+list %.1f us, stage2 %.1f us\n", n, S, B, grid,
-            (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3);
+    fprintf(stderr, "[car2] n=%d S=%d B=%d grid=%d: stage1 %.1f us, barrier+list %.1f us, stage2 %.1f us; block 10: own %.2f us, hand-over to 11 %.2f us\n", n, S, B, grid,
+            (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3, (t[5] - t[4]) * 1e-3, (t[6] - t[5]) * 1e-3);
   }
   *status_out = status;
   BASQ_CHECK(status == 0 || status == 3, BASQ_ERR_NUMERIC, "caratheodory: pivot chain watchdog fired (status %d)",
