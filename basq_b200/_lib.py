@@ -70,6 +70,10 @@ def _load():
         "basq_session_pass_begin": (I, [P, L, L, I]),
         "basq_session_level": (I, [P, I, I, P, P, P, P]),
         "basq_session_apply_cells": (I, [P, L, L, I, P, C.POINTER(L)]),
+        "basq_sample_mvn": (I, [P, C.c_uint64, L, L, I, I, P, P, P]),
+        "basq_mvn_logpdf": (I, [P, P, L, I, I, P, P, P]),
+        "basq_candidate_weights": (I, [P, I, D, I, P, P, L, I, P]),
+        "basq_cleanse_weights": (I, [P, P, L, D]),
         "basq_dgemm": (I, [P, I, I, I, I, I, D, P, I, P, I, D, P, I]),
         "basq_tgemm": (I, [P, I, I, I, P, I, P, I, P, I]),
     }

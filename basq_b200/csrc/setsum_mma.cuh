@@ -55,16 +55,25 @@ struct MmaCfg {
   static constexpr int A_TILE_BYTES = KA * 128 * 4;
   static constexpr int B_STAGE_BYTES = KA * NT * 4;
   static constexpr int W_STAGE_BYTES = NT * 8;
-  static constexpr int COMB_BYTES = MT * 128 * JT * 8;
+  static constexpr int EPI_WARPS = 16, PROD_WARPS = 4;
+  static constexpr int NPART = EPI_WARPS / 4;          // column parts of an accumulator buffer (one warp each per lane quarter)
+  static constexpr int COMB_SLOT_BYTES = MT * 128 * JT * 8;
+  static constexpr int SMEM_FIXED = MT * A_TILE_BYTES + NSTAGE * (B_STAGE_BYTES + W_STAGE_BYTES) + 256;
+  // End-of-item combine of the column parts.  With one slot per part (NPART - 1 slots) the parts
+  // hand their partial sums over with ONE arrive and go on to the next item while part 0 sums and
+  // writes G; with a single slot (large DP: no room) they take turns under full barriers.
+  static constexpr int NSLOT = (SMEM_FIXED + (NPART - 1) * COMB_SLOT_BYTES <= 227 * 1024) ? NPART - 1 : 1;
+  static constexpr int COMB_BYTES = NSLOT * COMB_SLOT_BYTES;
+  // landmark tiles are double-buffered (the next work item's tiles arrive while this item's MMAs
+  // run) whenever a second copy still fits the 227 KB of shared memory
+  static constexpr int NABUF = (SMEM_FIXED + COMB_BYTES + MT * A_TILE_BYTES <= 227 * 1024) ? 2 : 1;
   static constexpr int OFF_A = 0;
-  static constexpr int OFF_B = OFF_A + MT * A_TILE_BYTES;
+  static constexpr int OFF_B = OFF_A + NABUF * MT * A_TILE_BYTES;
   static constexpr int OFF_W = OFF_B + NSTAGE * B_STAGE_BYTES;
   static constexpr int OFF_COMB = OFF_W + NSTAGE * W_STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_COMB + COMB_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256;
   static constexpr int TMEM_COLS = 2 * NT;             // two accumulator buffers (256 or 512)
-  static constexpr int EPI_WARPS = 16, PROD_WARPS = 4;
-  static constexpr int NPART = EPI_WARPS / 4;          // column parts of an accumulator buffer (one warp each per lane quarter)
   static constexpr int THREADS = (EPI_WARPS + PROD_WARPS + 1) * 32;
 };
 
@@ -159,6 +168,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // the three tf32 pieces of an fp32 value (sum reproduces it to ~2^-33 relative)
 __device__ __forceinline__ void split3(float v, float& p1, float& p2, float& p3) {
@@ -224,9 +236,9 @@ __global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(cons
   uint64_t* b_empty = bars + NSTAGE;     // [NSTAGE]
   uint64_t* t_full = bars + 2 * NSTAGE;  // [2]
   uint64_t* t_empty = t_full + 2;        // [2]
-  uint64_t* a_full = t_empty + 2;        // [1]
-  uint64_t* a_empty = a_full + 1;        // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
+  uint64_t* a_full = t_empty + 2;        // [2]
+  uint64_t* a_empty = a_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -239,8 +251,10 @@ __global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(cons
       mma::mbar_init(&t_full[b], 1);
       mma::mbar_init(&t_empty[b], Cfg::EPI_WARPS);
     }
-    mma::mbar_init(a_full, 1);
-    mma::mbar_init(a_empty, 1);
+    for (int b = 0; b < 2; ++b) {
+      mma::mbar_init(&a_full[b], 1);
+      mma::mbar_init(&a_empty[b], 1);
+    }
     mma::fence_barrier_init();
   }
   if (warp == Cfg::EPI_WARPS + Cfg::PROD_WARPS) mma::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -269,7 +283,7 @@ __global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(cons
     constexpr int NPART = Cfg::NPART;
     constexpr int PART_COLS = NT / NPART;
     static_assert(PART_COLS % 32 == 0, "column part must be a multiple of the tcgen05.ld width");
-    uint32_t it = 0, tc = 0;
+    uint32_t it = 0, tc = 0, items_done = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int mg = item % a.n_mgroups, jg = item / a.n_mgroups;
       const int j0 = jg * JT;
@@ -312,37 +326,61 @@ __global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(cons
         if (lane == 0) mma::mbar_arrive(&b_empty[stage]);
       }
       // ---- combine the column parts in a fixed order (deterministic sums) and write G
-#pragma unroll
-      for (int pp = NPART - 1; pp >= 1; --pp) {
-        if (part == pp) {
+      constexpr int SLOT = MT * 128 * JT;
+      constexpr bool HANDOVER = (Cfg::NSLOT == NPART - 1);
+      if (HANDOVER) {
+        if (part > 0) {
+          if (items_done > 0) mma::named_bar_sync(2, Cfg::EPI_WARPS * 32);  // part 0 is done with the previous sums
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int jj = 0; jj < JT; ++jj) {
-              double* c = &sComb[(mt * 128 + row) * JT + jj];
-              *c = (pp == NPART - 1) ? acc[mt][jj] : (*c + acc[mt][jj]);
-            }
+            for (int jj = 0; jj < JT; ++jj) sComb[(part - 1) * SLOT + (mt * JT + jj) * 128 + row] = acc[mt][jj];
+          __threadfence_block();
+          mma::named_bar_arrive(1, Cfg::EPI_WARPS * 32);
+        } else {
+          mma::named_bar_sync(1, Cfg::EPI_WARPS * 32);
         }
-        mma::named_bar_sync(1, Cfg::EPI_WARPS * 32);
+      } else {
+#pragma unroll
+        for (int pp = NPART - 1; pp >= 1; --pp) {
+          if (part == pp) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+              for (int jj = 0; jj < JT; ++jj) {
+                double* c = &sComb[(mt * JT + jj) * 128 + row];
+                *c = (pp == NPART - 1) ? acc[mt][jj] : (*c + acc[mt][jj]);
+              }
+          }
+          mma::named_bar_sync(1, Cfg::EPI_WARPS * 32);
+        }
       }
       if (part == 0) {
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           const int m = (mg * MT + mt) * 128 + row;
-          if (m < a.Mtot) {
 #pragma unroll
-            for (int jj = 0; jj < JT; ++jj) {
-              const int j = j0 + jj;
-              if (j < a.S) {
-                const double v = acc[mt][jj] + sComb[(mt * 128 + row) * JT + jj];
-                double* dst = a.G + (int64_t)m * a.ldg + j;
-                *dst = a.accumulate ? (*dst + v) : v;
-              }
+          for (int jj = 0; jj < JT; ++jj) {
+            double c;
+            if (HANDOVER) {
+              c = sComb[(NPART - 2) * SLOT + (mt * JT + jj) * 128 + row];
+#pragma unroll
+              for (int pp = NPART - 3; pp >= 0; --pp) c += sComb[pp * SLOT + (mt * JT + jj) * 128 + row];
+            } else {
+              c = sComb[(mt * JT + jj) * 128 + row];
+            }
+            const int j = j0 + jj;
+            if (m < a.Mtot && j < a.S) {
+              const double v = acc[mt][jj] + c;
+              double* dst = a.G + (int64_t)m * a.ldg + j;
+              *dst = a.accumulate ? (*dst + v) : v;
             }
           }
         }
+        if (HANDOVER) mma::named_bar_arrive(2, Cfg::EPI_WARPS * 32);
       }
-      mma::named_bar_sync(1, Cfg::EPI_WARPS * 32);
+      if (!HANDOVER) mma::named_bar_sync(1, Cfg::EPI_WARPS * 32);
+      ++items_done;
     }
   } else if (warp < Cfg::EPI_WARPS + Cfg::PROD_WARPS) {
     // ======================================================================== producers
@@ -408,20 +446,38 @@ __global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(cons
   } else {
     // ======================================================================== MMA issuer
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
-    uint32_t it = 0, tc = 0, ac = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int mg = item % a.n_mgroups, jg = item / a.n_mgroups;
+    constexpr int NABUF = Cfg::NABUF;
+    uint32_t it = 0, tc = 0, ac = 0;  // ac counts the work items with tiles (= landmark tile loads)
+    auto next_item = [&](int item) {  // first item >= `item` of this CTA that has tiles; n_items if none
+      for (; item < n_items; item += gridDim.x) {
+        int64_t e_lo, n_tiles;
+        item_range((item / a.n_mgroups) * JT, e_lo, n_tiles);
+        if (n_tiles > 0) break;
+      }
+      return item < n_items ? item : n_items;
+    };
+    // request the landmark tiles of work item `item` as load number `ld` (buffer ld % NABUF)
+    auto load_A = [&](int item, uint32_t ld) {
+      const uint32_t ab = ld % NABUF, use = ld / NABUF;
+      if (use > 0) mma::mbar_wait(&a_empty[ab], (use - 1) & 1u);  // the buffer's previous item has issued all MMAs
+      if (lane == 0) {
+        const int mg = item % a.n_mgroups;
+        mma::mbar_expect_tx(&a_full[ab], MT * Cfg::A_TILE_BYTES);
+        mma::bulk_g2s(sA + ab * MT * Cfg::A_TILE_BYTES, a.lmA + (size_t)mg * MT * (Cfg::A_TILE_BYTES / 4),
+                      MT * Cfg::A_TILE_BYTES, &a_full[ab]);
+      }
+    };
+    int item = next_item(blockIdx.x);
+    if (item < n_items) load_A(item, 0);
+    while (item < n_items) {
+      const int jg = item / a.n_mgroups;
       int64_t e_lo, n_tiles;
       item_range(jg * JT, e_lo, n_tiles);
-      if (n_tiles == 0) continue;
-      // landmark tiles of this item: wait until the previous item's MMAs released the buffer
-      if (ac > 0) mma::mbar_wait(a_empty, (ac - 1) & 1u);
-      if (lane == 0) {
-        mma::mbar_expect_tx(a_full, MT * Cfg::A_TILE_BYTES);
-        mma::bulk_g2s(sA, a.lmA + (size_t)mg * MT * (Cfg::A_TILE_BYTES / 4), MT * Cfg::A_TILE_BYTES, a_full);
-      }
-      mma::mbar_wait(a_full, ac & 1u);
-      ++ac;
+      const int nxt = next_item(item + gridDim.x);
+      if (NABUF == 2 && nxt < n_items) load_A(nxt, ac + 1);
+      const uint32_t ab = ac % NABUF;
+      mma::mbar_wait(&a_full[ab], (ac / NABUF) & 1u);
+      unsigned char* const sAcur = sA + ab * MT * Cfg::A_TILE_BYTES;
       for (int64_t t = 0; t < n_tiles; ++t, ++it) {
         const int stage = it % NSTAGE;
         mma::mbar_wait(&b_full[stage], (it / NSTAGE) & 1u);
@@ -432,7 +488,7 @@ __global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(cons
           mma::mbar_wait(&t_empty[buf], ((tc >> 1) & 1u) ^ 1u);
           mma::tc_fence_after();
           if (lane == 0) {
-            const uint32_t a_base = mma::smem_u32(sA + mt * Cfg::A_TILE_BYTES);
+            const uint32_t a_base = mma::smem_u32(sAcur + mt * Cfg::A_TILE_BYTES);
             const uint32_t b_base = mma::smem_u32(sB + (size_t)stage * Cfg::B_STAGE_BYTES);
 #pragma unroll
             for (int ks = 0; ks < KA / 8; ++ks) {
@@ -447,8 +503,11 @@ __global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(cons
         if (lane == 0) mma::umma_commit(&b_empty[stage]);
         __syncwarp();
       }
-      if (lane == 0) mma::umma_commit(a_empty);
+      if (lane == 0) mma::umma_commit(&a_empty[ab]);
       __syncwarp();
+      ++ac;
+      if (NABUF == 1 && nxt < n_items) load_A(nxt, ac);
+      item = nxt;
     }
   }
 

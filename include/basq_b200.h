@@ -26,7 +26,7 @@ extern "C" {
 
 #define BASQ_ABI_VERSION 1
 #define BASQ_MAX_DIM 32
-#define BASQ_MAX_CELL_FACTOR 16 /* cells per set in a refined pass (basq_session_partial_cells) */
+#define BASQ_MAX_CELL_FACTOR 16 /* cells per set in a refined pass (basq_session_pass_begin) */
 
 enum basq_status {
   BASQ_OK = 0,
@@ -172,6 +172,29 @@ int basq_session_level(basq_session* s, int lvl, int K, const int* node_host, co
    path, 0 = dropped), drop the rest, compact.  New local count out. */
 int basq_session_apply_cells(basq_session* s, int64_t R_glob, int64_t off_glob, int F,
                              const double* factor_host, int64_t* R_loc_new_host);
+/* ---- candidate side: device sampling, prior density, importance weights --------- */
+/* X_out[N, d] (dtype) = mean + L z, z ~ N(0, I): PriorSampler.__call__ (BASQ/_sampler.py:21-34,
+   prior.sample) and SOBER Gaussian.sample (SOBER/_prior.py:107-118).  mean_host[d], chol_host[d, d]
+   (lower Cholesky factor of the covariance, row-major) are HOST arrays.  Philox4x32-10, counter =
+   (global row index, block of 4 dimensions), key = seed: row `offset + i` of the one stream defined
+   by `seed` lands in X_out[i], so ranks sample disjoint shards by passing their first global row. */
+int basq_sample_mvn(basq_ctx* ctx, uint64_t seed, int64_t offset, int64_t N, int d, int dtype,
+                    const double* mean_host, const double* chol_host, void* X_out);
+/* out[N] (fp64) = log N(x_i; mean, L L^T): prior.log_prob (BASQ/_sampler.py:136, 204-212),
+   Gaussian.pdf (SOBER/_prior.py:120-131). */
+int basq_mvn_logpdf(basq_ctx* ctx, const void* X, int64_t N, int d, int dtype, const double* mean_host,
+                    const double* chol_host, double* out);
+/* Weights over candidates from the GP moments mean[N], var[N] (basq_gp_predict), fp64 in and out.
+   kind 0: UncertaintySampler.calc_weights (BASQ/_sampler.py:190-217): |m| / (ratio v + (1 - ratio) |m|)
+           (or |m| / (ratio v) at ratio = 1) - the prior density cancels between f_rec and g_rec;
+   kind 1: PI_BQ.lfi (SOBER/_pi.py:121-139): Phi((m - 1) / sqrt(v)), log(. + eps32) when log_out.
+   normalise != 0 divides by the sum (uniform weights if the sum is zero or not finite). */
+int basq_candidate_weights(basq_ctx* ctx, int kind, double ratio, int log_out, const double* mean,
+                           const double* var, int64_t N, int normalise, double* w_out);
+/* In place: w < eps -> 0, inf / nan -> eps, then normalise (uniform if the sum is 0):
+   WeightsStabiliser.cleansing_weights (SOBER/_weights.py:21-38). */
+int basq_cleanse_weights(basq_ctx* ctx, double* w, int64_t N, double eps);
+
 /* ---- small dense helper exposed for tests ---------------------------------------------------- */
 /* C[m,n] = alpha * op(A) op(B) + beta * C, fp64 row-major; op = transpose when the flag is set. */
 int basq_dgemm(basq_ctx* ctx, int transA, int transB, int m, int n, int k, double alpha,

@@ -14,10 +14,10 @@ Z = X[:M].clone()
 U = torch.randn(q, M, generator=g, device=dev, dtype=torch.float64)
 spec = KernelSpec(_lib.RBF, _lib.PLAIN, torch.tensor([2.5]), 1.0)
 sess = ops.Session(spec, X, Z, U, N, 0)
-A = torch.zeros(sess.n, sess.S, dtype=torch.float64, device=dev)
 ctx = _lib.context_for(dev)
+F = int(os.environ.get("CELLS", "1"))
 for _ in range(2):
-    sess.partial(N, 0, 1, A)
+    sess.pass_begin(N, 0, F)
 ctx.profile(True); ctx.profile_read(True)
 reps = int(os.environ.get("REPS", "3"))
 import subprocess, threading
@@ -29,7 +29,7 @@ def sample():
 th = threading.Thread(target=sample, daemon=True)
 if reps > 5: th.start()
 for _ in range(reps):
-    sess.partial(N, 0, 1, A)
+    sess.pass_begin(N, 0, F)
 torch.cuda.synchronize()
 stop.set()
 if reps > 5:
@@ -37,5 +37,5 @@ if reps > 5:
 p = ctx.profile_read(True)
 ms = p["set_sum"][0] / reps
 pairs = float(M) * N
-print(f"{os.path.basename(os.environ.get('BASQ_B200_LIB', 'default')):24s} set_sum {ms:8.3f} ms  {pairs / ms / 1e9:7.1f} Gpairs/s  "
+print(f"{os.path.basename(os.environ.get('BASQ_B200_LIB', 'default')):24s} F={F:2d} N={N} set_sum {ms:8.3f} ms  {pairs / ms / 1e9:7.1f} Gpairs/s  "
       f"{pairs / (ms * 1e-3) / 148 / 1.965e9:6.2f} pairs/clk/SM@1965  projection {p['projection'][0] / reps:.2f} ms")
