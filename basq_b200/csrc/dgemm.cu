@@ -4,17 +4,17 @@
 // There is no fp64 kind in tcgen05; on sm_100a the fp64 tensor path is the warp-level
 // mma.sync.m8n8k4.f64 (DMMA), which runs at twice the DFMA-pipe rate measured on this part
 // (a register-tiled DFMA version of this kernel topped out at 14 TFLOP/s).
-// CTA tile (16*MF) x 128, BK = 8, 8 warps as 2 x 4, warp tile (8*MF) x 32 = MF x 4 fragments of
-// 8 x 8, accumulators in registers.  Operands are staged global -> registers -> shared with the next
-// tile's loads in flight during the current tile's MMAs; shared layout [k/4][row][k%4] makes every
-// fragment load one contiguous 256-byte warp access (conflict-free).  All four transpose
-// combinations, arbitrary sizes and leading dimensions.
+// Accumulators in registers, operands through a three-stage cp.async pipeline (see below).  All four
+// transpose combinations, arbitrary sizes and leading dimensions (16-byte copies when the operand
+// is 16-byte aligned with an even leading dimension, 8-byte copies otherwise).
+// Measured on B200 (999 x 11002 x 2000, the projection): 26.6 TFLOP/s; cuBLAS 12.9 reaches 33.2.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace basq {
 
 namespace {
-constexpr int BN = 128, BK = 8;
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -22,102 +22,138 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                : "d"(a), "d"(b));
 }
 
-template <bool TA, bool TB, int MF>
-__global__ void __launch_bounds__(256) dgemm_kernel(int M, int N, int K, double alpha, const double* __restrict__ A,
-                                                    int64_t lda, const double* __restrict__ B, int64_t ldb, double beta,
-                                                    double* __restrict__ C, int64_t ldc, int tri_k) {
-  constexpr int BM = 16 * MF;
-  constexpr int AV = BM * BK / 256;  // A elements staged per thread
-  constexpr int BV = BN * BK / 256;  // B elements staged per thread
-  __shared__ __align__(16) double As[2][BK / 4][BM][4];
-  __shared__ __align__(16) double Bs[2][BK / 4][BN][4];
+// ---------------------------------------------------------------------------------------------
+// BK = 16, three cp.async stages (no register staging, one barrier per 16 k),
+// warp grid WM x WN with MF x NF fragments per warp, so that the CTA tile (WM 8 MF) x (WN 8 NF) can
+// be chosen per problem to fill the 148 SMs (128 x 112 gives 144 tiles for the 999 x 2000
+// projection where 128 x 128 gives 128).  Shared layouts keep the operand's contiguous direction
+// contiguous (16-byte copies) and pad the other stride to 4 (mod 16) doubles: every fragment load
+// is conflict-free.
+// ---------------------------------------------------------------------------------------------
+constexpr int PK = 16, PST = 3;
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src, int bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src),
+               "r"(bytes)
+               : "memory");
+}
+
+// Stage one operand tile.  KCONT: the source is contiguous along k (tile stored [row][PK + 4]),
+// otherwise along the row index (tile stored [k][R + 4]).  Out-of-range elements are zero-filled.
+template <bool KCONT, int R, int NTHR>
+__device__ __forceinline__ void stage_tile(double* sm, const double* __restrict__ P, int64_t ld, int r0, int Rmax, int k0,
+                                           int K, int vec16, int tid) {
+  constexpr int CHUNKS = R * PK / 2;
+#pragma unroll
+  for (int c0 = 0; c0 < CHUNKS; c0 += NTHR) {
+    const int c = c0 + tid;
+    if (CHUNKS % NTHR != 0 && c >= CHUNKS) break;
+    int row, kk, inner_left;
+    const double* src;
+    double* dst;
+    if (KCONT) {
+      row = c / (PK / 2);
+      kk = (c % (PK / 2)) * 2;
+      const bool ok = r0 + row < Rmax;
+      inner_left = ok ? K - (k0 + kk) : 0;
+      src = P + (int64_t)(ok ? r0 + row : 0) * ld + k0 + kk;
+      dst = sm + row * (PK + 4) + kk;
+    } else {
+      kk = c / (R / 2);
+      row = (c % (R / 2)) * 2;
+      const bool ok = k0 + kk < K;
+      inner_left = ok ? Rmax - (r0 + row) : 0;
+      src = P + (int64_t)(ok ? k0 + kk : 0) * ld + r0 + row;
+      dst = sm + kk * (R + 4) + row;
+    }
+    const int n = inner_left >= 2 ? 2 : (inner_left == 1 ? 1 : 0);
+    if (n == 0) src = P;
+    if (vec16) {
+      cp_async16(dst, src, n * 8);
+    } else {
+      cp_async8(dst, src, n >= 1 ? 8 : 0);
+      cp_async8(dst + 1, n >= 2 ? src + 1 : P, n >= 2 ? 8 : 0);
+    }
+  }
+}
+
+template <bool TA, bool TB, int WM, int WN, int MF, int NF>
+__global__ void __launch_bounds__(WM* WN * 32) dgemm_pipe_kernel(int M, int N, int K, double alpha,
+                                                                const double* __restrict__ A, int64_t lda,
+                                                                const double* __restrict__ B, int64_t ldb, double beta,
+                                                                double* __restrict__ C, int64_t ldc, int tri_k, int a16,
+                                                                int b16) {
+  constexpr int BM = WM * 8 * MF, BNN = WN * 8 * NF, NTHR = WM * WN * 32;
+  constexpr int AS = TA ? BM + 4 : PK + 4, BS = TB ? PK + 4 : BNN + 4;
+  constexpr int A_EL = TA ? PK * (BM + 4) : BM * (PK + 4);
+  constexpr int B_EL = TB ? BNN * (PK + 4) : PK * (BNN + 4);
+  extern __shared__ __align__(16) double dg_smem[];
+  double* As = dg_smem;
+  double* Bs = dg_smem + PST * A_EL;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  // tri_k: op(B)[k][n] is zero for k > n (B lower triangular, used transposed): stop at the tile's last column
-  if (tri_k) K = min(K, n0 + BN);
+  const int wm = warp / WN, wn = warp % WN;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BNN;
+  if (tri_k) K = min(K, n0 + BNN);
+  const int KT = (K + PK - 1) / PK;
 
-  // staging maps: consecutive threads walk the contiguous index of each operand
-  int a_m[AV], a_k[AV], b_n[BV], b_k[BV];
-#pragma unroll
-  for (int i = 0; i < AV; ++i) {
-    const int e = tid + i * 256;
-    if (!TA) { a_k[i] = e % BK; a_m[i] = e / BK; } else { a_m[i] = e % BM; a_k[i] = e / BM; }
-  }
-#pragma unroll
-  for (int i = 0; i < BV; ++i) {
-    const int e = tid + i * 256;
-    if (!TB) { b_n[i] = e % BN; b_k[i] = e / BN; } else { b_k[i] = e % BK; b_n[i] = e / BK; }
-  }
-  auto fetchA = [&](int k0, double* r) {
-#pragma unroll
-    for (int i = 0; i < AV; ++i) {
-      const int m = m0 + a_m[i], k = k0 + a_k[i];
-      r[i] = (m < M && k < K) ? (TA ? A[(int64_t)k * lda + m] : A[(int64_t)m * lda + k]) : 0.0;
-    }
-  };
-  auto fetchB = [&](int k0, double* r) {
-#pragma unroll
-    for (int i = 0; i < BV; ++i) {
-      const int n = n0 + b_n[i], k = k0 + b_k[i];
-      r[i] = (n < N && k < K) ? (TB ? B[(int64_t)n * ldb + k] : B[(int64_t)k * ldb + n]) : 0.0;
-    }
-  };
-  auto stage = [&](int buf, const double* ra, const double* rb) {
-#pragma unroll
-    for (int i = 0; i < AV; ++i) As[buf][a_k[i] >> 2][a_m[i]][a_k[i] & 3] = ra[i];
-#pragma unroll
-    for (int i = 0; i < BV; ++i) Bs[buf][b_k[i] >> 2][b_n[i]][b_k[i] & 3] = rb[i];
+  auto load = [&](int kt, int st) {
+    stage_tile<!TA, BM, NTHR>(As + st * A_EL, A, lda, m0, M, kt * PK, K, a16, tid);
+    stage_tile<TB, BNN, NTHR>(Bs + st * B_EL, B, ldb, n0, N, kt * PK, K, b16, tid);
   };
 
-  double acc[MF][4][2];
+  double acc[MF][NF][2];
 #pragma unroll
   for (int i = 0; i < MF; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  double ra[AV], rb[BV];
-  fetchA(0, ra);
-  fetchB(0, rb);
-  stage(0, ra, rb);
-  __syncthreads();
-  int buf = 0;
-  const int fr = lane >> 2, fk = lane & 3;  // fragment row / k index of this lane
-  for (int k0 = 0; k0 < K; k0 += BK) {
-    const bool more = k0 + BK < K;
-    if (more) {
-      fetchA(k0 + BK, ra);
-      fetchB(k0 + BK, rb);
-    }
 #pragma unroll
-    for (int kc = 0; kc < BK / 4; ++kc) {
-      double af[MF], bf[4];
+  for (int s = 0; s < PST - 1; ++s) {
+    if (s < KT) load(s, s);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  const int fr = lane >> 2, fk = lane & 3;
+  for (int kt = 0; kt < KT; ++kt) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(PST - 2) : "memory");
+    __syncthreads();
+    if (kt + PST - 1 < KT) load(kt + PST - 1, (kt + PST - 1) % PST);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const double* as = As + (kt % PST) * A_EL;
+    const double* bs = Bs + (kt % PST) * B_EL;
 #pragma unroll
-      for (int i = 0; i < MF; ++i) af[i] = As[buf][kc][wm * (8 * MF) + i * 8 + fr][fk];
+    for (int kc = 0; kc < PK / 4; ++kc) {
+      double af[MF], bf[NF];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bf[j] = Bs[buf][kc][wn * 32 + j * 8 + fr][fk];
+      for (int i = 0; i < MF; ++i) {
+        const int r = wm * (8 * MF) + i * 8 + fr, k = kc * 4 + fk;
+        af[i] = TA ? as[k * AS + r] : as[r * AS + k];
+      }
+#pragma unroll
+      for (int j = 0; j < NF; ++j) {
+        const int c = wn * (8 * NF) + j * 8 + fr, k = kc * 4 + fk;
+        bf[j] = TB ? bs[c * BS + k] : bs[k * BS + c];
+      }
 #pragma unroll
       for (int i = 0; i < MF; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-    }
-    if (more) {
-      stage(buf ^ 1, ra, rb);
-      __syncthreads();
-      buf ^= 1;
+        for (int j = 0; j < NF; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
   }
 
-  // C fragment: row = lane / 4, columns = (lane % 4) * 2 + {0, 1}
 #pragma unroll
   for (int i = 0; i < MF; ++i) {
     const int m = m0 + wm * (8 * MF) + i * 8 + fr;
     if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NF; ++j) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int n = n0 + wn * 32 + j * 8 + fk * 2 + h;
+        const int n = n0 + wn * (8 * NF) + j * 8 + fk * 2 + h;
         if (n >= N) continue;
         double* c = C + (int64_t)m * ldc + n;
         *c = (beta == 0.0) ? alpha * acc[i][j][h] : fma(alpha, acc[i][j][h], beta * (*c));
@@ -126,18 +162,35 @@ __global__ void __launch_bounds__(256) dgemm_kernel(int M, int N, int K, double 
   }
 }
 
-template <bool TA, bool TB>
-void launch(basq_ctx* ctx, int m, int n, int k, double alpha, const double* A, int64_t lda, const double* B,
-            int64_t ldb, double beta, double* C, int64_t ldc, int tri_k) {
-  const int64_t tiles128 = (int64_t)ceil_div(m, 128) * ceil_div(n, BN);
-  if (tiles128 >= ctx->num_sms / 2) {
-    dim3 grid((unsigned)ceil_div(n, BN), (unsigned)ceil_div(m, 128));
-    dgemm_kernel<TA, TB, 8><<<grid, 256, 0, ctx->stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k);
-  } else {
-    dim3 grid((unsigned)ceil_div(n, BN), (unsigned)ceil_div(m, 64));
-    dgemm_kernel<TA, TB, 4><<<grid, 256, 0, ctx->stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k);
-  }
+template <bool TA, bool TB, int WM, int WN, int MF, int NF>
+int launch_pipe(basq_ctx* ctx, int m, int n, int k, double alpha, const double* A, int64_t lda, const double* B,
+                int64_t ldb, double beta, double* C, int64_t ldc, int tri_k) {
+  constexpr int BM = WM * 8 * MF, BNN = WN * 8 * NF;
+  constexpr int A_EL = TA ? PK * (BM + 4) : BM * (PK + 4);
+  constexpr int B_EL = TB ? BNN * (PK + 4) : PK * (BNN + 4);
+  constexpr int SMEM = PST * (A_EL + B_EL) * 8;
+  auto kern = dgemm_pipe_kernel<TA, TB, WM, WN, MF, NF>;
+  BASQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+  const int a16 = (lda % 2 == 0) && ((uintptr_t)A % 16 == 0), b16 = (ldb % 2 == 0) && ((uintptr_t)B % 16 == 0);
+  dim3 grid((unsigned)ceil_div(n, BNN), (unsigned)ceil_div(m, BM));
+  kern<<<grid, WM * WN * 32, SMEM, ctx->stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k, a16, b16);
+  return BASQ_OK;
 }
+
+// tile shape that needs the fewest SM-waves of work for an m x n output
+template <bool TA, bool TB>
+int launch_best(basq_ctx* ctx, int m, int n, int k, double alpha, const double* A, int64_t lda, const double* B,
+                int64_t ldb, double beta, double* C, int64_t ldc, int tri_k) {
+  auto cost = [&](int bm, int bn) {
+    const int64_t tiles = (int64_t)ceil_div(m, bm) * ceil_div(n, bn);
+    return (double)ceil_div64(tiles, ctx->num_sms) * bm * bn;
+  };
+  const double c0 = cost(128, 128), c1 = cost(128, 112), c2 = cost(64, 128);
+  if (c1 < c0 && c1 <= c2) return launch_pipe<TA, TB, 4, 2, 4, 7>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k);
+  if (c2 < c0) return launch_pipe<TA, TB, 2, 4, 4, 4>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k);
+  return launch_pipe<TA, TB, 2, 4, 8, 4>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k);
+}
+
 }  // namespace
 
 int dgemm(basq_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const double* A, int64_t lda,
@@ -146,10 +199,10 @@ int dgemm(basq_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, co
   if (m <= 0 || n <= 0) return BASQ_OK;
   BASQ_CHECK(k >= 0, BASQ_ERR_INVALID, "dgemm: negative k");
   BASQ_CHECK(ceil_div(m, 64) <= 65535, BASQ_ERR_UNSUPPORTED, "dgemm: m=%d too large for one launch", m);
-  if (!ta && !tb) launch<false, false>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k);
-  else if (ta && !tb) launch<true, false>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k);
-  else if (!ta && tb) launch<false, true>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k);
-  else launch<true, true>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k);
+  if (!ta && !tb) BASQ_TRY((launch_best<false, false>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k)));
+  else if (ta && !tb) BASQ_TRY((launch_best<true, false>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k)));
+  else if (!ta && tb) BASQ_TRY((launch_best<false, true>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k)));
+  else BASQ_TRY((launch_best<true, true>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k)));
   ctx->launches++;
   BASQ_CUDA(cudaGetLastError());
   return BASQ_OK;

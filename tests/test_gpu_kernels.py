@@ -30,7 +30,8 @@ def rel(a, b):
 
 # ------------------------------------------------------------------------------------------- dgemm
 @pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
-@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (65, 33, 17), (128, 64, 256), (200, 130, 1001)])
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (65, 33, 17), (128, 64, 256), (200, 130, 1001), (999, 2000, 130),
+                                   (300, 999, 64), (64, 2002, 48)])
 def test_dgemm(bq, ta, tb, m, n, k):
     _, _, ops = bq
     g = torch.Generator().manual_seed(m * 7 + n)
