@@ -184,18 +184,24 @@ __global__ void __launch_bounds__(NT, 1) car2_kernel(const Car2Dev a) {
 
   // rank-1 update of the own rows with pivot-row entries `pr` (pivot column cs); skip_row: the
   // pivot row itself when it lives in this CTA
+  static_assert(CPT <= 4 && RPT <= 4, "the column / row selectors below enumerate up to four slots");
   auto eliminate = [&](const double (&pr)[CPT], int cs, int skip_row) {
     const int js = cs / NT;
     if ((cs % NT) == tid) {
+      // this thread holds column cs: publish the multipliers of the B rows.  js is uniform, so a
+      // switch with static register indices replaces B*CPT select chains.
       elig &= ~(1u << js);
-#pragma unroll
-      for (int i2 = 0; i2 < B; ++i2) {
-        double f = 0.0;
-#pragma unroll
-        for (int j = 0; j < CPT; ++j)
-          if (j == js) f = reg[i2][j];
-        fbuf[par][i2] = f;
+#define BASQ_CAR_COL(J)                                                   \
+  if (J < CPT) {                                                          \
+    _Pragma("unroll") for (int i2 = 0; i2 < B; ++i2) fbuf[par][i2] = reg[i2][J < CPT ? J : 0]; \
+  }
+      switch (js) {
+        case 0: BASQ_CAR_COL(0) break;
+        case 1: BASQ_CAR_COL(1) break;
+        case 2: BASQ_CAR_COL(2) break;
+        default: BASQ_CAR_COL(3) break;
       }
+#undef BASQ_CAR_COL
     }
     __syncthreads();
 #pragma unroll
@@ -207,11 +213,12 @@ __global__ void __launch_bounds__(NT, 1) car2_kernel(const Car2Dev a) {
       }
     }
     if ((cs % NT) == tid) {  // the eliminated column is exactly zero in every other row
-#pragma unroll
-      for (int i2 = 0; i2 < B; ++i2)
-#pragma unroll
-        for (int j = 0; j < CPT; ++j)
-          if (j == js && i2 != skip_row) reg[i2][j] = 0.0;
+      switch (js) {
+        case 0: _Pragma("unroll") for (int i2 = 0; i2 < B; ++i2) if (i2 != skip_row) reg[i2][0] = 0.0; break;
+        case 1: _Pragma("unroll") for (int i2 = 0; i2 < B; ++i2) if (i2 != skip_row && CPT > 1) reg[i2][CPT > 1 ? 1 : 0] = 0.0; break;
+        case 2: _Pragma("unroll") for (int i2 = 0; i2 < B; ++i2) if (i2 != skip_row && CPT > 2) reg[i2][CPT > 2 ? 2 : 0] = 0.0; break;
+        default: _Pragma("unroll") for (int i2 = 0; i2 < B; ++i2) if (i2 != skip_row && CPT > 3) reg[i2][CPT > 3 ? 3 : 0] = 0.0; break;
+      }
     }
     par ^= 1;
   };
