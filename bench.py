@@ -6,12 +6,13 @@ recombined per second, N -> n at d = 10).
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One step = one full pass of the hot path over one batch of synthetic candidates: Nystrom basis of
-the landmark Gram matrix + the Tchernychova-Lyons / Caratheodory loop down to <= n weighted points.
+the landmark Gram matrix + the Tchernychova-Lyons / Caratheodory loop (refined passes)
+down to <= n weighted points.
 Workload (config.workload): BASELINE config 3 - 10-D Gaussian-mixture setting, batch n = 1000,
 N_rec = 1e7 candidates PER GPU (weak scaling: every rank owns 1e7 candidates, one 16 MB all-reduce
-per round), M = 1e4 landmarks, RBF kernel, VBQ posterior-covariance kernel object with n_obs = 1002.
+per Caratheodory level), M = 1e4 landmarks, RBF kernel, VBQ posterior-covariance kernel object with n_obs = 1002.
 `value` times the device-resident path; `e2e` times the host-buffer C-ABI call including the
-host<->device copies.  `--impl reference` times the CPU oracle port of the reference's algorithm
+host<->device copies; `iteration` times one BASQ iteration with the candidates drawn on the device.  `--impl reference` times the CPU oracle port of the reference's algorithm
 on a bounded sample (the reference is pure Python and does not ship to the GPU box).
 """
 from __future__ import annotations
@@ -209,6 +210,26 @@ def run_ours(a, rank, world, local_rank):
         idx, w = sharded.recombination_sharded(Xd, Zd, a.n, kern, N_glob, rank * N_loc, U)
         return idx.cpu(), w.cpu()
 
+    # BASELINE metric (2), "BASQ iteration time": candidates drawn on the device from the prior (every
+    # rank its slice of one Philox stream), landmarks = leading rows, Nystrom basis, recombination
+    # (GP hyper-parameter refit excluded, as in the reference's tutorial timing - SURVEY 8d)
+    from basq_b200 import sampler as bsampler
+    prior_mean = torch.zeros(a.d, dtype=torch.float64)
+    prior_tril = math.sqrt(2.0) * torch.eye(a.d, dtype=torch.float64)
+    it_count = [0]
+
+    def step_iteration():
+        it_count[0] += 1
+        seed = 4242 + it_count[0]
+        Xs = bsampler.sample_mvn(prior_mean, None, N_loc, seed=seed, offset=rank * N_loc, device=dev,
+                                 scale_tril=prior_tril)
+        Zs = Xs[: a.M] if world == 1 else bsampler.sample_mvn(prior_mean, None, a.M, seed=seed, offset=0, device=dev,
+                                                              scale_tril=prior_tril)
+        _, U = ops.nystrom_basis(kern, Zs, q, omega=Omega, want_S=False)
+        if world == 1:
+            return ops.recombine(kern, Xs, Zs, U)
+        return sharded.recombination_sharded(Xs, Zs, a.n, kern, N_glob, rank * N_loc, U)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -257,6 +278,10 @@ def run_ours(a, rank, world, local_rank):
         e2e = {"value": N_glob / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
 
+    step_iteration()
+    ms_iter, out3 = timed(step_iteration, a.steps)
+    assert 1 <= len(out3[0]) <= a.n and abs(float(out3[1].sum()) - 1.0) < 1e-9
+
     line = None
     if rank == 0:
         peaks = {}
@@ -292,6 +317,9 @@ def run_ours(a, rank, world, local_rank):
             "config": {"workload": workload_name(a), "N_total": N_glob, "parallelism": f"dp{world}",
                        "l2_policy": "inputs (640 MB of candidate records per GPU) exceed the 126 MB L2"},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
+            "iteration": {"ms": ms_iter, "unit": "ms per BASQ iteration",
+                          "what": "device prior sampling (Philox MVN) + Nystrom basis + recombination to n points; "
+                                  "GP refit excluded (BASELINE metric part 2)"},
             "phases_ms": {k: round(v[0] / a.steps, 3) for k, v in prof.items()}, "rounds": n_rounds,
             "roofline": {
                 "bound": "tensor", "kernel": "setsum_mma_kernel<RBF, 10> (tcgen05 kind::tf32 distance contraction + ex2 epilogue)",
