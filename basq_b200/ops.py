@@ -6,6 +6,7 @@ from __future__ import annotations
 
 import ctypes as C
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -216,10 +217,11 @@ class Session:
         """Local part of level `lvl` of the current pass into A [n, S] (see basq_session_level)."""
         assert A.dtype == torch.float64 and A.is_contiguous() and A.shape == (self.n, self.S)
         K = len(node)
-        nd = (C.c_int * K)(*node)
-        pp = (C.c_int * K)(*(ppos if lvl > 0 else [0] * K))
-        fp = (C.c_double * K)(*fpar)
-        _lib.check(_lib.lib.basq_session_level(self.handle, int(lvl), K, nd, pp, fp, A.data_ptr()))
+        nd = np.ascontiguousarray(node, dtype=np.int32)
+        pp = np.ascontiguousarray(ppos if lvl > 0 else np.zeros(K), dtype=np.int32)
+        fp = np.ascontiguousarray(fpar, dtype=np.float64)
+        _lib.check(_lib.lib.basq_session_level(self.handle, int(lvl), K, nd.ctypes.data, pp.ctypes.data,
+                                               fp.ctypes.data, A.data_ptr()))
 
     def car(self, A: torch.Tensor, C_cols: int, omega: torch.Tensor):
         _lib.check(_lib.lib.basq_car(self.ctx.handle, A.data_ptr(), self.n, int(C_cols), self.S, omega.data_ptr(), None))

@@ -12,6 +12,7 @@ gloo and an oracle-backed engine (tests/test_sharded_gloo.py); the product engin
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -33,13 +34,16 @@ def kept_before(g, S, keep_prefix, K):
 class LevelTree:
     """Host bookkeeping of one pass (mirror of LevelTree in csrc/api.cu): which nodes of the cell
     hierarchy are presented to the next Caratheodory level.  Node u of level l = cells
-    u + k * S * 2^l; its children are u (low half) and u + S * 2^l (high half)."""
+    u + k * S * 2^l; its children are u (low half) and u + S * 2^l (high half).  numpy arrays
+    throughout (int32 node ids / parent columns, fp64 factors): they go to the C ABI as they are."""
 
     def __init__(self, S, F, R_glob):
         self.S, self.F, self.L, self.lvl = S, F, F.bit_length() - 1, 0
         S0 = min(S, R_glob)
-        self.node, self.ppos, self.fpar = list(range(S0)), [0] * S0, [1.0] * S0
-        self.act, self.fac = list(self.node), list(self.fpar)
+        self.node = np.arange(S0, dtype=np.int32)
+        self.ppos = np.zeros(S0, dtype=np.int32)
+        self.fpar = np.ones(S0, dtype=np.float64)
+        self.act, self.fac = self.node, self.fpar
 
     def columns(self):
         return len(self.act)
@@ -47,22 +51,19 @@ class LevelTree:
     def advance(self, om, factor):
         """Consume the level's factors om (1 = untouched).  Returns (more_levels, kept); after the
         last level `factor` [F*S] holds the product of the factors along every surviving path."""
-        stride = self.S << self.lvl
-        node, ppos, fpar, kept = [], [], [], 0
-        for i, (u, f0, o) in enumerate(zip(self.act, self.fac, om)):
-            f = f0 * o
-            if not (o > 0.0 and f > 0.0):
-                continue
-            kept += 1
-            if self.lvl < self.L:
-                node.append(u); ppos.append(i); fpar.append(f)
-            else:
-                factor[u] = f
+        om = np.asarray(om, dtype=np.float64)
+        f = self.fac * om
+        keep = np.nonzero((om > 0.0) & (f > 0.0))[0]
+        kept = len(keep)
         if self.lvl == self.L:
+            factor[torch.from_numpy(self.act[keep].astype(np.int64))] = torch.from_numpy(f[keep])
             return False, kept
-        self.node, self.ppos, self.fpar = node, ppos, fpar
-        self.act = node + [u + stride for u in node]
-        self.fac = fpar + fpar
+        stride = self.S << self.lvl
+        self.node = np.ascontiguousarray(self.act[keep], dtype=np.int32)
+        self.ppos = keep.astype(np.int32)
+        self.fpar = np.ascontiguousarray(f[keep])
+        self.act = np.concatenate([self.node, self.node + np.int32(stride)])
+        self.fac = np.concatenate([self.fpar, self.fpar])
         self.lvl += 1
         return True, kept
 
@@ -104,9 +105,9 @@ def recombine_sharded(engine, n, S, group=None, device=None, max_rounds=256):
                 if world > 1:
                     dist.all_reduce(A, group=group)
                 engine.car(A, C, omega)                   # identical system -> identical factors on every rank
-                om = omega[:C].cpu().tolist()
+                om = omega[:C].cpu().numpy()
             else:
-                om = [1.0] * C
+                om = np.ones(C)
             more, kept = tree.advance(om, factor)
             if kept < 1:
                 raise RuntimeError("recombine_sharded: the Caratheodory step kept no set")

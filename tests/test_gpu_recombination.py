@@ -257,9 +257,9 @@ def test_staged_session_two_shards_one_gpu(bq):
                 kept_cols = (A0 + A1)[:, :C].cpu() @ om
                 assert float(torch.linalg.norm(kept_cols - total) / torch.linalg.norm(total)) < 1e-11
                 assert int((om > 0).sum()) <= n
-                om = om.tolist()
+                om = om.numpy()
             else:
-                om = [1.0] * C
+                om = np.ones(C)
             more, kept = tree.advance(om, factor)
             assert kept >= 1
             if not more:

@@ -55,8 +55,8 @@ class OracleEngine:
         """Columns of the level's nodes, every one folded directly from the cell columns (the
         library derives the high halves as parent - low half; the two must agree)."""
         stride, cnt = self.S << lvl, self.F >> lvl
-        ids = list(node) + ([u + (self.S << (lvl - 1)) for u in node] if lvl > 0 else [])
-        fs = list(fpar) + (list(fpar) if lvl > 0 else [])
+        ids = [int(u) for u in node] + ([int(u) + (self.S << (lvl - 1)) for u in node] if lvl > 0 else [])
+        fs = [float(f) for f in fpar] * (2 if lvl > 0 else 1)
         A.zero_()
         for i, (u, f) in enumerate(zip(ids, fs)):
             A[:, i] = f * sum(self.cellA[:, u + k * stride] for k in range(cnt))
