@@ -248,8 +248,11 @@ int session_create_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
 
   s->ldg = 0;  // G and the rank table are sized by the first pass (session_reserve_cells)
   if (nonlin) {
-    int64_t P = (int64_t)(96ll << 20) / (8ll * std::max<int64_t>(M, n_obs));
-    P = std::max<int64_t>(1024, std::min<int64_t>(P, 65536));
+    // points per chunk of the pairwise correction: corrT [P, M] may take up to 2 GB, so that a chunk
+    // spans many cells of a refined pass (every chunk re-reads the G columns it touches)
+    int64_t P = (int64_t)(2048ll << 20) / (8ll * std::max<int64_t>(M, n_obs));
+    P = std::max<int64_t>(1024, std::min<int64_t>(P, 131072));
+    P = std::min<int64_t>(P, std::max<int64_t>(N_loc, 1024));
     s->chunkP = P;
     BASQ_TRY(s->V.alloc(ctx, sizeof(double) * (size_t)n_obs * P));
     BASQ_TRY(s->corrT.alloc(ctx, sizeof(double) * (size_t)M * P));
@@ -288,7 +291,6 @@ int session_pass_begin(basq_session* s, int64_t R_glob, int64_t off, int F) {
   BASQ_CHECK(off >= 0 && off + s->pool.count <= R_glob, BASQ_ERR_INVALID,
              "pass: offset %lld + local %lld exceeds global %lld", (long long)off, (long long)s->pool.count,
              (long long)R_glob);
-  BASQ_CHECK(F == 1 || s->nl == NL_LIN, BASQ_ERR_UNSUPPORTED, "pass: the non-linear modes use plain rounds (F = 1)");
   const int c_eff = (int)std::min<int64_t>(cells, R_glob);
   BASQ_TRY(session_reserve_cells(s, cells));
   if (!s->Gf.p) {
@@ -475,9 +477,16 @@ int session_apply_impl(basq_session* s, int64_t R_glob, int64_t off, int F, cons
 // the lowest cost per level.  One evaluation ~ 4.4 fp64-GEMM flop at the measured kernel rates.
 int choose_cell_factor(const basq_session* s, int64_t R_glob, int64_t R_loc_max) {
   static const int forced = [] { const char* e = getenv("BASQ_CELL_FACTOR"); return e ? atoi(e) : 0; }();
-  if (s->nl != NL_LIN) return 1;  // the chunked non-linear path keeps the plain round
   const int64_t S = s->S;
   auto fits = [&](int f) { return R_glob >= (int64_t)4 * f * S; };
+  if (s->nl != NL_LIN && forced < 1) {
+    // pairwise non-linear kernels (WSABI-M, MMLT): a sweep costs an extra 2 n_obs M fp64 flop per
+    // candidate (the posterior correction per pair), far more than any projection: refine as far as
+    // the cells keep a handful of members
+    int F = 1;
+    while (F * 2 <= BASQ_MAX_CELL_FACTOR && fits(F * 2) && R_loc_max >= (int64_t)8 * F * 2 * S) F *= 2;
+    return F;
+  }
   if (forced >= 1) {
     int F = 1;
     while (F * 2 <= forced && F * 2 <= BASQ_MAX_CELL_FACTOR && fits(F * 2)) F *= 2;

@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(128) setsum_kernel(const SetSumDev a) {
   }
   const int64_t n_e = e_hi > e_lo ? e_hi - e_lo : 0;
   const int64_t n_chunks = (n_e + EC - 1) / EC;
+  if (a.accumulate && n_e == 0) return;  // nothing of this point range falls into the CTA's sets (uniform over the CTA)
 
   auto load_chunk = [&](int64_t c, int stage) {
     if (c < n_chunks) {
