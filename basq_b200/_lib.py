@@ -59,6 +59,9 @@ def _load():
         "basq_features": (I, [P, KD, P, L, P, L, P, I, P]),
         "basq_car": (I, [P, P, I, I, I, P, C.POINTER(I)]),
         "basq_recombine": (I, [P, KD, P, L, P, L, P, I, P, P, P, C.POINTER(I)]),
+        "basq_recombine_objective": (I, [P, KD, P, L, P, L, P, I, P, P, P, P, C.POINTER(I)]),
+        "basq_car_objective": (I, [P, P, I, I, I, P]),
+        "basq_session_set_objective": (I, [P, P]),
         "basq_recombine_host": (I, [P, KD, P, L, P, L, P, I, P, I, P, P, P, C.POINTER(I)]),
         "basq_session_create": (I, [P, KD, P, L, L, L, P, L, P, I, P, C.POINTER(P)]),
         "basq_session_destroy": (None, [P]),

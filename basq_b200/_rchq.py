@@ -49,14 +49,12 @@ def recombination(pts_rec, pts_nys, num_pts, kernel, device, *args, **kwargs):
     calc_obj = kwargs.pop("calc_obj", args.pop(0) if args else None)
     if args or kwargs:
         raise TypeError(f"recombination() got unexpected arguments {args} {kwargs}")
-    if calc_obj is not None:
-        raise NotImplementedError("calc_obj (SOBER/_rchq.py:67-69) is not on the accelerated path yet")
     mu = _as_weights(init_weights, len(pts_rec))
     if not sober and not HONOUR_INIT_WEIGHTS_IN_BASQ_SIGNATURE:
         mu = None
     if dtype is not None:
         pts_rec, pts_nys = pts_rec.to(dtype), pts_nys.to(dtype)
-    return rc_kernel_svd(pts_rec, pts_nys, num_pts, kernel, device, mu=mu)
+    return rc_kernel_svd(pts_rec, pts_nys, num_pts, kernel, device, mu=mu, calc_obj=calc_obj)
 
 
 def ker_svd_sparsify(pt, s, kernel, device=None):
@@ -68,19 +66,24 @@ def ker_svd_sparsify(pt, s, kernel, device=None):
     return S.to(pt.dtype), U.to(pt.dtype)
 
 
-def rc_kernel_svd(samp, pt, s, kernel, device, mu=None, use_obj=True):
-    """BASQ/_rchq.py:34-40: Nystrom basis, then the Tchernychova-Lyons loop.  Returns (idx, w)."""
+def rc_kernel_svd(samp, pt, s, kernel, device, mu=None, use_obj=True, calc_obj=None):
+    """BASQ/_rchq.py:34-40 (SOBER/_rchq.py:33-46 with calc_obj): Nystrom basis, then the
+    Tchernychova-Lyons loop.  Returns (idx, w)."""
     device = torch.device(device)
     _, U = ops.nystrom_basis(kernel, pt, s - 1, device=device, want_S=False)
-    w_star, idx_star = Mod_Tchernychova_Lyons(samp, U, pt, kernel, device, mu=mu)
+    w_star, idx_star = Mod_Tchernychova_Lyons(samp, U, pt, kernel, device, mu=mu, calc_obj=calc_obj)
     return idx_star, w_star
 
 
-def Mod_Tchernychova_Lyons(samp, U_svd, pt_nys, kernel, device, mu=None, use_obj=True, DEBUG=False):
-    """BASQ/_rchq.py:43-130.  Returns ``(w_star, idx_star)`` like the reference."""
+def Mod_Tchernychova_Lyons(samp, U_svd, pt_nys, kernel, device, mu=None, use_obj=True, DEBUG=False, calc_obj=None):
+    """BASQ/_rchq.py:43-130 (SOBER/_rchq.py:48-219 with ``calc_obj``: a callable samp -> [N] whose
+    expectation under the rule is pushed up, :67-69).  Returns ``(w_star, idx_star)`` like the reference."""
     device = torch.device(device)
     weights = _as_weights(mu, len(samp))
-    idx, w = ops.recombine(kernel, samp, pt_nys, U_svd, mu=weights, device=device)
+    obj = None
+    if calc_obj is not None:
+        obj = -1.0 * torch.as_tensor(calc_obj(samp)).reshape(-1)          # SOBER/_rchq.py:69
+    idx, w = ops.recombine(kernel, samp, pt_nys, U_svd, mu=weights, device=device, obj=obj)
     out_dtype = samp.dtype if samp.dtype in (torch.float32, torch.float64) else torch.float32
     return w.to(out_dtype), idx
 

@@ -120,7 +120,10 @@ struct basq_session {
   // state of the current pass (session_pass_begin / session_level)
   int pass_F = 0;
   int64_t pass_R = 0, pass_off = 0;
+  const double* obj = nullptr;  // [N_loc] objective per original local row (objective-aware mode), or NULL
+  int rows = 0;                 // rows of a level system: n, or n + 1 with the objective row
   DevBuf cellmass;  // [cells] mass of every cell
+  DevBuf cellobj;   // [cells] objective sum of every cell
   DevBuf Gf;        // [Mtot, S] folded set-sum columns of a level
   DevBuf raw[2];    // [n, S] unscaled local columns of the current / previous level
   int raw_cur = 0;
@@ -192,6 +195,7 @@ int session_create_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
   s->M = (int)M;
   s->q = q;
   s->n = q + 1;
+  s->rows = s->n;
   s->S = S_override > 0 ? S_override : 2 * (q + 1);
   s->idx_base = idx_base;
   const int mode = desc->mode;
@@ -272,7 +276,9 @@ int session_reserve_cells(basq_session* s, int cells) {
   BASQ_TRY(s->G.alloc(ctx, sizeof(double) * (size_t)s->Mtot * s->ldg));
   BASQ_TRY(s->rank.alloc(ctx, sizeof(int) * (size_t)cells));
   s->cellmass.release();
+  s->cellobj.release();
   BASQ_TRY(s->cellmass.alloc(ctx, sizeof(double) * (size_t)cells));
+  BASQ_TRY(s->cellobj.alloc(ctx, sizeof(double) * (size_t)cells));
   s->omega_host.resize(cells);
   s->rank_host.resize(cells);
   return BASQ_OK;
@@ -295,7 +301,7 @@ int session_pass_begin(basq_session* s, int64_t R_glob, int64_t off, int F) {
   BASQ_TRY(session_reserve_cells(s, cells));
   if (!s->Gf.p) {
     BASQ_TRY(s->Gf.alloc(ctx, sizeof(double) * (size_t)s->Mtot * s->S));
-    for (int i = 0; i < 2; ++i) BASQ_TRY(s->raw[i].alloc(ctx, sizeof(double) * (size_t)s->n * s->S));
+    for (int i = 0; i < 2; ++i) BASQ_TRY(s->raw[i].alloc(ctx, sizeof(double) * (size_t)(s->n + 1) * s->S));
     BASQ_TRY(s->lnode.alloc(ctx, sizeof(int) * s->S));
     BASQ_TRY(s->lppos.alloc(ctx, sizeof(int) * s->S));
     BASQ_TRY(s->lfpar.alloc(ctx, sizeof(double) * s->S));
@@ -305,6 +311,7 @@ int session_pass_begin(basq_session* s, int64_t R_glob, int64_t off, int F) {
   s->pass_off = off;
   PhaseTimer t(ctx, PH_SETSUM);
   BASQ_TRY(set_masses(ctx, s->pool, off, cells, c_eff, s->cellmass.as<double>()));
+  if (s->obj) BASQ_TRY(cell_objective(ctx, s->pool, off, cells, c_eff, s->obj, s->cellobj.as<double>()));
   BASQ_TRY(session_set_sums(s, off, cells, 0, s->pool.count, s->G.as<double>(), s->ldg));
   return BASQ_OK;
 }
@@ -318,7 +325,7 @@ int session_pass_begin(basq_session* s, int64_t R_glob, int64_t off, int F) {
 int session_level(basq_session* s, int lvl, int K, const int* node_host, const int* ppos_host,
                   const double* fpar_host, double* A_out) {
   basq_ctx* ctx = s->ctx;
-  const int n = s->n, S = s->S, F = s->pass_F;
+  const int n = s->n, S = s->S, F = s->pass_F, rows = s->rows;
   BASQ_CHECK(F >= 1 && lvl >= 0 && (1 << lvl) <= F, BASQ_ERR_INVALID, "level %d outside the pass (F = %d)", lvl, F);
   const int C = lvl == 0 ? K : 2 * K;
   BASQ_CHECK(K >= 1 && C <= S, BASQ_ERR_INVALID, "level %d: %d columns exceed S = %d", lvl, C, S);
@@ -330,7 +337,7 @@ int session_level(basq_session* s, int lvl, int K, const int* node_host, const i
   BASQ_CUDA(cudaMemcpyAsync(s->lnode.p, node_host, sizeof(int) * K, cudaMemcpyHostToDevice, ctx->stream));
   if (lvl > 0) BASQ_CUDA(cudaMemcpyAsync(s->lppos.p, ppos_host, sizeof(int) * K, cudaMemcpyHostToDevice, ctx->stream));
   BASQ_CUDA(cudaMemcpyAsync(s->lfpar.p, fpar_host, sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
-  BASQ_CUDA(cudaMemsetAsync(A_out, 0, sizeof(double) * (size_t)n * S, ctx->stream));
+  BASQ_CUDA(cudaMemsetAsync(A_out, 0, sizeof(double) * (size_t)rows * S, ctx->stream));
   double* raw = s->raw[s->raw_cur].as<double>();
   const double* prev = s->raw[s->raw_cur ^ 1].as<double>();
   const double* Gsrc = s->G.as<double>();
@@ -348,9 +355,15 @@ int session_level(basq_session* s, int lvl, int K, const int* node_host, const i
                                                                           s->lnode.as<int>(), stride, cnt, raw, S);
   ctx->launches++;
   BASQ_CUDA(cudaGetLastError());
+  if (s->obj) {  // objective row (SOBER/_rchq.py:138-146), folded like the masses
+    fold_cols_kernel<<<(unsigned)ceil_div64(K, 256), 256, 0, ctx->stream>>>(s->cellobj.as<double>(), 0, 1, K,
+                                                                            s->lnode.as<int>(), stride, cnt,
+                                                                            raw + (int64_t)n * S, S);
+    ctx->launches++;
+  }
   BASQ_TRY(dgemm(ctx, false, false, s->q, K, s->Mtot, 1.0, s->Uprime.as<double>(), s->Mtot, Gsrc, ldsrc, 0.0, raw + S, S));
-  level_finish_kernel<<<(unsigned)ceil_div64((int64_t)n * K, 256), 256, 0, ctx->stream>>>(
-      raw, prev, n, K, lvl > 0 ? 1 : 0, s->lppos.as<int>(), s->lfpar.as<double>(), A_out, S);
+  level_finish_kernel<<<(unsigned)ceil_div64((int64_t)rows * K, 256), 256, 0, ctx->stream>>>(
+      raw, prev, rows, K, lvl > 0 ? 1 : 0, s->lppos.as<int>(), s->lfpar.as<double>(), A_out, S);
   ctx->launches++;
   BASQ_CUDA(cudaGetLastError());
   // the host arrays may be reused by the caller as soon as we return
@@ -403,6 +416,83 @@ struct LevelTree {
   }
 };
 
+// columns of A (ld) selected by pick[t] and scaled by scale[t]: out[r, t] = scale[t] * A[r, pick[t]]
+__global__ void gather_scaled_kernel(const double* __restrict__ A, int64_t ld, int rows, int K, const int* __restrict__ pick,
+                                     const double* __restrict__ scale, double* __restrict__ out, int64_t ldo) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)rows * K) return;
+  const int r = (int)(t / K), i = (int)(t % K);
+  out[(int64_t)r * ldo + i] = scale[i] * A[(int64_t)r * ld + pick[i]];
+}
+
+// One Caratheodory level with the objective row of SOBER/_rchq.py:67-69,138-146,177-196.
+// A [n + 1, C] (ld): rows 0..n-1 the moment system, row n the objective sums (obj = -calc_obj, so the
+// rule's expected calc_obj goes UP when sum_t omega_t A[n, t] goes down).  Step 1: Caratheodory on all
+// n + 1 rows keeps <= n + 1 columns and their objective value.  Step 2 (:177-196): the kept columns
+// have a one-dimensional null space with respect to the n moment rows; move along it in the
+// direction that does not increase the objective row until one more column drops: <= n columns
+// survive, the n moments are preserved exactly, the objective is at least as good as the measure's.
+// omega_out [C] (device) receives the final relative factors.  A is destroyed.
+int car_with_objective(basq_ctx* ctx, double* A, int n, int C, int lda, double* omega_out) {
+  DevBuf copy, dpick, dscale;
+  BASQ_TRY(copy.alloc(ctx, sizeof(double) * (size_t)(n + 1) * lda));
+  BASQ_CUDA(cudaMemcpyAsync(copy.p, A, sizeof(double) * (size_t)(n + 1) * lda, cudaMemcpyDeviceToDevice, ctx->stream));
+  BASQ_TRY(caratheodory(ctx, A, n + 1, C, lda, omega_out));
+  std::vector<double> om(C), objrow(C);
+  BASQ_CUDA(cudaMemcpyAsync(om.data(), omega_out, sizeof(double) * C, cudaMemcpyDeviceToHost, ctx->stream));
+  BASQ_CUDA(cudaMemcpyAsync(objrow.data(), copy.as<double>() + (int64_t)n * lda, sizeof(double) * C,
+                            cudaMemcpyDeviceToHost, ctx->stream));
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  BASQ_TRY(check_finite_host(om.data(), C, "omega"));
+  std::vector<int> pick;
+  std::vector<double> scale;
+  for (int i = 0; i < C; ++i)
+    if (om[i] > 0.0) { pick.push_back(i); scale.push_back(om[i]); }
+  const int K = (int)pick.size();
+  if (K <= n) return BASQ_OK;  // already small enough (rank-deficient system)
+  BASQ_CHECK(K == n + 1, BASQ_ERR_NUMERIC, "objective step: %d columns survive a system of %d rows", K, n + 1);
+  BASQ_TRY(dpick.alloc(ctx, sizeof(int) * K));
+  BASQ_TRY(dscale.alloc(ctx, sizeof(double) * K));
+  BASQ_CUDA(cudaMemcpyAsync(dpick.p, pick.data(), sizeof(int) * K, cudaMemcpyHostToDevice, ctx->stream));
+  BASQ_CUDA(cudaMemcpyAsync(dscale.p, scale.data(), sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
+  gather_scaled_kernel<<<(unsigned)ceil_div64((int64_t)n * K, 256), 256, 0, ctx->stream>>>(
+      copy.as<double>(), lda, n, K, dpick.as<int>(), dscale.as<double>(), A, lda);
+  ctx->launches++;
+  BASQ_CUDA(cudaGetLastError());
+  DevBuf om2;
+  BASQ_TRY(om2.alloc(ctx, sizeof(double) * K));
+  BASQ_TRY(caratheodory(ctx, A, n, K, lda, om2.as<double>()));
+  std::vector<double> w2(K);
+  BASQ_CUDA(cudaMemcpyAsync(w2.data(), om2.p, sizeof(double) * K, cudaMemcpyDeviceToHost, ctx->stream));
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  BASQ_TRY(check_finite_host(w2.data(), K, "omega (objective step)"));
+  // null direction v = 1 - w2 of the scaled columns; d = its objective slope
+  double d = 0.0;
+  for (int t = 0; t < K; ++t) d += (1.0 - w2[t]) * scale[t] * objrow[pick[t]];
+  std::vector<double> rho(K);
+  if (d >= 0.0) {
+    rho = w2;  // moving by -v lowers (or keeps) the objective row: the step the kernel took
+  } else {
+    double beta = -1.0;
+    int arg = -1;
+    for (int t = 0; t < K; ++t) {
+      const double v = 1.0 - w2[t];
+      if (v < 0.0 && (arg < 0 || 1.0 / (-v) < beta)) { beta = 1.0 / (-v); arg = t; }
+    }
+    if (arg < 0) {
+      rho = w2;  // the direction has no negative entry: only the kernel's side reaches a face
+    } else {
+      for (int t = 0; t < K; ++t) rho[t] = std::max(0.0, 1.0 + beta * (1.0 - w2[t]));
+      rho[arg] = 0.0;
+    }
+  }
+  for (int i = 0; i < C; ++i) om[i] = 0.0;
+  for (int t = 0; t < K; ++t) om[pick[t]] = scale[t] * rho[t];
+  BASQ_CUDA(cudaMemcpyAsync(omega_out, om.data(), sizeof(double) * C, cudaMemcpyHostToDevice, ctx->stream));
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BASQ_OK;
+}
+
 // All levels of the current pass for a single rank: factor_host[F * S] out.
 int session_pass_levels(basq_session* s, double* A, double* omega_dev, double* factor_host) {
   basq_ctx* ctx = s->ctx;
@@ -417,7 +507,8 @@ int session_pass_levels(basq_session* s, double* A, double* omega_dev, double* f
     const int C = tree.columns();
     if (C > n) {
       BASQ_TRY(session_level(s, tree.lvl, K, tree.node.data(), tree.ppos.data(), tree.fpar.data(), A));
-      BASQ_TRY(caratheodory(ctx, A, n, C, S, omega_dev));
+      if (s->obj) BASQ_TRY(car_with_objective(ctx, A, n, C, S, omega_dev));
+      else BASQ_TRY(caratheodory(ctx, A, n, C, S, omega_dev));
       BASQ_CUDA(cudaMemcpyAsync(om.data(), omega_dev, sizeof(double) * C, cudaMemcpyDeviceToHost, ctx->stream));
       BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
       BASQ_TRY(check_finite_host(om.data(), C, "omega"));
@@ -524,7 +615,8 @@ int session_features(basq_session* s, double* Phi_out) {
 }
 
 int recombine_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t N, const void* Z, int64_t M,
-                   const double* U, int q, const double* mu, int64_t* idx_out, double* w_out, int* n_out_host) {
+                   const double* U, int q, const double* mu, int64_t* idx_out, double* w_out, int* n_out_host,
+                   const double* obj = nullptr) {
   BASQ_CHECK(idx_out && w_out && n_out_host, BASQ_ERR_INVALID, "recombine: NULL output");
   std::unique_ptr<basq_session> s(new (std::nothrow) basq_session());
   BASQ_CHECK(s, BASQ_ERR_INVALID, "out of host memory");
@@ -532,8 +624,9 @@ int recombine_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, i
   BASQ_TRY(session_create_impl(ctx, desc, X, N, N, 0, Z, M, U, q, mu, 0, s.get()));
   trace_point(ctx, "recombine: session created");
   const int n = s->n, S = s->S;
+  if (obj) { s->obj = obj; s->rows = n + 1; }
   DevBuf A, omega;
-  BASQ_TRY(A.alloc(ctx, sizeof(double) * (size_t)n * S));
+  BASQ_TRY(A.alloc(ctx, sizeof(double) * (size_t)(n + 1) * S));
   BASQ_TRY(omega.alloc(ctx, sizeof(double) * S));
   int64_t R = s->pool.count;
   std::vector<double> factor;
@@ -823,6 +916,29 @@ int basq_recombine(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, i
   BASQ_CHECK(ctx, BASQ_ERR_INVALID, "ctx is NULL");
   BASQ_CUDA(cudaSetDevice(ctx->device));
   return recombine_impl(ctx, desc, X, N, Z, M, U, q, mu, idx_out, w_out, n_out_host);
+}
+
+int basq_recombine_objective(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t N, const void* Z,
+                             int64_t M, const double* U, int q, const double* mu, const double* obj, int64_t* idx_out,
+                             double* w_out, int* n_out_host) {
+  BASQ_CHECK(ctx && obj, BASQ_ERR_INVALID, "basq_recombine_objective: NULL argument");
+  BASQ_CUDA(cudaSetDevice(ctx->device));
+  return recombine_impl(ctx, desc, X, N, Z, M, U, q, mu, idx_out, w_out, n_out_host, obj);
+}
+
+int basq_car_objective(basq_ctx* ctx, double* A, int n, int C, int lda, double* omega_out) {
+  BASQ_CHECK(ctx && A && omega_out, BASQ_ERR_INVALID, "basq_car_objective: NULL argument");
+  BASQ_CHECK(n >= 1 && C >= 1 && lda >= C, BASQ_ERR_INVALID, "basq_car_objective: bad shape");
+  BASQ_CUDA(cudaSetDevice(ctx->device));
+  if (C <= n) return caratheodory(ctx, A, n, C, lda, omega_out);
+  return car_with_objective(ctx, A, n, C, lda, omega_out);
+}
+
+int basq_session_set_objective(basq_session* s, const double* obj) {
+  BASQ_CHECK(s, BASQ_ERR_INVALID, "NULL argument");
+  s->obj = obj;
+  s->rows = obj ? s->n + 1 : s->n;
+  return BASQ_OK;
 }
 
 int basq_recombine_host(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X_host, int64_t N,

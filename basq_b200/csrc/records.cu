@@ -178,6 +178,41 @@ int set_masses(basq_ctx* ctx, const RecPool& pool, int64_t off_glob, int S, int 
   return BASQ_OK;
 }
 
+// cell objective sums: out[j] = sum of mu_p * obj[idx_p] over local points in cell j (the extra row
+// of the objective-aware recombination, SOBER/_rchq.py:138-146); obj is indexed by the candidate's
+// original local row, which every record carries
+__global__ void cell_obj_kernel(const unsigned char* __restrict__ recs, int rec_bytes, int f64, int64_t count,
+                                int64_t off, int S, int S_eff, const double* __restrict__ obj,
+                                double* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= S) return;
+  double s = 0.0;
+  if (warp < S_eff) {
+    int64_t p0 = ((int64_t)warp - off) % S;
+    if (p0 < 0) p0 += S;
+    for (int64_t p = p0 + (int64_t)lane * S; p < count; p += (int64_t)32 * S) {
+      const unsigned char* rec = recs + p * rec_bytes;
+      const int64_t idx = f64 ? reinterpret_cast<const int64_t*>(rec)[2] : (int64_t) reinterpret_cast<const int*>(rec)[4];
+      s = fma(reinterpret_cast<const double*>(rec)[1], obj[idx], s);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) out[warp] = s;
+}
+
+int cell_objective(basq_ctx* ctx, const RecPool& pool, int64_t off_glob, int S, int S_eff, const double* obj,
+                   double* out) {
+  const int threads = 256;
+  const int blocks = ceil_div((int64_t)S * 32, threads);
+  cell_obj_kernel<<<blocks, threads, 0, ctx->stream>>>(pool.buf[pool.cur].as<unsigned char>(), pool.rec_bytes,
+                                                       pool.dtype == BASQ_F64 ? 1 : 0, pool.count, off_glob, S, S_eff,
+                                                       obj, out);
+  ctx->launches++;
+  BASQ_CUDA(cudaGetLastError());
+  return BASQ_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // apply a round: mu *= omega[set] (and wf when it carries the measure), drop omega == 0, compact.
 // Kept-point destination is analytic: D(g) = (g / S) * K + rank_excl[g % S]  (g = global position),

@@ -115,8 +115,9 @@ def tgemm(A, B):
     return Cm
 
 
-def recombine(kernel, pts_rec, pts_nys, U, mu=None, device=None):
-    """Tchernychova-Lyons recombination with a given basis U [q, M]: (idx int64, w fp64) on device."""
+def recombine(kernel, pts_rec, pts_nys, U, mu=None, device=None, obj=None):
+    """Tchernychova-Lyons recombination with a given basis U [q, M]: (idx int64, w fp64) on device.
+    obj [N]: the reference's ``-calc_obj(samp)`` for the objective-aware variant (SOBER/_rchq.py:67-69)."""
     spec, ctx, device, dtype = _common(kernel, pts_rec, device)
     Xd, Zd = _prep(pts_rec, device, dtype), _prep(pts_nys, device, dtype)
     Ud = _prep(U, device, torch.float64)
@@ -132,6 +133,15 @@ def recombine(kernel, pts_rec, pts_nys, U, mu=None, device=None):
     idx = torch.empty(q + 1, dtype=torch.int64, device=device)
     w = torch.empty(q + 1, dtype=torch.float64, device=device)
     n_out = C.c_int(0)
+    if obj is not None:
+        objd = _prep(obj, device, torch.float64)
+        if objd.shape != (len(Xd),):
+            raise ValueError("obj must have one entry per candidate")
+        _lib.check(_lib.lib.basq_recombine_objective(ctx.handle, C.byref(desc), Xd.data_ptr(), len(Xd), Zd.data_ptr(),
+                                                     len(Zd), Ud.data_ptr(), q,
+                                                     mud.data_ptr() if mud is not None else None, objd.data_ptr(),
+                                                     idx.data_ptr(), w.data_ptr(), C.byref(n_out)))
+        return idx[: n_out.value], w[: n_out.value]
     _lib.check(_lib.lib.basq_recombine(ctx.handle, C.byref(desc), Xd.data_ptr(), len(Xd), Zd.data_ptr(), len(Zd),
                                        Ud.data_ptr(), q, mud.data_ptr() if mud is not None else None,
                                        idx.data_ptr(), w.data_ptr(), C.byref(n_out)))
@@ -168,7 +178,7 @@ def recombine_host(kernel, X_host, Z_host, q, U_host=None, omega_host=None, mu_h
 class Session:
     """Staged recombination over a rank-local shard (basq_session_* in the C ABI)."""
 
-    def __init__(self, kernel, X_loc, Z, U, N_glob, idx_base, mu_loc=None, device=None):
+    def __init__(self, kernel, X_loc, Z, U, N_glob, idx_base, mu_loc=None, device=None, obj_loc=None):
         spec, ctx, device, dtype = _common(kernel, X_loc, device)
         self.ctx, self.device = ctx, device
         Xd, Zd = _prep(X_loc, device, dtype), _prep(Z, device, dtype)
@@ -185,6 +195,14 @@ class Session:
                                                 Ud.data_ptr(), self.q,
                                                 mud.data_ptr() if mud is not None else None, C.byref(h)))
         self.handle = h
+        self.rows = self.n
+        if obj_loc is not None:
+            objd = _prep(obj_loc, device, torch.float64)
+            assert objd.shape == (len(Xd),)
+            self._keep.append(objd)
+            _lib.check(_lib.lib.basq_session_set_objective(h, objd.data_ptr()))
+            self.rows = self.n + 1
+        self.has_obj = obj_loc is not None
 
     def close(self):
         h, self.handle = getattr(self, "handle", None), None
@@ -215,7 +233,7 @@ class Session:
 
     def level(self, lvl, node, ppos, fpar, A: torch.Tensor):
         """Local part of level `lvl` of the current pass into A [n, S] (see basq_session_level)."""
-        assert A.dtype == torch.float64 and A.is_contiguous() and A.shape == (self.n, self.S)
+        assert A.dtype == torch.float64 and A.is_contiguous() and A.shape == (self.rows, self.S)
         K = len(node)
         nd = np.ascontiguousarray(node, dtype=np.int32)
         pp = np.ascontiguousarray(ppos if lvl > 0 else np.zeros(K), dtype=np.int32)
@@ -224,7 +242,11 @@ class Session:
                                                fp.ctypes.data, A.data_ptr()))
 
     def car(self, A: torch.Tensor, C_cols: int, omega: torch.Tensor):
-        _lib.check(_lib.lib.basq_car(self.ctx.handle, A.data_ptr(), self.n, int(C_cols), self.S, omega.data_ptr(), None))
+        if self.has_obj:
+            _lib.check(_lib.lib.basq_car_objective(self.ctx.handle, A.data_ptr(), self.n, int(C_cols), self.S,
+                                                   omega.data_ptr()))
+        else:
+            _lib.check(_lib.lib.basq_car(self.ctx.handle, A.data_ptr(), self.n, int(C_cols), self.S, omega.data_ptr(), None))
 
     def apply(self, R_glob, off_glob, F, factor: torch.Tensor) -> int:
         c = C.c_int64(0)

@@ -83,7 +83,7 @@ def recombine_sharded(engine, n, S, group=None, device=None, max_rounds=256):
     if world > 1:
         dist.all_reduce(counts, group=group)
     counts = counts.cpu().tolist()
-    A = torch.zeros(n, S, dtype=torch.float64, device=device)
+    A = torch.zeros(getattr(engine, "rows", n), S, dtype=torch.float64, device=device)   # n + 1 rows with an objective
     omega = torch.zeros(S, dtype=torch.float64, device=device)
     rounds = 0
     while sum(counts) > n:
@@ -155,13 +155,14 @@ def gather_result(idx, w, n, group=None):
 
 
 def recombination_sharded(pts_rec_local, pts_nys, num_pts, kernel, N_glob, idx_base, U, init_weights_local=None,
-                          group=None):
+                          group=None, obj_local=None):
     """Sharded counterpart of recombination(): this rank holds pts_rec_local = rows
     [idx_base, idx_base + len) of the global candidate set; pts_nys, U and the GP caches are
     replicated.  Returns the full (idx, w) on every rank."""
     from . import ops
 
-    sess = ops.Session(kernel, pts_rec_local, pts_nys, U, N_glob, idx_base, mu_loc=init_weights_local)
+    sess = ops.Session(kernel, pts_rec_local, pts_nys, U, N_glob, idx_base, mu_loc=init_weights_local,
+                       obj_loc=obj_local)
     try:
         idx, w = recombine_sharded(sess, sess.n, sess.S, group=group, device=sess.device)
         return gather_result(idx, w, sess.n, group=group)

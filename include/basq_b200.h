@@ -123,6 +123,16 @@ int basq_car(basq_ctx* ctx, double* A, int n, int S, int lda, double* omega_out,
 int basq_recombine(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t N,
                    const void* Z, int64_t M, const double* U, int q, const double* mu,
                    int64_t* idx_out, double* w_out, int* n_out_host);
+/* Objective-aware recombination, SOBER/_rchq.py:67-69,138-146,177-196 (calc_obj): obj[N] (fp64) holds
+   the reference's `obj = -calc_obj(samp)` per candidate.  Every Caratheodory level carries the
+   objective as an extra row, keeps n + 1 columns, and then drops one more along the null direction of
+   the moment rows that does not increase sum_i w_i obj_i: the rule preserves the same q + 1 moments
+   with <= q + 1 points and an expected calc_obj at least that of the input measure. */
+int basq_recombine_objective(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t N,
+                             const void* Z, int64_t M, const double* U, int q, const double* mu,
+                             const double* obj, int64_t* idx_out, double* w_out, int* n_out_host);
+/* One such level on A[n + 1, C] (ld = lda; row n = objective sums), omega_out[C]; A is destroyed. */
+int basq_car_objective(basq_ctx* ctx, double* A, int n, int C, int lda, double* omega_out);
 /* Same with HOST buffers for X, Z, U, mu and the outputs (the copies are part of the call);
    desc->Xobs / W / alpha stay device pointers (they belong to the GP model, not to the call).
    If U_host is NULL the basis is built on the device from Omega_host[M,q] (basq_nystrom_basis). */
@@ -138,6 +148,10 @@ int basq_session_create(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
                         int64_t N_glob, int64_t idx_base, const void* Z, int64_t M,
                         const double* U, int q, const double* mu, basq_session** out);
 void basq_session_destroy(basq_session* s);
+/* Objective-aware mode for a staged session: obj[N_loc] (device, fp64, -calc_obj per local row, kept
+   by the caller) or NULL to switch it off.  Level systems then have n + 1 rows (basq_session_level
+   writes [n + 1, S]) and are reduced with basq_car_objective.  Call before the first pass. */
+int basq_session_set_objective(basq_session* s, const double* obj);
 /* live local points (after dropping zero weights / after the last apply) */
 int basq_session_count(const basq_session* s, int64_t* R_loc_host);
 /* Local part of the round's barycentre system: A[n = q+1, S = 2n] (ld = S), columns >= min(S,R_glob)

@@ -100,6 +100,86 @@ def tchernychova_lyons(samp, U, pt_nys, kernel, mu=None, chunk=1):
         alive = torch.cat([survivors, tail]) if (len(tail) and last_kept) else survivors
 
 
+def objective_step(bary, obj_bary, w, keep):
+    """The extra null-space step of the objective-aware variant (``SOBER/_rchq.py:177-196`` and
+    :86-104): among the kept points, move along the null vector of [bary | 1]^T in the direction
+    with obj . w_null >= 0 until one more weight vanishes.  Returns (w, keep) with one point less
+    (unchanged when the kept system has no null space, i.e. <= q + 1 points)."""
+    Xp = torch.cat([bary[keep].T, torch.ones(1, len(keep), dtype=bary.dtype)], 0)      # :178-180
+    if Xp.shape[1] <= Xp.shape[0]:
+        return w, keep
+    _, _, Vh = torch.linalg.svd(Xp)                                                   # :181
+    w_null = Vh[-1]                                                                   # :182
+    if float(obj_bary[keep] @ w_null) < 0:                                            # :183-184
+        w_null = -w_null
+    pos = w_null > 0                                                                  # :187
+    if not bool(pos.any()):
+        return w, keep
+    alpha = torch.where(pos, w / w_null, torch.tensor(float("inf"), dtype=w.dtype))   # :188-189
+    k = int(torch.argmin(alpha))                                                      # :190-191
+    w = w - alpha[k] * w_null                                                         # :192
+    w[k] = 0.0                                                                        # :193
+    live = w > 0                                                                      # :195-196
+    return w[live], keep[live]
+
+
+def tchernychova_lyons_objective(samp, U, pt_nys, kernel, calc_obj, mu=None):
+    """``Mod_Tchernychova_Lyons`` with ``calc_obj`` (``SOBER/_rchq.py:48-219``), restated on the set
+    structure of :func:`tchernychova_lyons` (BASQ's tail handling: SOBER's own adds the tail sums
+    twice, :128-135 and :153-164, which breaks the moments - SURVEY 2b - and is not reproduced).
+    The objective obj = -calc_obj(samp) (:69) rides along as one more test function (:138-150);
+    after every Caratheodory step the kept sets lose one more member by :func:`objective_step`.
+    Returns (w_star, idx_star) with at most q + 1 points."""
+    N = len(samp)
+    q, M = U.shape
+    S = 2 * (q + 1)
+    dt = U.dtype
+    mu = torch.full((N,), 1.0 / N, dtype=dt) if mu is None else mu.to(dt).clone()
+    obj = -1.0 * calc_obj(samp).to(dt)
+    alive = torch.arange(N)[mu != 0]
+    while True:
+        R = len(alive)
+        if R <= q + 1:
+            idx = torch.nonzero(mu > 0).squeeze(1)
+            return mu[idx], idx
+        if R <= S:                                                                    # :76-111
+            feats = (U @ kernel(pt_nys, samp[alive])).T
+            ext = torch.cat([feats, obj[alive].unsqueeze(1)], 1)
+            w, keep = caratheodory(ext, mu[alive])
+            w, keep = objective_step(feats, obj[alive], w, keep)
+            alive = alive[keep]
+            mu = torch.zeros_like(mu)
+            mu[alive] = w
+            if len(alive) <= q + 1:
+                return mu[mu > 0], alive
+            continue
+        E = R // S
+        body = alive[: E * S].reshape(E, S)
+        tail = alive[E * S:]
+        ids = body.reshape(-1)
+        Kb = kernel(pt_nys, samp[ids]) * mu[ids].unsqueeze(0)
+        G = Kb.reshape(M, E, S).sum(1)
+        bary = (U @ G).T
+        objs = (obj[body] * mu[body]).sum(0)
+        mass = mu[body].sum(0)
+        if len(tail):
+            bary[-1] += (U @ kernel(pt_nys, samp[tail])) @ mu[tail]
+            objs[-1] += obj[tail] @ mu[tail]
+            mass[-1] += mu[tail].sum()
+        bary = bary / mass.unsqueeze(1)
+        objs = objs / mass
+        w, keep = caratheodory(torch.cat([bary, objs.unsqueeze(1)], 1), mass.clone())  # :171-175
+        w, keep = objective_step(bary, objs, w, keep)                                  # :177-196
+        scale = torch.zeros(S, dtype=dt)
+        scale[keep] = w / mass[keep]
+        mu[body.reshape(-1)] = (mu[body] * scale.unsqueeze(0)).reshape(-1)
+        last_kept = bool(scale[-1] > 0)
+        if len(tail):
+            mu[tail] = mu[tail] * scale[-1]
+        survivors = body[:, keep].reshape(-1)
+        alive = torch.cat([survivors, tail]) if (len(tail) and last_kept) else survivors
+
+
 def nystrom_basis(pt, s, kernel):
     """``ker_svd_sparsify`` (``BASQ/_rchq.py:28-31``): randomised rank-s SVD of K(pt, pt)
     (torch.svd_lowrank, niter=2, consumes the global torch RNG); returns (S, U [s, M])."""

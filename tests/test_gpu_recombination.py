@@ -105,8 +105,8 @@ def test_recombination_entry_points(bq):
     assert w2.dtype == torch.float64
     with pytest.raises(TypeError):
         basq_b200.recombination(X, Z, n, lambda a, b: a @ b.T, DEV)
-    with pytest.raises(NotImplementedError):
-        basq_b200.recombination(X, Z, n, cov.forward, DEV, torch.float64, None, lambda x: x.sum(1))
+    idx3, w3 = basq_b200.recombination(X, Z, n, cov.forward, DEV, torch.float64, None, lambda x: x.sum(1))  # calc_obj
+    _check_rule(idx3, w3, N, n)
 
 
 def test_own_basis_moments_config1(bq):
@@ -322,3 +322,42 @@ def test_size_independent_properties_large(bq):
     # idempotence: recombining the rule itself changes nothing (already <= n points)
     idx2, w2 = ops.recombine(cov.forward, X[idx], Z, U, mu=w)
     assert len(idx2) == len(idx) and torch.allclose(w2, w, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("N,n", [(20_011, 16), (300_000, 100), (37, 16)])
+def test_objective_aware_recombination(bq, dtype, N, n):
+    """SOBER's calc_obj variant (SOBER/_rchq.py:67-69,138-146,177-196) through the SOBER signature:
+    same q + 1 moments with <= q + 1 points, and an expected objective that is not below the
+    measure's - the properties of the oracle's restatement (test_oracle_golden.py); the selected
+    points differ (different Caratheodory vertices)."""
+    basq_b200, _, ops, _ = bq
+    g = torch.Generator().manual_seed(N + n)
+    d, M = 4, 256
+    X = (math.sqrt(2.0) * torch.randn(N, d, generator=g, dtype=torch.float64)).to(dtype)
+    Z = (math.sqrt(2.0) * torch.randn(M, d, generator=g, dtype=torch.float64)).to(dtype)
+    U = torch.linalg.qr(torch.randn(M, n - 1, generator=g, dtype=torch.float64)).Q.T.contiguous()
+    cov = _plain_model(0, 1.6)
+    calc_obj = lambda x: torch.exp(-0.5 * ((x.double() - 0.7) ** 2).sum(-1))
+    w_api, idx = basq_b200.Mod_Tchernychova_Lyons(X.to(DEV), U.to(DEV), Z.to(DEV), cov.forward, DEV, calc_obj=calc_obj)
+    idx2, w = ops.recombine(cov.forward, X.to(DEV), Z.to(DEV), U.to(DEV), obj=-calc_obj(X).to(DEV))
+    assert torch.equal(idx, idx2)
+    _check_rule(idx, w, N, n)
+    mu = torch.full((N,), 1.0 / N, dtype=torch.float64)
+    Phi = ops.features(cov.forward, X.to(DEV), Z.to(DEV), U.to(DEV)).cpu()
+    assert orchq.moment_residual(Phi, mu, idx.cpu(), w.cpu()) < 1e-8
+    gain = float(w.cpu() @ calc_obj(X[idx.cpu()])) - float(mu @ calc_obj(X))
+    assert gain >= -1e-10, gain
+    if N >= 20_000 and dtype == torch.float64:
+        # the oracle's restatement reaches a comparable objective on the same inputs
+        w_o, idx_o = orchq.tchernychova_lyons_objective(X.double(), U, Z.double(), cov.forward, calc_obj) if N < 50_000 else (None, None)
+        if w_o is not None:
+            assert orchq.moment_residual(orchq.features(X.double(), U, Z.double(), cov.forward), mu, idx_o, w_o) < 1e-10
+            assert float(w_o @ calc_obj(X[idx_o])) >= float(mu @ calc_obj(X)) - 1e-12
+    # sharded driver with the objective (world size 1)
+    from basq_b200 import sharded
+    idx3, w3 = sharded.recombination_sharded(X.to(DEV), Z.to(DEV), n, cov.forward, N, 0, U.to(DEV),
+                                             obj_local=-calc_obj(X).to(DEV))
+    _check_rule(idx3, w3, N, n)
+    assert orchq.moment_residual(Phi, mu, idx3.cpu(), w3.cpu()) < 1e-8
+    assert float(w3.cpu() @ calc_obj(X[idx3.cpu()])) - float(mu @ calc_obj(X)) >= -1e-10

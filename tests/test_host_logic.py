@@ -66,8 +66,8 @@ def test_descriptor_fields():
 def test_recombination_signatures(monkeypatch):
     seen = {}
 
-    def fake(samp, pt, s, kernel, device, mu=None, use_obj=True):
-        seen.update(dtype=samp.dtype, mu=mu, s=s)
+    def fake(samp, pt, s, kernel, device, mu=None, use_obj=True, calc_obj=None):
+        seen.update(dtype=samp.dtype, mu=mu, s=s, calc_obj=calc_obj)
         return torch.arange(2), torch.ones(2)
 
     monkeypatch.setattr(_rchq, "rc_kernel_svd", fake)
@@ -88,8 +88,11 @@ def test_recombination_signatures(monkeypatch):
     assert seen["mu"] is w0
     with pytest.raises(ValueError):
         _rchq.recombination(X, Z, 4, "k", "cpu", torch.float64, torch.rand(7))
-    with pytest.raises(NotImplementedError):
-        _rchq.recombination(X, Z, 4, "k", "cpu", torch.float64, None, lambda x: x)
+    f = lambda x: x[:, 0]
+    _rchq.recombination(X, Z, 4, "k", "cpu", torch.float64, None, f)           # SOBER's calc_obj is forwarded
+    assert seen["calc_obj"] is f
+    _rchq.recombination(X, Z, 4, "k", "cpu")
+    assert seen["calc_obj"] is None
 
 
 def test_shard_bounds_and_survivor_counts():

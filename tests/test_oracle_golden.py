@@ -82,3 +82,23 @@ def test_weighted_variant_preserves_moments():
     Phi = rchq.features(X, U, Z, kern)
     assert rchq.moment_residual(Phi, mu, idx, w) < 1e-11
     assert bool((mu[idx] > 0).all())
+
+
+def test_objective_variant_invariants():
+    """The oracle's restatement of SOBER's calc_obj path (SOBER/_rchq.py:67-69,138-146,177-196): the
+    q + 1 moments are preserved with <= q + 1 points, and the rule's expected objective is not
+    below the measure's (every step moves along obj . w_null >= 0).  SOBER/_rchq.py itself
+    double-counts the tail sums, so there is no reference output to compare with ("parity unpinned")."""
+    g = torch.Generator().manual_seed(9)
+    N, d, M, n = 1203, 3, 40, 8
+    X = math.sqrt(2.0) * torch.randn(N, d, generator=g, dtype=torch.float64)
+    Z = math.sqrt(2.0) * torch.randn(M, d, generator=g, dtype=torch.float64)
+    U = torch.linalg.qr(torch.randn(M, n - 1, generator=g, dtype=torch.float64)).Q.T.contiguous()
+    kern = _kernel(0, 1.3)
+    calc_obj = lambda x: torch.exp(-0.5 * ((x - 0.7) ** 2).sum(-1))
+    w, idx = rchq.tchernychova_lyons_objective(X, U, Z, kern, calc_obj)
+    assert len(idx) <= n and bool((w > 0).all()) and abs(float(w.sum()) - 1.0) < 1e-12
+    mu = torch.full((N,), 1.0 / N, dtype=torch.float64)
+    Phi = rchq.features(X, U, Z, kern)
+    assert rchq.moment_residual(Phi, mu, idx, w) < 1e-11
+    assert float(w @ calc_obj(X[idx])) >= float(mu @ calc_obj(X)) - 1e-12
