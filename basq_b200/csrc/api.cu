@@ -957,24 +957,67 @@ int basq_recombine_host(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
   BASQ_TRY(dU.alloc(ctx, sizeof(double) * (size_t)q * M));
   BASQ_TRY(didx.alloc(ctx, sizeof(int64_t) * (q + 1)));
   BASQ_TRY(dw.alloc(ctx, sizeof(double) * (q + 1)));
-  BASQ_CUDA(cudaMemcpyAsync(dX.p, X_host, esz * (size_t)N * desc->d, cudaMemcpyHostToDevice, ctx->stream));
-  BASQ_CUDA(cudaMemcpyAsync(dZ.p, Z_host, esz * (size_t)M * desc->d, cudaMemcpyHostToDevice, ctx->stream));
-  if (mu_host) {
-    BASQ_TRY(dmu.alloc(ctx, sizeof(double) * N));
-    BASQ_CUDA(cudaMemcpyAsync(dmu.p, mu_host, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+  // The candidates (the bulk of the bytes) travel on a side stream while the basis is built from the
+  // landmarks on the main stream: the Nystrom phase hides the host-to-device copy.
+  cudaStream_t side = nullptr;
+  cudaEvent_t x_ready = nullptr, buffers_ready = nullptr;
+  BASQ_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+  BASQ_CUDA(cudaEventCreateWithFlags(&x_ready, cudaEventDisableTiming));
+  BASQ_CUDA(cudaEventCreateWithFlags(&buffers_ready, cudaEventDisableTiming));
+  auto cleanup = [&]() {
+    cudaStreamSynchronize(side);
+    cudaEventDestroy(x_ready);
+    cudaEventDestroy(buffers_ready);
+    cudaStreamDestroy(side);
+  };
+  // Landmarks and the test matrix go first (the copy engine serves requests in order, and the basis
+  // cannot start without them); the candidates follow on the side stream.
+  int rc = BASQ_OK;
+  {
+    cudaError_t e2 = cudaMemcpyAsync(dZ.p, Z_host, esz * (size_t)M * desc->d, cudaMemcpyHostToDevice, ctx->stream);
+    if (e2 == cudaSuccess && U_host)
+      e2 = cudaMemcpyAsync(dU.p, U_host, sizeof(double) * (size_t)q * M, cudaMemcpyHostToDevice, ctx->stream);
+    if (e2 == cudaSuccess && !U_host) {
+      rc = dOm.alloc(ctx, sizeof(double) * (size_t)M * q);
+      if (rc == BASQ_OK)
+        e2 = cudaMemcpyAsync(dOm.p, Omega_host, sizeof(double) * (size_t)M * q, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    if (e2 != cudaSuccess) {
+      set_error("basq_recombine_host: landmark copy failed: %s", cudaGetErrorString(e2));
+      rc = BASQ_ERR_CUDA;
+    }
   }
-  if (U_host) {
-    BASQ_CUDA(cudaMemcpyAsync(dU.p, U_host, sizeof(double) * (size_t)q * M, cudaMemcpyHostToDevice, ctx->stream));
-  } else {
-    trace_point(ctx, "host: X/Z copied");
-    BASQ_TRY(dOm.alloc(ctx, sizeof(double) * (size_t)M * q));
-    BASQ_CUDA(cudaMemcpyAsync(dOm.p, Omega_host, sizeof(double) * (size_t)M * q, cudaMemcpyHostToDevice, ctx->stream));
-    BASQ_TRY(nystrom_basis(ctx, desc, dZ.p, M, q, dOm.as<double>(), niter, dU.as<double>(), nullptr));
+  if (rc == BASQ_OK && mu_host) rc = dmu.alloc(ctx, sizeof(double) * N);
+  if (rc != BASQ_OK) {
+    cleanup();
+    return rc;
+  }
+  BASQ_CUDA(cudaEventRecord(buffers_ready, ctx->stream));        // dX / dmu come from the stream-ordered pool
+  BASQ_CUDA(cudaStreamWaitEvent(side, buffers_ready, 0));
+  cudaError_t ce = cudaMemcpyAsync(dX.p, X_host, esz * (size_t)N * desc->d, cudaMemcpyHostToDevice, side);
+  if (ce == cudaSuccess && mu_host)
+    ce = cudaMemcpyAsync(dmu.p, mu_host, sizeof(double) * N, cudaMemcpyHostToDevice, side);
+  if (ce == cudaSuccess) ce = cudaEventRecord(x_ready, side);
+  if (ce != cudaSuccess) {
+    cleanup();
+    set_error("basq_recombine_host: candidate copy failed: %s", cudaGetErrorString(ce));
+    return BASQ_ERR_CUDA;
+  }
+  if (!U_host) {
+    trace_point(ctx, "host: Z / Omega copies issued");
+    rc = nystrom_basis(ctx, desc, dZ.p, M, q, dOm.as<double>(), niter, dU.as<double>(), nullptr);
+  }
+  if (rc == BASQ_OK && cudaStreamWaitEvent(ctx->stream, x_ready, 0) != cudaSuccess) rc = BASQ_ERR_CUDA;
+  if (rc != BASQ_OK) {
+    cleanup();
+    return rc;
   }
   trace_point(ctx, "host: inputs + basis on device");
   int n_out = 0;
-  BASQ_TRY(recombine_impl(ctx, desc, dX.p, N, dZ.p, M, dU.as<double>(), q, mu_host ? dmu.as<double>() : nullptr,
-                          didx.as<int64_t>(), dw.as<double>(), &n_out));
+  rc = recombine_impl(ctx, desc, dX.p, N, dZ.p, M, dU.as<double>(), q, mu_host ? dmu.as<double>() : nullptr,
+                      didx.as<int64_t>(), dw.as<double>(), &n_out);
+  cleanup();
+  if (rc != BASQ_OK) return rc;
   BASQ_CUDA(cudaMemcpyAsync(idx_out_host, didx.p, sizeof(int64_t) * n_out, cudaMemcpyDeviceToHost, ctx->stream));
   BASQ_CUDA(cudaMemcpyAsync(w_out_host, dw.p, sizeof(double) * n_out, cudaMemcpyDeviceToHost, ctx->stream));
   BASQ_CUDA(cudaStreamSynchronize(ctx->stream));

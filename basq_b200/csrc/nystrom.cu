@@ -318,26 +318,36 @@ __global__ void diag_spread_kernel(const double* __restrict__ T, int q, int64_t 
   if (threadIdx.x == 0) out[0] = hi[0] > 0.0 ? lo[0] / hi[0] : 0.0;
 }
 
-// out[0] = trace(G), out[1] = max |G - I| (how far the columns behind this Gram matrix are from orthonormal)
-__global__ void trace_kernel(const double* __restrict__ G, int q, int64_t ld, double* __restrict__ out, int want_dev) {
-  __shared__ double sh[256], shd[256];
-  double s = 0.0, dev = 0.0;
+// out[0] = trace(G)
+__global__ void trace_kernel(const double* __restrict__ G, int q, int64_t ld, double* __restrict__ out) {
+  __shared__ double sh[256];
+  double s = 0.0;
   for (int i = threadIdx.x; i < q; i += 256) s += G[(int64_t)i * ld + i];
-  for (int64_t e = threadIdx.x; want_dev && e < (int64_t)q * q; e += 256) {
-    const int r = (int)(e / q), c = (int)(e % q);
-    dev = fmax(dev, fabs(G[(int64_t)r * ld + c] - (r == c ? 1.0 : 0.0)));
-  }
   sh[threadIdx.x] = s;
-  shd[threadIdx.x] = dev;
   __syncthreads();
   for (int w = 128; w > 0; w >>= 1) {
-    if ((int)threadIdx.x < w) {
-      sh[threadIdx.x] += sh[threadIdx.x + w];
-      shd[threadIdx.x] = fmax(shd[threadIdx.x], shd[threadIdx.x + w]);
-    }
+    if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
     __syncthreads();
   }
-  if (threadIdx.x == 0) { out[0] = sh[0]; out[1] = shd[0]; }
+  if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+// out[1] = max |G - I| (how far the columns behind this Gram matrix are from orthonormal); one row per
+// block, combined with an integer atomic max on the bit pattern (non-negative doubles order like
+// unsigned integers, so the result does not depend on the order of arrival).  out[1] must be zeroed.
+__global__ void gram_dev_kernel(const double* __restrict__ G, int q, int64_t ld, double* __restrict__ out) {
+  __shared__ double sh[256];
+  const int r = blockIdx.x;
+  double dev = 0.0;
+  for (int c = threadIdx.x; c < q; c += 256) dev = fmax(dev, fabs(G[(int64_t)r * ld + c] - (r == c ? 1.0 : 0.0)));
+  sh[threadIdx.x] = dev;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + w]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    atomicMax(reinterpret_cast<unsigned long long*>(out + 1), (unsigned long long)__double_as_longlong(sh[0]));
 }
 
 // out [cols, rows] = in [rows, cols]^T (both row-major), 32 x 32 tiles through shared memory
@@ -416,9 +426,13 @@ int orthonormalise(basq_ctx* ctx, OrthWs& ws, double* Y, int64_t M, int q, int p
   if (adaptive) passes = 4;
   for (int pass = 0; pass < passes; ++pass) {
     BASQ_TRY(dgemm(ctx, true, false, q, q, (int)M, 1.0, Y, q, Y, q, 0.0, ws.gram.as<double>(), q));
-    trace_kernel<<<1, 256, 0, ctx->stream>>>(ws.gram.as<double>(), q, q, ws.scal.as<double>(),
-                                             adaptive && pass > 0 ? 1 : 0);
+    BASQ_CUDA(cudaMemsetAsync(ws.scal.p, 0, 2 * sizeof(double), ctx->stream));
+    trace_kernel<<<1, 256, 0, ctx->stream>>>(ws.gram.as<double>(), q, q, ws.scal.as<double>());
     ctx->launches++;
+    if (adaptive && pass > 0) {
+      gram_dev_kernel<<<q, 256, 0, ctx->stream>>>(ws.gram.as<double>(), q, q, ws.scal.as<double>());
+      ctx->launches++;
+    }
     double trdev[2] = {0.0, 0.0};
     BASQ_CUDA(cudaMemcpyAsync(trdev, ws.scal.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
