@@ -136,7 +136,9 @@ def run_reference(a, rank):
     if rank != 0:
         return
     cores = torch.get_num_threads()
-    n_sample = max(a.cpu_sample, 4 * a.n, a.M)
+    # bounded sample: about 40 s of CPU work per step at the default 1e5 candidates; shrink it when more
+    # than three timed steps are requested so that the whole run stays within a few minutes
+    n_sample = max(int(a.cpu_sample * min(1.0, 3.0 / max(a.steps, 1))), 4 * a.n, a.M)
     for _ in range(min(a.warmup, 1)):
         oracle_step(a, max(4 * a.n, a.M, n_sample // 8))
     times = [oracle_step(a, n_sample, seed=s) for s in range(max(1, a.steps))]
