@@ -164,6 +164,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// 16 lanes x 32 columns: thread T receives rows T/4 and T/4 + 8 of the 16 lanes at the address and, of
+// every group of 8 columns k, columns 2 (T%4) and 2 (T%4) + 1 (v[4k+0..1] row T/4, v[4k+2..3] row T/4 + 8)
+__device__ __forceinline__ void tmem_ld16x256_x4(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -278,8 +289,14 @@ __global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(cons
 
   if (warp < Cfg::EPI_WARPS) {
     // ======================================================================== epilogue
+    // Accumulator fragments are read with the 16x256b shape: a thread then owns 4 landmarks (rows
+    // r0 + {0, 8, 16, 24}) and, with JT = 8 sets interleaved over the columns, exactly TWO sets
+    // (2 (lane % 4) and the next one) - so one 16-byte weight load serves 8 evaluations, and the
+    // thread still carries MT * 4 * 2 = MT * JT accumulators.
+    static_assert(JT == 8, "the fragment mapping below assumes 8 sets per work item");
     const int quarter = warp & 3, part = warp >> 2;
-    const int row = quarter * 32 + lane;
+    const int r0 = quarter * 32 + (lane >> 2);   // first of the thread's four rows (within the 128-row tile)
+    const int s0 = 2 * (lane & 3);               // first of the thread's two sets
     constexpr int NPART = Cfg::NPART;
     constexpr int PART_COLS = NT / NPART;
     static_assert(PART_COLS % 32 == 0, "column part must be a multiple of the tcgen05.ld width");
@@ -289,14 +306,14 @@ __global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(cons
       const int j0 = jg * JT;
       int64_t e_lo, n_tiles;
       item_range(j0, e_lo, n_tiles);
-      double acc[MT][JT];
+      double acc[MT][4][2];  // [landmark tile][row slot: r0 + 8 * slot][set s0 + {0, 1}]
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int jj = 0; jj < JT; ++jj) acc[mt][jj] = 0.0;
+        for (int rs = 0; rs < 4; ++rs) acc[mt][rs][0] = acc[mt][rs][1] = 0.0;
       for (int64_t t = 0; t < n_tiles; ++t, ++it) {
         const int stage = it % NSTAGE;
-        const double* wst = sW + stage * NT + part * PART_COLS;
+        const double* wst = sW + stage * NT + part * PART_COLS + s0;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt, ++tc) {
           const uint32_t buf = tc & 1u;
@@ -305,16 +322,24 @@ __global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(cons
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * NT + part * PART_COLS;
 #pragma unroll 1
           for (int cb = 0; cb < PART_COLS; cb += 32) {
-            uint32_t v[32];
-            mma::tmem_ld32(taddr + cb, v);
+            uint32_t va[16], vb[16];
+            mma::tmem_ld16x256_x4(taddr + cb, va);                         // lanes +0 .. +15
+            mma::tmem_ld16x256_x4(taddr + ((uint32_t)16 << 16) + cb, vb);  // lanes +16 .. +31
             mma::tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-              const double2 w2 = *reinterpret_cast<const double2*>(wst + cb + c);
-              const float k0 = finish_f32(FAM, __uint_as_float(v[c]), a.os_f);
-              const float k1 = finish_f32(FAM, __uint_as_float(v[c + 1]), a.os_f);
-              acc[mt][c % JT] = fma(f2d_pos(k0), w2.x, acc[mt][c % JT]);
-              acc[mt][(c + 1) % JT] = fma(f2d_pos(k1), w2.y, acc[mt][(c + 1) % JT]);
+            for (int k = 0; k < 4; ++k) {
+              const double2 w2 = *reinterpret_cast<const double2*>(wst + cb + 8 * k);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const float k00 = finish_f32(FAM, __uint_as_float(h ? vb[4 * k + 0] : va[4 * k + 0]), a.os_f);
+                const float k01 = finish_f32(FAM, __uint_as_float(h ? vb[4 * k + 1] : va[4 * k + 1]), a.os_f);
+                const float k10 = finish_f32(FAM, __uint_as_float(h ? vb[4 * k + 2] : va[4 * k + 2]), a.os_f);
+                const float k11 = finish_f32(FAM, __uint_as_float(h ? vb[4 * k + 3] : va[4 * k + 3]), a.os_f);
+                acc[mt][2 * h][0] = fma(f2d_pos(k00), w2.x, acc[mt][2 * h][0]);
+                acc[mt][2 * h][1] = fma(f2d_pos(k01), w2.y, acc[mt][2 * h][1]);
+                acc[mt][2 * h + 1][0] = fma(f2d_pos(k10), w2.x, acc[mt][2 * h + 1][0]);
+                acc[mt][2 * h + 1][1] = fma(f2d_pos(k11), w2.y, acc[mt][2 * h + 1][1]);
+              }
             }
           }
           mma::tc_fence_before();
@@ -326,15 +351,19 @@ __global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(cons
         if (lane == 0) mma::mbar_arrive(&b_empty[stage]);
       }
       // ---- combine the column parts in a fixed order (deterministic sums) and write G
+      // the thread's accumulator (mt, rs, c) belongs to tile row r0 + 8 rs and set s0 + c
       constexpr int SLOT = MT * 128 * JT;
       constexpr bool HANDOVER = (Cfg::NSLOT == NPART - 1);
+      auto slot_of = [&](int mt, int rs, int c) { return (mt * JT + s0 + c) * 128 + r0 + 8 * rs; };
       if (HANDOVER) {
         if (part > 0) {
           if (items_done > 0) mma::named_bar_sync(2, Cfg::EPI_WARPS * 32);  // part 0 is done with the previous sums
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-            for (int jj = 0; jj < JT; ++jj) sComb[(part - 1) * SLOT + (mt * JT + jj) * 128 + row] = acc[mt][jj];
+            for (int rs = 0; rs < 4; ++rs)
+#pragma unroll
+              for (int c = 0; c < 2; ++c) sComb[(part - 1) * SLOT + slot_of(mt, rs, c)] = acc[mt][rs][c];
           __threadfence_block();
           mma::named_bar_arrive(1, Cfg::EPI_WARPS * 32);
         } else {
@@ -347,36 +376,40 @@ __global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(cons
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-              for (int jj = 0; jj < JT; ++jj) {
-                double* c = &sComb[(mt * JT + jj) * 128 + row];
-                *c = (pp == NPART - 1) ? acc[mt][jj] : (*c + acc[mt][jj]);
-              }
+              for (int rs = 0; rs < 4; ++rs)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                  double* d = &sComb[slot_of(mt, rs, c)];
+                  *d = (pp == NPART - 1) ? acc[mt][rs][c] : (*d + acc[mt][rs][c]);
+                }
           }
           mma::named_bar_sync(1, Cfg::EPI_WARPS * 32);
         }
       }
       if (part == 0) {
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          const int m = (mg * MT + mt) * 128 + row;
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-          for (int jj = 0; jj < JT; ++jj) {
-            double c;
-            if (HANDOVER) {
-              c = sComb[(NPART - 2) * SLOT + (mt * JT + jj) * 128 + row];
+          for (int rs = 0; rs < 4; ++rs) {
+            const int m = (mg * MT + mt) * 128 + r0 + 8 * rs;
 #pragma unroll
-              for (int pp = NPART - 3; pp >= 0; --pp) c += sComb[pp * SLOT + (mt * JT + jj) * 128 + row];
-            } else {
-              c = sComb[(mt * JT + jj) * 128 + row];
-            }
-            const int j = j0 + jj;
-            if (m < a.Mtot && j < a.S) {
-              const double v = acc[mt][jj] + c;
-              double* dst = a.G + (int64_t)m * a.ldg + j;
-              *dst = a.accumulate ? (*dst + v) : v;
+            for (int c = 0; c < 2; ++c) {
+              double others;
+              if (HANDOVER) {
+                others = sComb[(NPART - 2) * SLOT + slot_of(mt, rs, c)];
+#pragma unroll
+                for (int pp = NPART - 3; pp >= 0; --pp) others += sComb[pp * SLOT + slot_of(mt, rs, c)];
+              } else {
+                others = sComb[slot_of(mt, rs, c)];
+              }
+              const int j = j0 + s0 + c;
+              if (m < a.Mtot && j < a.S) {
+                const double v = acc[mt][rs][c] + others;
+                double* dst = a.G + (int64_t)m * a.ldg + j;
+                *dst = a.accumulate ? (*dst + v) : v;
+              }
             }
           }
-        }
         if (HANDOVER) mma::named_bar_arrive(2, Cfg::EPI_WARPS * 32);
       }
       if (!HANDOVER) mma::named_bar_sync(1, Cfg::EPI_WARPS * 32);
