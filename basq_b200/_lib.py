@@ -72,6 +72,9 @@ def _load():
         "basq_session_cell_factor": (I, [P, L, L, C.POINTER(I)]),
         "basq_session_pass_begin": (I, [P, L, L, I]),
         "basq_session_level": (I, [P, I, I, P, P, P, P]),
+        "basq_session_landmarks": (I, [P, C.POINTER(I)]),
+        "basq_session_level_fold": (I, [P, I, I, P, P, L]),
+        "basq_session_level_project": (I, [P, I, I, P, P, P, P, L, I, I, P]),
         "basq_session_apply_cells": (I, [P, L, L, I, P, C.POINTER(L)]),
         "basq_sample_mvn": (I, [P, C.c_uint64, L, L, I, I, P, P, P]),
         "basq_mvn_logpdf": (I, [P, P, L, I, I, P, P, P]),

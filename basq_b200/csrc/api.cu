@@ -322,17 +322,47 @@ int session_pass_begin(basq_session* s, int64_t R_glob, int64_t off, int F) {
 //   lvl > 0: 2 K columns [low halves | high halves] of the K surviving nodes of the previous level;
 //            node[i] = id of the low half (cells node[i] + k (S << lvl)), ppos[i] = the parent's column
 //            in the previous level, fpar[i] = the parent's factor; high half = parent - low half.
-int session_level(basq_session* s, int lvl, int K, const int* node_host, const int* ppos_host,
-                  const double* fpar_host, double* A_out) {
-  basq_ctx* ctx = s->ctx;
-  const int n = s->n, S = s->S, F = s->pass_F, rows = s->rows;
+// The two halves of session_level, also exposed on their own so that ranks can exchange the folded
+// columns between them (sharded.py: reduce-scatter by landmark rows, every rank then projects 1/G of
+// the rows instead of all of them).
+//   fold:    Gf_out[m, i] = sum_k G[m, node[i] + k (S << lvl)]   for m < Mtot, i < K   (ld = ld_gf)
+//   project: rows 1..q of the level's raw columns = U'[:, row0 .. row0 + nrows) Gf_rows[nrows, K];
+//            masses / objective rows from this rank's cells; high halves by linearity; A_out scaled.
+int session_level_check(basq_session* s, int lvl, int K, const int* node_host, const int* ppos_host) {
+  const int S = s->S, F = s->pass_F;
   BASQ_CHECK(F >= 1 && lvl >= 0 && (1 << lvl) <= F, BASQ_ERR_INVALID, "level %d outside the pass (F = %d)", lvl, F);
   const int C = lvl == 0 ? K : 2 * K;
   BASQ_CHECK(K >= 1 && C <= S, BASQ_ERR_INVALID, "level %d: %d columns exceed S = %d", lvl, C, S);
-  const int stride = S << lvl, cnt = F >> lvl;
+  const int stride = S << lvl;
   for (int i = 0; i < K; ++i)
-    BASQ_CHECK(node_host[i] >= 0 && node_host[i] < stride && (lvl == 0 || (ppos_host[i] >= 0 && ppos_host[i] < S)),
+    BASQ_CHECK(node_host[i] >= 0 && node_host[i] < stride &&
+                   (lvl == 0 || !ppos_host || (ppos_host[i] >= 0 && ppos_host[i] < S)),
                BASQ_ERR_INVALID, "level %d: bad node %d", lvl, i);
+  return BASQ_OK;
+}
+
+int session_level_fold(basq_session* s, int lvl, int K, const int* node_host, double* Gf_out, int64_t ld_gf) {
+  basq_ctx* ctx = s->ctx;
+  BASQ_TRY(session_level_check(s, lvl, K, node_host, nullptr));
+  PhaseTimer t(ctx, PH_PROJ);
+  const int stride = s->S << lvl, cnt = s->pass_F >> lvl;
+  BASQ_CUDA(cudaMemcpyAsync(s->lnode.p, node_host, sizeof(int) * K, cudaMemcpyHostToDevice, ctx->stream));
+  fold_cols_kernel<<<(unsigned)ceil_div64((int64_t)s->Mtot * K, 256), 256, 0, ctx->stream>>>(
+      s->G.as<double>(), s->ldg, s->Mtot, K, s->lnode.as<int>(), stride, cnt, Gf_out, ld_gf);
+  ctx->launches++;
+  BASQ_CUDA(cudaGetLastError());
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));  // node_host may be reused
+  return BASQ_OK;
+}
+
+int session_level_project(basq_session* s, int lvl, int K, const int* node_host, const int* ppos_host,
+                          const double* fpar_host, const double* Gf_rows, int64_t ld_gf, int row0, int nrows,
+                          double* A_out) {
+  basq_ctx* ctx = s->ctx;
+  const int n = s->n, S = s->S, F = s->pass_F, rows = s->rows;
+  BASQ_TRY(session_level_check(s, lvl, K, node_host, ppos_host));
+  BASQ_CHECK(row0 >= 0 && nrows >= 0 && row0 + nrows <= s->Mtot, BASQ_ERR_INVALID, "level: bad landmark row range");
+  const int stride = S << lvl, cnt = F >> lvl;
   PhaseTimer t(ctx, PH_PROJ);
   BASQ_CUDA(cudaMemcpyAsync(s->lnode.p, node_host, sizeof(int) * K, cudaMemcpyHostToDevice, ctx->stream));
   if (lvl > 0) BASQ_CUDA(cudaMemcpyAsync(s->lppos.p, ppos_host, sizeof(int) * K, cudaMemcpyHostToDevice, ctx->stream));
@@ -340,17 +370,6 @@ int session_level(basq_session* s, int lvl, int K, const int* node_host, const i
   BASQ_CUDA(cudaMemsetAsync(A_out, 0, sizeof(double) * (size_t)rows * S, ctx->stream));
   double* raw = s->raw[s->raw_cur].as<double>();
   const double* prev = s->raw[s->raw_cur ^ 1].as<double>();
-  const double* Gsrc = s->G.as<double>();
-  int64_t ldsrc = s->ldg;
-  bool identity = (cnt == 1 && lvl == 0);  // plain round: the sets ARE the cells, project G as it is
-  for (int i = 0; identity && i < K; ++i) identity = node_host[i] == i;
-  if (!identity) {
-    fold_cols_kernel<<<(unsigned)ceil_div64((int64_t)s->Mtot * K, 256), 256, 0, ctx->stream>>>(
-        s->G.as<double>(), s->ldg, s->Mtot, K, s->lnode.as<int>(), stride, cnt, s->Gf.as<double>(), S);
-    ctx->launches++;
-    Gsrc = s->Gf.as<double>();
-    ldsrc = S;
-  }
   fold_cols_kernel<<<(unsigned)ceil_div64(K, 256), 256, 0, ctx->stream>>>(s->cellmass.as<double>(), 0, 1, K,
                                                                           s->lnode.as<int>(), stride, cnt, raw, S);
   ctx->launches++;
@@ -361,7 +380,12 @@ int session_level(basq_session* s, int lvl, int K, const int* node_host, const i
                                                                             raw + (int64_t)n * S, S);
     ctx->launches++;
   }
-  BASQ_TRY(dgemm(ctx, false, false, s->q, K, s->Mtot, 1.0, s->Uprime.as<double>(), s->Mtot, Gsrc, ldsrc, 0.0, raw + S, S));
+  if (nrows > 0) {
+    BASQ_TRY(dgemm(ctx, false, false, s->q, K, nrows, 1.0, s->Uprime.as<double>() + row0, s->Mtot, Gf_rows, ld_gf, 0.0,
+                   raw + S, S));
+  } else {
+    BASQ_CUDA(cudaMemset2DAsync(raw + S, sizeof(double) * S, 0, sizeof(double) * K, s->q, ctx->stream));
+  }
   level_finish_kernel<<<(unsigned)ceil_div64((int64_t)rows * K, 256), 256, 0, ctx->stream>>>(
       raw, prev, rows, K, lvl > 0 ? 1 : 0, s->lppos.as<int>(), s->lfpar.as<double>(), A_out, S);
   ctx->launches++;
@@ -370,6 +394,17 @@ int session_level(basq_session* s, int lvl, int K, const int* node_host, const i
   BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
   s->raw_cur ^= 1;
   return BASQ_OK;
+}
+
+int session_level(basq_session* s, int lvl, int K, const int* node_host, const int* ppos_host,
+                  const double* fpar_host, double* A_out) {
+  const int cnt = s->pass_F >> lvl;
+  bool identity = (cnt == 1 && lvl == 0);  // plain round: the sets ARE the cells, project G as it is
+  for (int i = 0; identity && i < K; ++i) identity = node_host[i] == i;
+  if (identity)
+    return session_level_project(s, lvl, K, node_host, ppos_host, fpar_host, s->G.as<double>(), s->ldg, 0, s->Mtot, A_out);
+  BASQ_TRY(session_level_fold(s, lvl, K, node_host, s->Gf.as<double>(), s->S));
+  return session_level_project(s, lvl, K, node_host, ppos_host, fpar_host, s->Gf.as<double>(), s->S, 0, s->Mtot, A_out);
 }
 
 // Host bookkeeping of a pass's level tree, shared by the single-call loop (recombine_impl) and
@@ -1066,6 +1101,27 @@ int basq_session_pass_begin(basq_session* s, int64_t R_glob, int64_t off_glob, i
   BASQ_CHECK(s, BASQ_ERR_INVALID, "NULL argument");
   BASQ_CUDA(cudaSetDevice(s->ctx->device));
   return session_pass_begin(s, R_glob, off_glob, F);
+}
+
+int basq_session_landmarks(const basq_session* s, int* Mtot_out_host) {
+  BASQ_CHECK(s && Mtot_out_host, BASQ_ERR_INVALID, "NULL argument");
+  *Mtot_out_host = s->Mtot;
+  return BASQ_OK;
+}
+
+int basq_session_level_fold(basq_session* s, int lvl, int K, const int* node_host, double* Gf_out, int64_t ld_gf) {
+  BASQ_CHECK(s && node_host && Gf_out && ld_gf >= K, BASQ_ERR_INVALID, "basq_session_level_fold: bad argument");
+  BASQ_CUDA(cudaSetDevice(s->ctx->device));
+  return session_level_fold(s, lvl, K, node_host, Gf_out, ld_gf);
+}
+
+int basq_session_level_project(basq_session* s, int lvl, int K, const int* node_host, const int* ppos_host,
+                               const double* fpar_host, const double* Gf_rows, int64_t ld_gf, int row0, int nrows,
+                               double* A_out) {
+  BASQ_CHECK(s && node_host && fpar_host && A_out && (lvl == 0 || ppos_host) && (Gf_rows || nrows == 0) && ld_gf >= K,
+             BASQ_ERR_INVALID, "basq_session_level_project: bad argument");
+  BASQ_CUDA(cudaSetDevice(s->ctx->device));
+  return session_level_project(s, lvl, K, node_host, ppos_host, fpar_host, Gf_rows, ld_gf, row0, nrows, A_out);
 }
 
 int basq_session_level(basq_session* s, int lvl, int K, const int* node_host, const int* ppos_host,

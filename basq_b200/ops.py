@@ -241,6 +241,38 @@ class Session:
         _lib.check(_lib.lib.basq_session_level(self.handle, int(lvl), K, nd.ctypes.data, pp.ctypes.data,
                                                fp.ctypes.data, A.data_ptr()))
 
+    # --- the same level in two halves, with a reduce-scatter of the folded columns in between ---------
+    def landmarks(self) -> int:
+        m = C.c_int(0)
+        _lib.check(_lib.lib.basq_session_landmarks(self.handle, C.byref(m)))
+        return int(m.value)
+
+    def shared_buffers(self, world):
+        """(Gf flat buffer for [Mtot_pad, K] views, block buffer for [Mtot_pad / world, K]); rows padded
+        to a multiple of `world` (padding rows never enter a projection)."""
+        if getattr(self, "_shared", None) is None or self._shared[0] != world:
+            Mtot = self.landmarks()
+            rows_blk = -(-Mtot // world)
+            Gf = torch.zeros(rows_blk * world * self.S, dtype=torch.float64, device=self.device)
+            blk = torch.zeros(rows_blk * self.S, dtype=torch.float64, device=self.device)
+            self._shared = (world, Mtot, rows_blk, Gf, blk)
+        return self._shared[1:]
+
+    def level_fold(self, lvl, node, Gf: torch.Tensor):
+        K = len(node)
+        nd = np.ascontiguousarray(node, dtype=np.int32)
+        _lib.check(_lib.lib.basq_session_level_fold(self.handle, int(lvl), K, nd.ctypes.data, Gf.data_ptr(), K))
+
+    def level_project(self, lvl, node, ppos, fpar, Gf_rows: torch.Tensor, row0, nrows, A: torch.Tensor):
+        assert A.dtype == torch.float64 and A.is_contiguous() and A.shape == (self.rows, self.S)
+        K = len(node)
+        nd = np.ascontiguousarray(node, dtype=np.int32)
+        pp = np.ascontiguousarray(ppos if lvl > 0 else np.zeros(K), dtype=np.int32)
+        fp = np.ascontiguousarray(fpar, dtype=np.float64)
+        _lib.check(_lib.lib.basq_session_level_project(self.handle, int(lvl), K, nd.ctypes.data, pp.ctypes.data,
+                                                       fp.ctypes.data, Gf_rows.data_ptr(), K, int(row0), int(nrows),
+                                                       A.data_ptr()))
+
     def car(self, A: torch.Tensor, C_cols: int, omega: torch.Tensor):
         if self.has_obj:
             _lib.check(_lib.lib.basq_car_objective(self.ctx.handle, A.data_ptr(), self.n, int(C_cols), self.S,

@@ -5,12 +5,16 @@ Per Tchernychova-Lyons pass every rank forms the barycentre numerators of ITS po
 Caratheodory levels one all-reduce sums the small [n, S] system over NVLink, every rank runs the
 same deterministic Caratheodory kernel on the identical reduced system, and at the end of the pass
 rescales / compacts its own shard.  Counts and offsets after a round follow analytically from the kept sets,
-so the only collective on the data path is that all-reduce.
+so the collectives on the data path are that all-reduce and, under NCCL, a
+reduce-scatter of the level's folded set-sum columns by landmark rows in front of it, which lets
+every rank project 1/G of the rows instead of repeating the whole fp64 projection.
 
 The loop is written against a tiny engine interface so the host logic can be exercised on CPU with
 gloo and an oracle-backed engine (tests/test_sharded_gloo.py); the product engine is ops.Session.
 """
 from __future__ import annotations
+
+import os
 
 import numpy as np
 import torch
@@ -83,6 +87,10 @@ def recombine_sharded(engine, n, S, group=None, device=None, max_rounds=256):
     if world > 1:
         dist.all_reduce(counts, group=group)
     counts = counts.cpu().tolist()
+    # With NCCL the ranks also share the projection (level_fold -> reduce-scatter -> level_project):
+    # BASQ_SHARE_PROJECTION=0 keeps every rank projecting its own cell sums.
+    share_projection = (world > 1 and hasattr(engine, "level_fold") and dist.get_backend(group) == "nccl"
+                        and os.environ.get("BASQ_SHARE_PROJECTION", "1") != "0")
     A = torch.zeros(getattr(engine, "rows", n), S, dtype=torch.float64, device=device)   # n + 1 rows with an objective
     omega = torch.zeros(S, dtype=torch.float64, device=device)
     rounds = 0
@@ -100,7 +108,19 @@ def recombine_sharded(engine, n, S, group=None, device=None, max_rounds=256):
         while True:
             C = tree.columns()
             if C > n or tree.lvl < tree.L:
-                engine.level(tree.lvl, tree.node, tree.ppos, tree.fpar, A)
+                if share_projection:
+                    # fold locally, reduce-scatter the folded columns by landmark rows, project 1/world
+                    # of the rows here; the all-reduce of A below completes the sum over row blocks
+                    K = len(tree.node)
+                    Mtot, rows_blk, Gf, blk = engine.shared_buffers(world)
+                    Gv, bv = Gf[: rows_blk * world * K].view(rows_blk * world, K), blk[: rows_blk * K].view(rows_blk, K)
+                    engine.level_fold(tree.lvl, tree.node, Gv)
+                    dist.reduce_scatter_tensor(bv, Gv, group=group)
+                    row0 = min(rank * rows_blk, Mtot)
+                    engine.level_project(tree.lvl, tree.node, tree.ppos, tree.fpar, bv, row0,
+                                         min(rows_blk, Mtot - row0), A)
+                else:
+                    engine.level(tree.lvl, tree.node, tree.ppos, tree.fpar, A)
             if C > n:
                 if world > 1:
                     dist.all_reduce(A, group=group)

@@ -182,6 +182,17 @@ int basq_session_pass_begin(basq_session* s, int64_t R_glob, int64_t off_glob, i
    accumulated factor.  Levels must be requested in order.  Sum A over ranks, then basq_car. */
 int basq_session_level(basq_session* s, int lvl, int K, const int* node_host, const int* ppos_host,
                        const double* fpar_host, double* A_out);
+/* basq_session_level in two halves, for ranks that share the projection: fold writes the level's
+   K set-sum columns of THIS rank's points, Gf_out[M_tot, K] (device, ld = ld_gf; M_tot = landmarks incl.
+   appended observations, basq_session_landmarks); after a reduce-scatter of Gf by landmark rows over
+   the ranks, project takes the summed rows [row0, row0 + nrows) (Gf_rows[nrows, K]) and writes this
+   rank's part of the level system: U'[:, rows] Gf_rows plus its local masses.  The all-reduce of A
+   that follows completes both sums; every rank has done 1/G of the projection flops. */
+int basq_session_landmarks(const basq_session* s, int* Mtot_out_host);
+int basq_session_level_fold(basq_session* s, int lvl, int K, const int* node_host, double* Gf_out, int64_t ld_gf);
+int basq_session_level_project(basq_session* s, int lvl, int K, const int* node_host, const int* ppos_host,
+                               const double* fpar_host, const double* Gf_rows, int64_t ld_gf, int row0,
+                               int nrows, double* A_out);
 /* Rescale the kept cells by factor_host[F*S] (HOST; product of the level factors along each cell's
    path, 0 = dropped), drop the rest, compact.  New local count out. */
 int basq_session_apply_cells(basq_session* s, int64_t R_glob, int64_t off_glob, int F,

@@ -361,3 +361,65 @@ def test_objective_aware_recombination(bq, dtype, N, n):
     _check_rule(idx3, w3, N, n)
     assert orchq.moment_residual(Phi, mu, idx3.cpu(), w3.cpu()) < 1e-8
     assert float(w3.cpu() @ calc_obj(X[idx3.cpu()])) - float(mu @ calc_obj(X)) >= -1e-10
+
+
+def test_shared_projection_two_shards_one_gpu(bq):
+    """The NCCL path of sharded.recombine_sharded with the collectives done by hand on one GPU: every
+    shard folds its level columns (basq_session_level_fold), the folded columns are summed and split by
+    landmark rows (the reduce-scatter), each shard projects its row block
+    (basq_session_level_project) and the partial systems are added (the all-reduce).  The level
+    systems must equal the unshared path's, and the rule must preserve the moments of the union."""
+    basq_b200, _, ops, sharded = bq
+    g = torch.Generator().manual_seed(78)
+    N, d, M, n = 12_007, 5, 96, 12
+    X = math.sqrt(2.0) * torch.randn(N, d, generator=g, dtype=torch.float64)
+    Z = math.sqrt(2.0) * torch.randn(M, d, generator=g, dtype=torch.float64)
+    U = torch.linalg.qr(torch.randn(M, n - 1, generator=g, dtype=torch.float64)).Q.T.contiguous()
+    model = ogp.make_gp(d, 30, lengthscale=1.8, outputscale=1.1, noise=1e-5, seed=3)
+    kern = ogp.VanillaGP(model).predictive_kernel          # M_tot = M + n_obs landmarks
+    cut = 5000
+    mk = lambda: (ops.Session(kern, X[:cut].to(DEV), Z.to(DEV), U.to(DEV), N, 0),
+                  ops.Session(kern, X[cut:].to(DEV), Z.to(DEV), U.to(DEV), N, cut))
+    (s0, s1), (r0, r1) = mk(), mk()                        # shared-projection pair, reference pair
+    S, Mtot = s0.S, s0.landmarks()
+    assert Mtot == M + 30
+    h = -(-Mtot // 2)
+    A0 = torch.zeros(n, S, dtype=torch.float64, device=DEV); A1 = torch.zeros_like(A0)
+    B0 = torch.zeros_like(A0); B1 = torch.zeros_like(A0)
+    omega = torch.zeros(S, dtype=torch.float64, device=DEV)
+    c0, c1 = s0.count(), s1.count()
+    while c0 + c1 > n:
+        R = c0 + c1
+        F = 4 if R >= 4 * 4 * S else 1
+        for s_, off in ((s0, 0), (s1, c0), (r0, 0), (r1, c0)):
+            s_.pass_begin(R, off, F)
+        factor = torch.zeros(F * S, dtype=torch.float64)
+        tree = sharded.LevelTree(S, F, R)
+        while True:
+            C, K = tree.columns(), len(tree.node)
+            G0 = torch.zeros(Mtot, K, dtype=torch.float64, device=DEV); G1 = torch.zeros_like(G0)
+            s0.level_fold(tree.lvl, tree.node, G0); s1.level_fold(tree.lvl, tree.node, G1)
+            Gs = G0 + G1
+            s0.level_project(tree.lvl, tree.node, tree.ppos, tree.fpar, Gs[:h].contiguous(), 0, h, A0)
+            s1.level_project(tree.lvl, tree.node, tree.ppos, tree.fpar, Gs[h:].contiguous(), h, Mtot - h, A1)
+            r0.level(tree.lvl, tree.node, tree.ppos, tree.fpar, B0); r1.level(tree.lvl, tree.node, tree.ppos, tree.fpar, B1)
+            A = (A0 + A1).contiguous()
+            assert float(torch.linalg.norm(A - (B0 + B1)) / torch.linalg.norm(B0 + B1)) < 1e-12
+            if C > n:
+                s0.car(A, C, omega)
+                om = omega[:C].cpu().numpy()
+            else:
+                om = np.ones(C)
+            more, kept = tree.advance(om, factor)
+            assert kept >= 1
+            if not more:
+                break
+        c0n, c1n = s0.apply(R, 0, F, factor), s1.apply(R, c0, F, factor)
+        assert (r0.apply(R, 0, F, factor), r1.apply(R, c0, F, factor)) == (c0n, c1n)
+        c0, c1 = c0n, c1n
+    i0, w0 = s0.result(); i1, w1 = s1.result()
+    idx, w = torch.cat([i0, i1]), torch.cat([w0, w1])
+    _check_rule(idx, w, N, n)
+    Phi = orchq.features(X, U, Z, kern)
+    mu = torch.full((N,), 1.0 / N, dtype=torch.float64)
+    assert orchq.moment_residual(Phi, mu, idx.cpu(), w.cpu()) < 1e-9
