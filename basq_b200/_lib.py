@@ -80,6 +80,7 @@ def _load():
         "basq_mvn_logpdf": (I, [P, P, L, I, I, P, P, P]),
         "basq_candidate_weights": (I, [P, I, D, I, P, P, L, I, P]),
         "basq_cleanse_weights": (I, [P, P, L, D]),
+        "basq_sir_resample": (I, [P, P, L, L, C.c_uint64, P, C.POINTER(L)]),
         "basq_dgemm": (I, [P, I, I, I, I, I, D, P, I, P, I, D, P, I]),
         "basq_tgemm": (I, [P, I, I, I, P, I, P, I, P, I]),
     }

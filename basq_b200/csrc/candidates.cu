@@ -8,6 +8,7 @@
 //   basq_candidate_weights UncertaintySampler.calc_weights (BASQ/_sampler.py:190-217),
 //                          PI_BQ.lfi (SOBER/_pi.py:121-139)
 //   basq_cleanse_weights   WeightsStabiliser.cleansing_weights (SOBER/_weights.py:21-38)
+//   basq_sir_resample      UncertaintySampler.SIR = torch.multinomial(weights, n) (BASQ/_sampler.py:104-118)
 //
 // Random numbers: Philox4x32-10 (Salmon et al., SC'11), counter = (sample index lo, hi, block of 4
 // dimensions, 0), key = 64-bit seed.  A sample depends only on (seed, global index), so shards drawn
@@ -16,6 +17,7 @@
 // Box-Muller, (x0, x1) -> (r cos 2 pi u1, r sin 2 pi u1), r = sqrt(-2 ln u0), likewise (x2, x3).
 #include <math.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -163,6 +165,33 @@ __global__ void scale_or_fill_kernel(double* __restrict__ w, int64_t N, const do
   w[i] = (t != 0.0 && isfinite(t)) ? w[i] / t : 1.0 / (double)N;
 }
 
+// Sequential importance resampling without replacement (torch.multinomial(weights, n), as
+// UncertaintySampler.SIR, BASQ/_sampler.py:104-118) as an exponential race (Efraimidis-Spirakis):
+// key_i = -log(u_i) / w_i with u_i uniform; the n smallest keys, in increasing order, are distributed
+// like n successive draws proportional to the remaining weights.  u_i = Philox(seed; i), top 24 bits.
+// This kernel appends every (key, index) with key < cut to out (unordered; the host sorts the few
+// survivors) and counts them.
+__global__ void sir_keys_kernel(const double* __restrict__ w, int64_t N, uint64_t seed, double cut, int64_t cap,
+                                double* __restrict__ key_out, int64_t* __restrict__ idx_out,
+                                unsigned long long* __restrict__ count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const double wi = w[i];
+  if (!(wi > 0.0)) return;
+  uint32_t r[4];
+  philox4x32_10((uint32_t)i, (uint32_t)((uint64_t)i >> 32), 0u, 0x53495200u /* "SIR" stream */, (uint32_t)seed,
+                (uint32_t)(seed >> 32), r);
+  const double u = ((double)(r[0] >> 8) + 0.5) * 5.9604644775390625e-08;
+  const double key = -log(u) / wi;
+  if (key < cut) {
+    const unsigned long long slot = atomicAdd(count, 1ull);
+    if ((int64_t)slot < cap) {
+      key_out[slot] = key;
+      idx_out[slot] = i;
+    }
+  }
+}
+
 int pack_mvn(int d, const double* mean_host, const double* chol_host, MvnDev* p, double* log_norm) {
   BASQ_CHECK(d >= 1 && d <= BASQ_MAX_DIM, BASQ_ERR_INVALID, "mvn: dimension %d out of range", d);
   BASQ_CHECK(mean_host && chol_host, BASQ_ERR_INVALID, "mvn: NULL parameter");
@@ -250,6 +279,58 @@ int basq_candidate_weights(basq_ctx* ctx, int kind, double ratio, int log_out, c
     BASQ_CUDA(cudaGetLastError());
     BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
   }
+  return BASQ_OK;
+}
+
+int basq_sir_resample(basq_ctx* ctx, const double* w, int64_t N, int64_t n_out, uint64_t seed, int64_t* idx_out_host,
+                      int64_t* n_drawn_host) {
+  BASQ_CHECK(ctx && w && idx_out_host && n_drawn_host, BASQ_ERR_INVALID, "basq_sir_resample: NULL argument");
+  BASQ_CHECK(N >= 1 && n_out >= 0, BASQ_ERR_INVALID, "basq_sir_resample: bad sizes");
+  BASQ_CUDA(cudaSetDevice(ctx->device));
+  *n_drawn_host = 0;
+  if (n_out == 0) return BASQ_OK;
+  DevBuf total, keys, idxs, count;
+  BASQ_TRY(total.alloc(ctx, sizeof(double)));
+  BASQ_TRY(sum_device(ctx, w, N, total.as<double>()));
+  double tot = 0.0;
+  BASQ_CUDA(cudaMemcpyAsync(&tot, total.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  BASQ_CHECK(isfinite(tot) && tot > 0.0, BASQ_ERR_NUMERIC, "basq_sir_resample: weights sum to %g", tot);
+  const int64_t want = std::min<int64_t>(n_out, N);
+  const int64_t cap = std::min<int64_t>(N, 4 * want + 4096);
+  BASQ_TRY(keys.alloc(ctx, sizeof(double) * cap));
+  BASQ_TRY(idxs.alloc(ctx, sizeof(int64_t) * cap));
+  BASQ_TRY(count.alloc(ctx, sizeof(unsigned long long)));
+  // #keys below t is about t * sum(w) while t * max(w) << 1: start 50 % above the target, double on a miss
+  double cut = 1.5 * (double)want / tot + 1e-300;
+  unsigned long long got = 0;
+  for (int attempt = 0; attempt < 80; ++attempt) {
+    BASQ_CUDA(cudaMemsetAsync(count.p, 0, sizeof(unsigned long long), ctx->stream));
+    sir_keys_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, ctx->stream>>>(w, N, seed, cut, cap, keys.as<double>(),
+                                                                           idxs.as<int64_t>(),
+                                                                           count.as<unsigned long long>());
+    ctx->launches++;
+    BASQ_CUDA(cudaGetLastError());
+    BASQ_CUDA(cudaMemcpyAsync(&got, count.p, sizeof(got), cudaMemcpyDeviceToHost, ctx->stream));
+    BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    if ((int64_t)got > cap) { cut *= 0.6; continue; }            // overshoot: more survivors than the buffer holds
+    if ((int64_t)got >= want || !isfinite(cut)) break;            // enough (or every positive weight is in)
+    cut = (cut > 1e300) ? INFINITY : cut * 2.0;
+  }
+  BASQ_CHECK((int64_t)got <= cap, BASQ_ERR_NUMERIC, "basq_sir_resample: could not bracket the %lld-th key", (long long)want);
+  std::vector<double> hk((size_t)got);
+  std::vector<int64_t> hi((size_t)got);
+  BASQ_CUDA(cudaMemcpyAsync(hk.data(), keys.p, sizeof(double) * got, cudaMemcpyDeviceToHost, ctx->stream));
+  BASQ_CUDA(cudaMemcpyAsync(hi.data(), idxs.p, sizeof(int64_t) * got, cudaMemcpyDeviceToHost, ctx->stream));
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<int64_t> order((size_t)got);
+  for (size_t t = 0; t < order.size(); ++t) order[t] = (int64_t)t;
+  std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+    return hk[a] < hk[b] || (hk[a] == hk[b] && hi[a] < hi[b]);
+  });
+  const int64_t take = std::min<int64_t>(want, (int64_t)got);   // fewer than n positive weights: all of them
+  for (int64_t t = 0; t < take; ++t) idx_out_host[t] = hi[order[t]];
+  *n_drawn_host = take;
   return BASQ_OK;
 }
 

@@ -7,6 +7,7 @@ Mirrors of the reference objects that produce ``pts_rec`` / ``pts_nys`` / ``init
 * ``lfi``                     - ``PI_BQ.lfi``, ``SOBER/_pi.py:121-139``
 * ``cleansing_weights``       - ``WeightsStabiliser.cleansing_weights``, ``SOBER/_weights.py:21-38``
 * ``mvn_logpdf``              - ``prior.log_prob`` / ``Gaussian.pdf``
+* ``SIR`` / ``sir_indices``   - ``UncertaintySampler.SIR``, ``BASQ/_sampler.py:104-118`` (torch.multinomial)
 
 Everything computes inside libbasq_b200.so (csrc/candidates.cu); torch only owns the buffers.
 Random numbers are Philox4x32-10 keyed by (seed, global row), so N candidates sharded over ranks are
@@ -97,6 +98,23 @@ def cleansing_weights(weights, eps=torch.finfo(torch.float32).eps):
     ctx = _lib.context_for(w.device)
     _lib.check(_lib.lib.basq_cleanse_weights(ctx.handle, w.data_ptr(), w.numel(), float(eps)))
     return w
+
+
+def sir_indices(weights, n_return, seed=0):
+    """Indices of `n_return` draws without replacement proportional to `weights`, in draw order
+    (torch.multinomial(weights, n_return) of UncertaintySampler.SIR, BASQ/_sampler.py:104-118)."""
+    w = weights.detach().to(torch.float64).contiguous()
+    ctx = _lib.context_for(w.device)
+    idx = torch.empty(int(n_return), dtype=torch.int64)
+    got = C.c_int64(0)
+    _lib.check(_lib.lib.basq_sir_resample(ctx.handle, w.data_ptr(), w.numel(), int(n_return),
+                                          C.c_uint64(int(seed) & (2 ** 64 - 1)), idx.data_ptr(), C.byref(got)))
+    return idx[: got.value].to(w.device)
+
+
+def SIR(X, weights, n_return, seed=0):
+    """UncertaintySampler.SIR (BASQ/_sampler.py:104-118): ``X[torch.multinomial(weights, n_return)]``."""
+    return X[sir_indices(weights, n_return, seed=seed)]
 
 
 class PriorSampler:

@@ -220,6 +220,14 @@ int basq_candidate_weights(basq_ctx* ctx, int kind, double ratio, int log_out, c
    WeightsStabiliser.cleansing_weights (SOBER/_weights.py:21-38). */
 int basq_cleanse_weights(basq_ctx* ctx, double* w, int64_t N, double eps);
 
+/* Resampling without replacement proportional to w[N] (device, fp64, need not be normalised):
+   UncertaintySampler.SIR = torch.multinomial(weights, n_return) (BASQ/_sampler.py:104-118), as an
+   exponential race: key_i = -log(u_i) / w_i, u_i = Philox(seed; i); the n_out smallest keys in
+   increasing order are n_out successive draws.  idx_out_host[n_out] (HOST) receives the indices in
+   draw order, n_drawn_host their number (= min(n_out, #positive weights)). */
+int basq_sir_resample(basq_ctx* ctx, const double* w, int64_t N, int64_t n_out, uint64_t seed,
+                      int64_t* idx_out_host, int64_t* n_drawn_host);
+
 /* ---- small dense helper exposed for tests ---------------------------------------------------- */
 /* C[m,n] = alpha * op(A) op(B) + beta * C, fp64 row-major; op = transpose when the flag is set. */
 int basq_dgemm(basq_ctx* ctx, int transA, int transB, int m, int n, int k, double alpha,

@@ -97,6 +97,31 @@ def lfi(mu_pred, var_pred, log=False):
     return np.log(v + np.finfo(np.float32).eps) if log else v
 
 
+def sir_indices(weights, n_return, seed=0):
+    """UncertaintySampler.SIR (BASQ/_sampler.py:104-118) draws torch.multinomial(weights, n) without
+    replacement; restated as the exponential race the library runs (include/basq_b200.h:
+    basq_sir_resample): key_i = -log(u_i) / w_i, u_i from Philox(seed; counter (i, 0, 0x53495200)),
+    n smallest keys in increasing order.  The draws are distributed like multinomial's (Efraimidis &
+    Spirakis 2006); the values depend on the generator, as in the reference."""
+    w = np.asarray(weights, dtype=np.float64)
+    N = len(w)
+    i = np.arange(N, dtype=np.uint64)
+    ctr = np.zeros((N, 4), dtype=np.uint32)
+    ctr[:, 0] = (i & MASK).astype(np.uint32)
+    ctr[:, 1] = (i >> np.uint64(32)).astype(np.uint32)
+    ctr[:, 3] = 0x53495200
+    key = np.empty((N, 2), dtype=np.uint32)
+    key[:, 0] = np.uint32(seed & 0xFFFFFFFF)
+    key[:, 1] = np.uint32((seed >> 32) & 0xFFFFFFFF)
+    r = philox4x32_10(ctr, key)
+    u = ((r[:, 0] >> np.uint32(8)).astype(np.float64) + 0.5) * 2.0 ** -24
+    with np.errstate(divide="ignore"):
+        keys = np.where(w > 0, -np.log(u) / np.where(w > 0, w, 1.0), np.inf)
+    order = np.lexsort((np.arange(N), keys))
+    n = min(int(n_return), int((w > 0).sum()))
+    return order[:n]
+
+
 def cleansing_weights(weights, eps=float(np.finfo(np.float32).eps)):
     """SOBER/_weights.py:32-38."""
     w = np.array(weights, dtype=np.float64, copy=True)

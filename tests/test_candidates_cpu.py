@@ -72,3 +72,16 @@ def test_lfi_is_a_normal_cdf():
     ref = torch.distributions.Normal(0.0, 1.0).cdf(torch.tensor((m - 1.0) / np.sqrt(v))).numpy()
     np.testing.assert_allclose(osam.lfi(m, v), ref, rtol=1e-12)
     np.testing.assert_allclose(osam.lfi(m, v, log=True), np.log(ref + torch.finfo().eps), rtol=1e-12)
+
+
+def test_sir_race_is_proportional_without_replacement():
+    """The oracle's exponential race behaves like torch.multinomial(weights, n) without replacement:
+    no repeats, zero weights never drawn, first-draw frequencies proportional to the weights."""
+    w = np.array([0.0, 1.0, 2.0, 5.0, 0.0, 2.0])
+    firsts = np.zeros(6)
+    for s in range(3000):
+        d = osam.sir_indices(w, 3, seed=s)
+        assert len(set(d.tolist())) == 3 and w[d].min() > 0
+        firsts[d[0]] += 1
+    np.testing.assert_allclose(firsts / 3000, w / w.sum(), atol=0.03)
+    assert len(osam.sir_indices(w, 10, seed=1)) == 4

@@ -103,3 +103,27 @@ def test_prior_sampler_call_pattern(bs):
     cov = ogp.ScaleKernel(ogp.RBFKernel(1.5), 1.0)
     idx, wq = basq_b200.recombination(pts_rec, pts_nys, 20, cov.forward, DEV)
     assert 1 <= len(idx) <= 20 and bool((wq > 0).all())
+
+
+def test_sir_matches_oracle_race_and_weights(bs):
+    """UncertaintySampler.SIR (torch.multinomial without replacement): same draws as the oracle's
+    exponential race on the same Philox stream, no repeats, zero-weight points never drawn, and
+    inclusion frequencies proportional to the weights when n << N."""
+    g = torch.Generator().manual_seed(3)
+    N, n = 200_000, 1000
+    w = torch.rand(N, generator=g, dtype=torch.float64) ** 3
+    w[::5] = 0.0
+    idx = bs.sir_indices(w.to(DEV), n, seed=99).cpu().numpy()
+    ref = osam.sir_indices(w.numpy(), n, seed=99)
+    assert np.array_equal(idx, ref)
+    assert len(set(idx.tolist())) == n and bool((w[idx] > 0).all())
+    # more draws than positive weights: every positive-weight point exactly once
+    w2 = torch.zeros(5000, dtype=torch.float64); w2[torch.arange(0, 5000, 50)] = 1.0
+    idx2 = bs.sir_indices(w2.to(DEV), 500, seed=1).cpu()
+    assert sorted(idx2.tolist()) == list(range(0, 5000, 50))
+    # frequencies: two weight classes 3 : 1, many independent seeds
+    w3 = torch.ones(4000, dtype=torch.float64); w3[:2000] = 3.0
+    hi = sum(int((bs.sir_indices(w3.to(DEV), 40, seed=s) < 2000).sum()) for s in range(200))
+    assert abs(hi / (200 * 40) - 0.75) < 0.02
+    Xs = bs.SIR(torch.arange(4000, dtype=torch.float32, device=DEV).unsqueeze(1), w3.to(DEV), 7, seed=5)
+    assert Xs.shape == (7, 1)
