@@ -14,12 +14,15 @@
 // set).  What remains on the CUDA cores per pair is 1 MUFU + 2 integer ops + 1 DFMA; the DP-long
 // FFMA chain of the scalar kernel moved to the tensor pipe.
 //
-// CTA = 21 warps, one CTA per SM, persistent over work items (MT landmark tiles x JT sets):
-//   warps 0-15  epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31 (one landmark per thread) and
-//               column part w / 4 of every accumulator buffer (4 warps per scheduler hide the
-//               tcgen05.ld / MUFU / DFMA latencies of one another; the MUFU pipe is the bound)
-//   warps 16-19 producers: candidate records (HBM/L2) -> hi/lo split -> K-major B stage in smem
-//   warp  20    TMEM allocation, landmark (A) tile bulk copies, tcgen05.mma issue (one lane)
+// CTA = 20 warps, one CTA per SM, persistent over work items (MT landmark tiles x JT sets).  (20, not
+// 21: registers are allotted per group of 4 warps, so a 21st warp would cap every thread at 80
+// registers instead of 96 - measured 42.2 -> 39.3 ms for the round-1 sweep.)
+//   warps 0-15  epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31 (read as 16x256b fragments: four
+//               landmarks x two sets per thread) and column part w / 4 of every accumulator buffer
+//               (4 warps per scheduler hide the tcgen05.ld / MUFU / DFMA latencies of one another;
+//               the MUFU pipe is the bound)
+//   warps 16-18 producers: candidate records (HBM/L2) -> hi/lo split -> K-major B stage in smem
+//   warp  19    TMEM allocation, landmark (A) tile bulk copies, tcgen05.mma issue (one lane)
 // Pipelines (mbarriers): B stages full/empty (3-deep ring), TMEM accumulators full/empty (2 buffers),
 // A tiles full/empty.
 #pragma once
@@ -55,7 +58,7 @@ struct MmaCfg {
   static constexpr int A_TILE_BYTES = KA * 128 * 4;
   static constexpr int B_STAGE_BYTES = KA * NT * 4;
   static constexpr int W_STAGE_BYTES = NT * 8;
-  static constexpr int EPI_WARPS = 16, PROD_WARPS = 4;
+  static constexpr int EPI_WARPS = 16, PROD_WARPS = 3;  // 20 warps: registers are allotted per 4 warps, 21 would cap a thread at 80
   static constexpr int NPART = EPI_WARPS / 4;          // column parts of an accumulator buffer (one warp each per lane quarter)
   static constexpr int COMB_SLOT_BYTES = MT * 128 * JT * 8;
   static constexpr int SMEM_FIXED = MT * A_TILE_BYTES + NSTAGE * (B_STAGE_BYTES + W_STAGE_BYTES) + 256;
@@ -320,7 +323,7 @@ __global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(cons
           mma::mbar_wait(&t_full[buf], (tc >> 1) & 1u);
           mma::tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * NT + part * PART_COLS;
-#pragma unroll 1
+#pragma unroll
           for (int cb = 0; cb < PART_COLS; cb += 32) {
             uint32_t va[16], vb[16];
             mma::tmem_ld16x256_x4(taddr + cb, va);                         // lanes +0 .. +15
