@@ -58,7 +58,10 @@ struct MmaCfg {
   static constexpr int A_TILE_BYTES = KA * 128 * 4;
   static constexpr int B_STAGE_BYTES = KA * NT * 4;
   static constexpr int W_STAGE_BYTES = NT * 8;
-  static constexpr int EPI_WARPS = 16, PROD_WARPS = 3;  // 20 warps: registers are allotted per 4 warps, 21 would cap a thread at 80
+#ifndef BASQ_EPI_WARPS
+#define BASQ_EPI_WARPS 16
+#endif
+  static constexpr int EPI_WARPS = BASQ_EPI_WARPS, PROD_WARPS = 3;  // 20 warps: registers are allotted per 4 warps, 21 would cap a thread at 80
   static constexpr int NPART = EPI_WARPS / 4;          // column parts of an accumulator buffer (one warp each per lane quarter)
   static constexpr int COMB_SLOT_BYTES = MT * 128 * JT * 8;
   static constexpr int SMEM_FIXED = MT * A_TILE_BYTES + NSTAGE * (B_STAGE_BYTES + W_STAGE_BYTES) + 256;
