@@ -386,8 +386,10 @@ int set_sums(basq_ctx* ctx, const KParams& kp, const SetSumArgs& a);
 
 // dgemm.cu
 int dgemm(basq_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const double* A, int64_t lda,
-          const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool b_lower_tri = false);
+          const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool b_lower_tri = false,
+          bool a_lower_tri = false);
 // b_lower_tri (with tb): B is lower triangular, C = A B^T only visits k <= column
+// a_lower_tri (without ta): A is lower triangular, C = A B only visits k <= row
 
 // car.cu
 int caratheodory(basq_ctx* ctx, double* A, int n, int S, int lda, double* omega_out);

@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(WM* WN * 32) dgemm_pipe_kernel(int M, int N, i
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp / WN, wn = warp % WN;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BNN;
-  if (tri_k) K = min(K, n0 + BNN);
+  if (tri_k & 1) K = min(K, n0 + BNN);  // op(B)[k][n] = 0 for k > n
+  if (tri_k & 2) K = min(K, m0 + BM);   // op(A)[m][k] = 0 for k > m
   const int KT = (K + PK - 1) / PK;
 
   auto load = [&](int kt, int st) {
@@ -194,8 +195,8 @@ int launch_best(basq_ctx* ctx, int m, int n, int k, double alpha, const double* 
 }  // namespace
 
 int dgemm(basq_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const double* A, int64_t lda,
-          const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool b_lower_tri) {
-  const int tri_k = (b_lower_tri && tb) ? 1 : 0;
+          const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool b_lower_tri, bool a_lower_tri) {
+  const int tri_k = ((b_lower_tri && tb) ? 1 : 0) | ((a_lower_tri && !ta) ? 2 : 0);
   if (m <= 0 || n <= 0) return BASQ_OK;
   BASQ_CHECK(k >= 0, BASQ_ERR_INVALID, "dgemm: negative k");
   BASQ_CHECK(ceil_div(m, 64) <= 65535, BASQ_ERR_UNSUPPORTED, "dgemm: m=%d too large for one launch", m);

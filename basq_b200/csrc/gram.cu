@@ -144,6 +144,15 @@ __global__ void coldot_kernel(const double* __restrict__ V, const double* __rest
   out[p] = base - s;
 }
 
+// T[i][k] = W[i][k] + W[k][i] (k < i), W[i][i] (k == i), 0 (k > i): v^T W v = sum_i v_i (T v)_i with a
+// lower-triangular T - half the flops of W v for the posterior variance
+__global__ void tri_fold_kernel(const double* __restrict__ W, int n, double* __restrict__ T) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)n * n) return;
+  const int i = (int)(t / n), k = (int)(t % n);
+  T[t] = k < i ? W[t] + W[(int64_t)k * n + i] : (k == i ? W[t] : 0.0);
+}
+
 // MMLT factor: mu_g = exp(m_h + v_h / 2) - 1   (SOBER/BASQ/_scale_mmlt.py:211-223)
 __global__ void mmlt_factor_kernel(const double* __restrict__ mean, const double* __restrict__ var, int64_t n,
                                    double* __restrict__ out) {
@@ -175,26 +184,30 @@ int gp_predict_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const KParams& 
   if (mean_out) BASQ_TRY(landmark_dot(ctx, kp, lmobs, desc->alpha, desc->mean_const, X, N, mean_out));
   if (!var_out || N == 0) return BASQ_OK;
   const int n_obs = desc->n_obs;
-  // chunk so that V and Y (n_obs x P fp64 each) stay around 64 MB
-  int64_t P = (int64_t)(64ll << 20) / (8ll * n_obs);
+  // chunk so that V and Y (n_obs x P fp64 each) stay around 512 MB (large GEMMs: fewer, fuller waves)
+  int64_t P = (int64_t)(512ll << 20) / (8ll * n_obs);
   P = P < 1024 ? 1024 : (P > 65536 ? 65536 : P);
   P = (P / 128) * 128;
   if (P > N) P = N;
-  DevBuf V, Y;
+  DevBuf V, Y, T;
   BASQ_TRY(V.alloc(ctx, sizeof(double) * n_obs * P));
   BASQ_TRY(Y.alloc(ctx, sizeof(double) * n_obs * P));
+  BASQ_TRY(T.alloc(ctx, sizeof(double) * (size_t)n_obs * n_obs));
+  tri_fold_kernel<<<(unsigned)ceil_div64((int64_t)n_obs * n_obs, 256), 256, 0, ctx->stream>>>(desc->W, n_obs, T.as<double>());
+  ctx->launches++;
   const size_t esz = desc->dtype == BASQ_F64 ? 8 : 4;
   for (int64_t p0 = 0; p0 < N; p0 += P) {
     const int64_t cnt = (N - p0 < P) ? N - p0 : P;
     const void* Xc = (const unsigned char*)X + (size_t)p0 * desc->d * esz;
     BASQ_TRY(base_gram(ctx, kp, lmobs, Xc, cnt, V.as<double>(), P));
-    BASQ_TRY(dgemm(ctx, false, false, n_obs, (int)cnt, n_obs, 1.0, desc->W, n_obs, V.as<double>(), P, 0.0,
-                   Y.as<double>(), P));
+    BASQ_TRY(dgemm(ctx, false, false, n_obs, (int)cnt, n_obs, 1.0, T.as<double>(), n_obs, V.as<double>(), P, 0.0,
+                   Y.as<double>(), P, /*b_lower_tri=*/false, /*a_lower_tri=*/true));
     coldot_kernel<<<ceil_div(cnt, 256), 256, 0, ctx->stream>>>(V.as<double>(), Y.as<double>(), n_obs, cnt, P,
                                                                 desc->outputscale + desc->noise, var_out + p0);
     ctx->launches++;
     BASQ_CUDA(cudaGetLastError());
   }
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));  // scratch goes out of scope
   return BASQ_OK;
 }
 
