@@ -72,35 +72,45 @@ __device__ __forceinline__ void write_record_f64(const KParams& kp, unsigned cha
   for (int i = 3; i < nd; ++i) h[i] = (i - 3 < kp.dp) ? xs[i - 3] : 0.0;
 }
 
-// pass 3 (or the only pass when mu == nullptr): write the records of the kept points in order
+// pass 3 (or the only pass when mu == nullptr): write the records of the kept points in order.
+// The kept records of a block are contiguous in the pool (slot = rank of the point among the block's
+// kept points), so they are assembled in shared memory and streamed out with 16-byte stores that
+// consecutive threads issue to consecutive addresses.
 template <typename T, bool F64>
 __global__ void build_records_kernel(KParams kp, const T* __restrict__ X, int64_t N, double uniform_w,
                                      const double* __restrict__ mu, const double* __restrict__ factor,
                                      int factor_in_weight, const int64_t* __restrict__ block_off,
                                      unsigned char* __restrict__ recs, int rec_bytes) {
+  extern __shared__ __align__(16) unsigned char stage_rec[];  // [256][rec_bytes]
   __shared__ int warp_tot[8];
   const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const double m = (p < N) ? (mu ? mu[p] : uniform_w) : 0.0;
   const bool keep = (p < N) && (m != 0.0);
-  int64_t dest = p;
-  if (mu) {
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int pre = __popc(bal & ((1u << lane) - 1u));
-    if (lane == 0) warp_tot[warp] = __popc(bal);
-    __syncthreads();
-    int wbase = 0;
-    for (int w = 0; w < warp; ++w) wbase += warp_tot[w];
-    dest = block_off[blockIdx.x] + wbase + pre;
+  const unsigned bal = __ballot_sync(0xffffffffu, keep);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pre = __popc(bal & ((1u << lane) - 1u));
+  if (lane == 0) warp_tot[warp] = __popc(bal);
+  __syncthreads();
+  int wbase = 0, kept = 0;
+  for (int w = 0; w < 8; ++w) {
+    if (w < warp) wbase += warp_tot[w];
+    kept += warp_tot[w];
   }
-  if (!keep) return;
-  const double fac = factor ? factor[p] : 1.0;
-  const double wf = factor_in_weight ? m * fac : fac;
-  unsigned char* rec = recs + dest * (int64_t)rec_bytes;
-  if (F64)
-    write_record_f64(kp, rec, rec_bytes, X + p * kp.d, wf, m, p);
-  else
-    write_record_f32(kp, rec, rec_bytes, X + p * kp.d, wf, m, (int)p);
+  if (keep) {
+    const double fac = factor ? factor[p] : 1.0;
+    const double wf = factor_in_weight ? m * fac : fac;
+    unsigned char* rec = stage_rec + (size_t)(wbase + pre) * rec_bytes;
+    if (F64)
+      write_record_f64(kp, rec, rec_bytes, X + p * kp.d, wf, m, p);
+    else
+      write_record_f32(kp, rec, rec_bytes, X + p * kp.d, wf, m, (int)p);
+  }
+  __syncthreads();
+  const int64_t first = mu ? block_off[blockIdx.x] : (int64_t)blockIdx.x * 256;
+  uint4* dst = reinterpret_cast<uint4*>(recs + first * (int64_t)rec_bytes);
+  const uint4* src = reinterpret_cast<const uint4*>(stage_rec);
+  const int chunks = kept * (rec_bytes / 16);
+  for (int c = threadIdx.x; c < chunks; c += 256) dst[c] = src[c];
 }
 
 int build_records(basq_ctx* ctx, const KParams& kp, int dtype, const void* X, int64_t N, double uniform_w,
@@ -131,14 +141,18 @@ int build_records(basq_ctx* ctx, const KParams& kp, int dtype, const void* X, in
   }
   unsigned char* recs = pool->buf[0].as<unsigned char>();
   const int64_t* boff = mu ? offs.as<int64_t>() : nullptr;
-  if (dtype == BASQ_F32)
-    build_records_kernel<float, false><<<nb, 256, 0, ctx->stream>>>(kp, (const float*)X, N, uniform_w, mu, factor,
-                                                                  factor_in_weight ? 1 : 0, boff, recs,
-                                                                  pool->rec_bytes);
-  else
-    build_records_kernel<double, true><<<nb, 256, 0, ctx->stream>>>(kp, (const double*)X, N, uniform_w, mu, factor,
-                                                                   factor_in_weight ? 1 : 0, boff, recs,
-                                                                   pool->rec_bytes);
+  const size_t smem = (size_t)256 * pool->rec_bytes;
+  if (dtype == BASQ_F32) {
+    BASQ_CUDA(cudaFuncSetAttribute(build_records_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    build_records_kernel<float, false><<<nb, 256, smem, ctx->stream>>>(kp, (const float*)X, N, uniform_w, mu, factor,
+                                                                     factor_in_weight ? 1 : 0, boff, recs,
+                                                                     pool->rec_bytes);
+  } else {
+    BASQ_CUDA(cudaFuncSetAttribute(build_records_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    build_records_kernel<double, true><<<nb, 256, smem, ctx->stream>>>(kp, (const double*)X, N, uniform_w, mu, factor,
+                                                                      factor_in_weight ? 1 : 0, boff, recs,
+                                                                      pool->rec_bytes);
+  }
   ctx->launches++;
   BASQ_CUDA(cudaGetLastError());
   if (mu) {
