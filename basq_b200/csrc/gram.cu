@@ -17,7 +17,10 @@ constexpr int LT = 32;   // landmarks staged per tile
 
 // MODE 0: write out[m, p] ; MODE 1: accumulate coef[m] * k into a per-point fp64 sum
 // FROMREC: the points are live candidate records (already centred and scaled), P = first record.
-template <typename TIN, bool F64, int MODE, bool FROMREC>
+// DPM > 0 (fp32 only): the point's coordinates stay in registers (dp rounded up to DPM, a multiple of 4,
+// padded with zeros: the extra fma(0, 0, acc) leave every bit of the result unchanged) and the staged
+// landmarks are read back as broadcast 128-bit loads.
+template <typename TIN, bool F64, int MODE, bool FROMREC, int DPM>
 __global__ void __launch_bounds__(PT) landmark_point_kernel(KParams kp, const void* __restrict__ zz_,
                                                             const float* __restrict__ bz, int Mtot,
                                                             const TIN* __restrict__ P, int64_t npts,
@@ -30,7 +33,67 @@ __global__ void __launch_bounds__(PT) landmark_point_kernel(KParams kp, const vo
   const int64_t p = (int64_t)blockIdx.x * PT + tid;
   const bool pok = p < npts;
 
-  if (!F64) {
+  if (!F64 && DPM > 0) {
+    constexpr int D4 = DPM > 0 ? DPM : 4;
+    float* zs = reinterpret_cast<float*>(smem_raw);          // [LT][D4]
+    float* bs = zs + LT * D4;                                // [LT]
+    float xr[D4];
+#pragma unroll
+    for (int i = 0; i < D4; ++i) xr[i] = 0.f;
+    float nrm = 0.f, pa = 0.f;
+    if (FROMREC) {
+      if (pok) {
+        const float* f = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(P) + p * rec_bytes);
+        pa = f[5];
+#pragma unroll
+        for (int i = 0; i < D4; ++i)
+          if (i < dp) xr[i] = f[6 + i];
+      }
+    } else {
+      if (pok) {
+        float xl[BASQ_MAX_DIM];
+        prep_point_f32(kp, P + p * kp.d, xl, &nrm);
+#pragma unroll
+        for (int i = 0; i < D4; ++i)
+          if (i < dp) xr[i] = xl[i];
+      }
+      pa = point_a_term(kp, nrm);
+    }
+    const float* zz = reinterpret_cast<const float*>(zz_);
+    double sum = 0.0;
+    const int m_begin = (MODE == 0) ? blockIdx.y * LT : 0;
+    const int m_end = (MODE == 0) ? min(Mtot, m_begin + LT) : Mtot;
+    for (int mt = m_begin; mt < m_end; mt += LT) {
+      __syncthreads();
+      const int cnt = min(LT, m_end - mt);
+      for (int x = tid; x < LT * D4; x += PT) {
+        const int l = x / D4, i = x % D4;
+        zs[x] = (l < cnt && i < dp) ? zz[(int64_t)(mt + l) * dp + i] : 0.f;
+      }
+      for (int x = tid; x < cnt; x += PT) bs[x] = bz[mt + x];
+      __syncthreads();
+      if (pok) {
+        for (int l = 0; l < cnt; ++l) {
+          float acc = __fadd_rn(pa, bs[l]);
+          const float4* z4 = reinterpret_cast<const float4*>(zs + l * D4);
+#pragma unroll
+          for (int i4 = 0; i4 < D4 / 4; ++i4) {
+            const float4 z = z4[i4];
+            acc = __fmaf_rn(xr[4 * i4 + 0], z.x, acc);
+            acc = __fmaf_rn(xr[4 * i4 + 1], z.y, acc);
+            acc = __fmaf_rn(xr[4 * i4 + 2], z.z, acc);
+            acc = __fmaf_rn(xr[4 * i4 + 3], z.w, acc);
+          }
+          const float k = finish_f32(kp.family, acc, kp.os_f);
+          if (MODE == 0)
+            out[(int64_t)(mt + l) * ldo + p] = f2d_pos(k);
+          else
+            sum = fma(f2d_pos(k), coef[mt + l], sum);
+        }
+      }
+    }
+    if (MODE == 1 && pok) out[p] = c0 + sum;
+  } else if (!F64) {
     float* xs = reinterpret_cast<float*>(smem_raw);          // [dp][PT]
     float* zs = xs + dp * PT;                                // [LT][dp]
     float* bs = zs + LT * dp;                                // [LT]
@@ -123,12 +186,25 @@ int launch_lp(basq_ctx* ctx, const KParams& kp, const LmView& lm, const void* P,
   BASQ_CHECK(gx < (1ll << 31), BASQ_ERR_UNSUPPORTED, "too many points for one launch");
   dim3 grid((unsigned)gx, MODE == 0 ? (unsigned)ceil_div(lm.count, LT) : 1u);
   BASQ_CHECK(grid.y <= 65535, BASQ_ERR_UNSUPPORTED, "too many landmarks (%d) for one Gram launch", lm.count);
-  if (f64)
-    landmark_point_kernel<double, true, MODE, FROMREC><<<grid, PT, smem, ctx->stream>>>(
+  if (f64) {
+    landmark_point_kernel<double, true, MODE, FROMREC, 0><<<grid, PT, smem, ctx->stream>>>(
         kp, lm.zz, nullptr, lm.count, (const double*)P, npts, out, ldo, coef, c0, rec_bytes);
-  else
-    landmark_point_kernel<float, false, MODE, FROMREC><<<grid, PT, smem, ctx->stream>>>(
-        kp, lm.zz, lm.b, lm.count, (const float*)P, npts, out, ldo, coef, c0, rec_bytes);
+  } else {
+    const int d4 = (kp.dp + 3) / 4 * 4;
+#define BASQ_LP_CASE(D)                                                                                   \
+  case D:                                                                                                \
+    landmark_point_kernel<float, false, MODE, FROMREC, D><<<grid, PT, 4 * (LT * D + LT), ctx->stream>>>(  \
+        kp, lm.zz, lm.b, lm.count, (const float*)P, npts, out, ldo, coef, c0, rec_bytes);                  \
+    break;
+    switch (d4) {
+      BASQ_LP_CASE(4) BASQ_LP_CASE(8) BASQ_LP_CASE(12) BASQ_LP_CASE(16) BASQ_LP_CASE(20) BASQ_LP_CASE(24)
+      BASQ_LP_CASE(28) BASQ_LP_CASE(32)
+      default:
+        landmark_point_kernel<float, false, MODE, FROMREC, 0><<<grid, PT, smem, ctx->stream>>>(
+            kp, lm.zz, lm.b, lm.count, (const float*)P, npts, out, ldo, coef, c0, rec_bytes);
+    }
+#undef BASQ_LP_CASE
+  }
   ctx->launches++;
   BASQ_CUDA(cudaGetLastError());
   return BASQ_OK;
