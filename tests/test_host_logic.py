@@ -107,3 +107,36 @@ def test_shard_bounds_and_survivor_counts():
     K = int(prefix[S])
     brute = [sum(int(keep[g % S]) for g in range(p)) for p in range(R + 1)]
     assert [sharded.kept_before(p, S, prefix, K) for p in range(R + 1)] == brute
+
+
+def test_level_tree_bookkeeping():
+    """sharded.LevelTree (mirror of LevelTree in csrc/api.cu): node ids, parent columns and factors of
+    a pass with F = 4 cells per set, checked against the definition - node u of level l = cells
+    u + k S 2^l; children u (low) and u + S 2^l (high); a cell's factor = product along its path."""
+    import numpy as np
+    S, F, R = 6, 4, 1000
+    tree = sharded.LevelTree(S, F, R)
+    factor = torch.zeros(F * S, dtype=torch.float64)
+    assert tree.columns() == S and list(tree.node) == list(range(S)) and tree.lvl == 0
+    # level 0: keep sets 1, 3, 4 with factors 2, 3, 5
+    om0 = np.array([0.0, 2.0, 0.0, 3.0, 5.0, 0.0])
+    more, kept = tree.advance(om0, factor)
+    assert more and kept == 3 and tree.lvl == 1
+    assert list(tree.node) == [1, 3, 4] and list(tree.ppos) == [1, 3, 4] and list(tree.fpar) == [2.0, 3.0, 5.0]
+    assert list(tree.act) == [1, 3, 4, 1 + S, 3 + S, 4 + S]              # low halves, then high halves
+    # level 1: keep low(1), high(3), high(4)
+    om1 = np.array([0.5, 0.0, 0.0, 0.0, 2.0, 1.0])
+    more, kept = tree.advance(om1, factor)
+    assert more and kept == 3 and tree.lvl == 2
+    assert list(tree.node) == [1, 3 + S, 4 + S] and list(tree.ppos) == [0, 4, 5]
+    assert list(tree.fpar) == [1.0, 6.0, 5.0]
+    assert list(tree.act) == [1, 3 + S, 4 + S, 1 + 2 * S, 3 + 3 * S, 4 + 3 * S]
+    # level 2 (cells): keep three of the six
+    om2 = np.array([1.0, 0.0, 0.25, 0.0, 1.5, 0.0])
+    more, kept = tree.advance(om2, factor)
+    assert not more and kept == 3
+    expect = torch.zeros(F * S, dtype=torch.float64)
+    expect[1] = 1.0; expect[4 + S] = 1.25; expect[3 + 3 * S] = 9.0
+    assert torch.equal(factor, expect)
+    # fewer live points than sets: only min(S, R) columns at level 0
+    assert sharded.LevelTree(S, 1, 4).columns() == 4
