@@ -10,6 +10,8 @@
 // Measured on B200 (999 x 11002 x 2000, the projection): 26.6 TFLOP/s; cuBLAS 12.9 reaches 33.2.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace basq {
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(WM* WN * 32) dgemm_pipe_kernel(int M, int N, i
                                                                 const double* __restrict__ A, int64_t lda,
                                                                 const double* __restrict__ B, int64_t ldb, double beta,
                                                                 double* __restrict__ C, int64_t ldc, int tri_k, int a16,
-                                                                int b16) {
+                                                                int b16, int kchunk, double* __restrict__ part) {
   constexpr int BM = WM * 8 * MF, BNN = WN * 8 * NF, NTHR = WM * WN * 32;
   constexpr int AS = TA ? BM + 4 : PK + 4, BS = TB ? PK + 4 : BNN + 4;
   constexpr int A_EL = TA ? PK * (BM + 4) : BM * (PK + 4);
@@ -100,11 +102,14 @@ __global__ void __launch_bounds__(WM* WN * 32) dgemm_pipe_kernel(int M, int N, i
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BNN;
   if (tri_k & 1) K = min(K, n0 + BNN);  // op(B)[k][n] = 0 for k > n
   if (tri_k & 2) K = min(K, m0 + BM);   // op(A)[m][k] = 0 for k > m
-  const int KT = (K + PK - 1) / PK;
+  // split-K (small outputs, long K): slice blockIdx.z covers k in [kb, K) with K clipped to the slice
+  const int kb = kchunk > 0 ? blockIdx.z * kchunk : 0;
+  if (kchunk > 0) K = min(K, kb + kchunk);
+  const int KT = K > kb ? (K - kb + PK - 1) / PK : 0;
 
   auto load = [&](int kt, int st) {
-    stage_tile<!TA, BM, NTHR>(As + st * A_EL, A, lda, m0, M, kt * PK, K, a16, tid);
-    stage_tile<TB, BNN, NTHR>(Bs + st * B_EL, B, ldb, n0, N, kt * PK, K, b16, tid);
+    stage_tile<!TA, BM, NTHR>(As + st * A_EL, A, lda, m0, M, kb + kt * PK, K, a16, tid);
+    stage_tile<TB, BNN, NTHR>(Bs + st * B_EL, B, ldb, n0, N, kb + kt * PK, K, b16, tid);
   };
 
   double acc[MF][NF][2];
@@ -156,11 +161,26 @@ __global__ void __launch_bounds__(WM* WN * 32) dgemm_pipe_kernel(int M, int N, i
       for (int h = 0; h < 2; ++h) {
         const int n = n0 + wn * (8 * NF) + j * 8 + fk * 2 + h;
         if (n >= N) continue;
-        double* c = C + (int64_t)m * ldc + n;
-        *c = (beta == 0.0) ? alpha * acc[i][j][h] : fma(alpha, acc[i][j][h], beta * (*c));
+        if (part) {  // split-K: the raw partial sum of this slice; splitk_reduce_kernel finishes
+          part[((int64_t)blockIdx.z * M + m) * N + n] = acc[i][j][h];
+        } else {
+          double* c = C + (int64_t)m * ldc + n;
+          *c = (beta == 0.0) ? alpha * acc[i][j][h] : fma(alpha, acc[i][j][h], beta * (*c));
+        }
       }
     }
   }
+}
+
+// C = alpha * (sum of the slices, in slice order: deterministic) + beta * C
+__global__ void splitk_reduce_kernel(const double* __restrict__ part, int splits, int M, int N, double alpha,
+                                     double beta, double* __restrict__ C, int64_t ldc) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)M * N) return;
+  double s = 0.0;
+  for (int z = 0; z < splits; ++z) s += part[(int64_t)z * M * N + t];
+  double* c = C + (t / N) * ldc + (t % N);
+  *c = (beta == 0.0) ? alpha * s : fma(alpha, s, beta * (*c));
 }
 
 template <bool TA, bool TB, int WM, int WN, int MF, int NF>
@@ -174,8 +194,28 @@ int launch_pipe(basq_ctx* ctx, int m, int n, int k, double alpha, const double* 
   BASQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
   const int a16 = (lda % 2 == 0) && ((uintptr_t)A % 16 == 0), b16 = (ldb % 2 == 0) && ((uintptr_t)B % 16 == 0);
   dim3 grid((unsigned)ceil_div(n, BNN), (unsigned)ceil_div(m, BM));
-  kern<<<grid, WM * WN * 32, SMEM, ctx->stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k, a16, b16);
-  return BASQ_OK;
+  // split-K when the output has far fewer tiles than the GPU has SMs and K is long (e.g. the 99 x 200
+  // projection of a batch of 100 over 10^4 landmarks, the q x q Gram matrices of CholeskyQR)
+  const int64_t tiles = (int64_t)grid.x * grid.y;
+  int splits = 1;
+  if (tri_k == 0 && tiles * 2 <= ctx->num_sms && k >= 16 * PK)
+    splits = (int)std::min<int64_t>(ctx->num_sms / tiles, k / (8 * PK));
+  if (splits <= 1) {
+    kern<<<grid, WM * WN * 32, SMEM, ctx->stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k, a16, b16, 0,
+                                                    nullptr);
+    return BASQ_OK;
+  }
+  const int kchunk = ceil_div(ceil_div(k, splits), PK) * PK;
+  splits = ceil_div(k, kchunk);
+  DevBuf part;
+  BASQ_TRY(part.alloc(ctx, sizeof(double) * (size_t)splits * m * n));
+  grid.z = (unsigned)splits;
+  kern<<<grid, WM * WN * 32, SMEM, ctx->stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k, a16, b16, kchunk,
+                                                  part.as<double>());
+  splitk_reduce_kernel<<<(unsigned)ceil_div64((int64_t)m * n, 256), 256, 0, ctx->stream>>>(part.as<double>(), splits, m, n,
+                                                                                          alpha, beta, C, ldc);
+  ctx->launches++;
+  return BASQ_OK;  // `part` returns to the stream-ordered pool after the reduction
 }
 
 // tile shape that needs the fewest SM-waves of work for an m x n output

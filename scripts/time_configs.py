@@ -22,11 +22,15 @@ def run(name, kern, d, N, M, n, reps=3):
         _, U = ops.nystrom_basis(kern, Z, n - 1, omega=Om, want_S=False)
         return ops.recombine(kern, X, Z, U)
     step(); torch.cuda.synchronize()
+    ctx = _lib.context_for(dev)
+    ctx.profile(True); ctx.profile_read(True)
     t0 = time.perf_counter()
     for _ in range(reps): idx, w = step()
     torch.cuda.synchronize()
     ms = (time.perf_counter() - t0) / reps * 1e3
-    print(f"{name:58s} N={N:.0e} M={M} n={n} d={d}: {ms:9.1f} ms  {N / ms * 1e3:.3g} points/s  ({len(idx)} points)")
+    prof = ctx.profile_read(True); ctx.profile(False)
+    phases = ", ".join(f"{k} {v[0] / reps:.1f}" for k, v in prof.items() if v[0] > 0)
+    print(f"{name:58s} N={N:.0e} M={M} n={n} d={d}: {ms:9.1f} ms  {N / ms * 1e3:.3g} points/s  ({len(idx)} points)  [{phases}]")
 
 Xo, yo = observations(2, 102, 3)
 m2 = gp.FixedGP(Xo.to(dev, torch.float32), yo.to(dev), gp.ScaleKernel(gp.RBFKernel(1.0), 1.0), noise=1e-4)
