@@ -32,6 +32,10 @@ def run(name, kern, d, N, M, n, reps=3):
     phases = ", ".join(f"{k} {v[0] / reps:.1f}" for k, v in prof.items() if v[0] > 0)
     print(f"{name:58s} N={N:.0e} M={M} n={n} d={d}: {ms:9.1f} ms  {N / ms * 1e3:.3g} points/s  ({len(idx)} points)  [{phases}]")
 
+Xo, yo = observations(10, 102, 2)
+m1 = gp.FixedGP(Xo.to(dev, torch.float32), yo.to(dev), gp.ScaleKernel(gp.RBFKernel(2.5), 1.0), noise=1e-4)
+run("config 1: main.py default, 10-D, VBQ (batch selection)", spec_from_model(m1, _lib.PRED_COV), 10, 20_000, 200, 100, reps=10)
+run("config 1: main.py default, 10-D, VBQ (quadrature)", spec_from_model(m1, _lib.PRED_COV), 10, 100_000, 200, 100, reps=10)
 Xo, yo = observations(2, 102, 3)
 m2 = gp.FixedGP(Xo.to(dev, torch.float32), yo.to(dev), gp.ScaleKernel(gp.RBFKernel(1.0), 1.0), noise=1e-4)
 run("config 2: Tutorial 01, 2-D, VBQ posterior covariance", spec_from_model(m2, _lib.PRED_COV), 2, 1_000_000, 10_000, 100)
