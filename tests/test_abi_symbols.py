@@ -47,3 +47,18 @@ def test_no_cpu_fallback():
     import basq_b200
     with pytest.raises(_lib.BasqError):
         basq_b200.recombination(X, X[:4], 3, spec, torch.device("cpu"))
+
+
+def test_binding_argument_counts_match_header():
+    """Every ctypes signature in basq_b200/_lib.py has as many arguments as the header's prototype
+    (a mismatch would silently corrupt the call on the GPU box)."""
+    from basq_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "basq_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = dict(re.findall(r"\b(basq_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S))
+    assert set(protos) == set(_lib.SYMBOLS)
+    for name, args in protos.items():
+        args = " ".join(args.split())
+        n_header = 0 if args in ("", "void") else args.count(",") + 1
+        fn = getattr(_lib.lib, name)
+        assert len(fn.argtypes) == n_header, f"{name}: header has {n_header} arguments, binding {len(fn.argtypes)}"
