@@ -31,7 +31,7 @@ class KernelDesc(C.Structure):
         ("outputscale", C.c_double),
         ("lengthscale", C.c_double * BASQ_MAX_DIM),
         ("noise", C.c_double), ("mean_const", C.c_double), ("diag_add", C.c_double),
-        ("n_obs", C.c_int32), ("reserved", C.c_int32),
+        ("n_obs", C.c_int32), ("noise_diag", C.c_int32),
         ("Xobs", C.c_void_p), ("W", C.c_void_p), ("alpha", C.c_void_p),
     ]
 
@@ -49,6 +49,8 @@ def _load():
         "basq_last_error": (C.c_char_p, []),
         "basq_ctx_create": (I, [I, P, C.POINTER(P)]),
         "basq_ctx_destroy": (None, [P]),
+        "basq_ctx_trim": (I, [P, L]),
+        "basq_ctx_conditioning": (I, [P, D, C.POINTER(D), C.POINTER(L)]),
         "basq_ctx_launch_count": (L, [P]),
         "basq_ctx_pair_evals": (L, [P]),
         "basq_ctx_profile": (I, [P, I]),
@@ -121,6 +123,17 @@ class Context:
     @property
     def pair_evals(self) -> int:
         return int(lib.basq_ctx_pair_evals(self.handle))
+
+    def trim(self, keep_bytes: int = 0):
+        """Hand the context's cached scratch memory back to the driver (down to keep_bytes)."""
+        check(lib.basq_ctx_trim(self.handle, int(keep_bytes)))
+
+    def conditioning(self, kappa_max: float = -1.0):
+        """(last kappa = max_m |(K_ZX W)_m|_1, number of fp32 -> fp64 promotions so far); a non-negative
+        kappa_max sets the promotion threshold (0 = never promote)."""
+        k, n = C.c_double(0.0), C.c_int64(0)
+        check(lib.basq_ctx_conditioning(self.handle, float(kappa_max), C.byref(k), C.byref(n)))
+        return float(k.value), int(n.value)
 
     def profile(self, enable: bool):
         check(lib.basq_ctx_profile(self.handle, 1 if enable else 0))

@@ -24,13 +24,16 @@ __global__ void scale_columns_kernel(double* __restrict__ U, int rows, int cols,
   U[(int64_t)r * ld + c] *= s[c];
 }
 
-// out = f(C, fx, fy) elementwise for the warped kernels; diag_add on the leading diagonal
+// out = f(C, fx, fy) elementwise for the warped kernels.  On the leading diagonal the likelihood
+// noise enters the covariance BEFORE the warping (predictive_covariance adds it, BASQ/_gp.py:275-276,
+// and wsabi*_kernel warp its result, BASQ/_wsabi.py:216-224), the jitter after it.
 __global__ void warp_gram_kernel(double* __restrict__ C, int64_t a, int64_t b, int mode, const double* __restrict__ fx,
-                                 const double* __restrict__ fy, double diag_add) {
+                                 const double* __restrict__ fy, double pre_add, double diag_add) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a * b) return;
   const int64_t i = t / b, j = t % b;
   double c = C[t];
+  if (i == j) c += pre_add;
   if (mode == BASQ_WSABI_L) c = fx[i] * c * fy[j];
   else if (mode == BASQ_WSABI_M) c = fx[i] * c * fy[j] + 0.5 * c * c;
   else if (mode == BASQ_MMLT_G) c = fx[i] * fy[j] * expm1(c);
@@ -88,6 +91,26 @@ __global__ void level_finish_kernel(double* __restrict__ raw, const double* __re
   }
 }
 
+__global__ void f32_to_f64_kernel(const float* __restrict__ in, int64_t n, double* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = (double)in[t];
+}
+
+// kappa = max over rows m of sum_o |A[m, o]|  (non-negative doubles order like their bit patterns)
+__global__ void row_l1_max_kernel(const double* __restrict__ A, int rows, int cols, unsigned long long* __restrict__ out) {
+  __shared__ double sh[256];
+  const int m = blockIdx.x;
+  double acc = 0.0;
+  for (int o = threadIdx.x; o < cols; o += blockDim.x) acc += fabs(A[(int64_t)m * cols + o]);
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicMax(out, (unsigned long long)__double_as_longlong(sh[0]));
+}
+
 int check_finite_host(const double* v, int64_t n, const char* what) {
   for (int64_t i = 0; i < n; ++i)
     BASQ_CHECK(isfinite(v[i]), BASQ_ERR_NUMERIC, "%s contains a non-finite value at %lld", what, (long long)i);
@@ -130,6 +153,11 @@ struct basq_session {
   DevBuf lnode, lppos, lfpar;  // device copies of a level's node ids, parent positions, parent factors
   DevBuf V, corrT;  // chunk buffers of the non-linear modes
   int64_t chunkP = 0;
+  // fp32 inputs whose posterior correction would amplify the fp32 kernel noise beyond tolerance are
+  // promoted to the all-fp64 path (session_create_impl): fp64 copies of the inputs live here
+  DevBuf X64, Z64, Xobs64;
+  bool promoted = false;
+  double kappa = 0.0;
   int64_t idx_base = 0;
   bool scale_wf = true;
   std::vector<double> omega_host;
@@ -209,6 +237,57 @@ int session_create_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
   BASQ_TRY(prep_landmarks(ctx, s->kp, desc->dtype, Z, M, augment ? desc->Xobs : nullptr, augment ? n_obs : 0, &s->lm));
   s->Mtot = s->lm.count;
 
+  if (mode != BASQ_PLAIN) {
+    // Az = K(Z, Xobs) W   (BASQ/_gp.py:270-273: KxX @ woodbury_inv)
+    DevBuf KzX, kap;
+    BASQ_TRY(KzX.alloc(ctx, sizeof(double) * (size_t)M * n_obs));
+    BASQ_TRY(s->Az.alloc(ctx, sizeof(double) * (size_t)M * n_obs));
+    BASQ_TRY(base_gram(ctx, s->kp, s->lm.view(0, (int)M), desc->Xobs, n_obs, KzX.as<double>(), n_obs));
+    BASQ_TRY(dgemm(ctx, false, false, (int)M, n_obs, n_obs, 1.0, KzX.as<double>(), n_obs, desc->W, n_obs, 0.0,
+                   s->Az.as<double>(), n_obs));
+    // Conditioning guard.  The correction K_ZX W k(Xobs, x) multiplies the kernel values by the rows of
+    // Az, so an evaluation error eps_k of k (fp32: ~2e-7 relative) reaches the covariance as
+    // eps_k |Az_m|_1 sigma_f^2.  kappa = max_m |Az_m|_1 is O(10) for well-separated observations even at
+    // the reference's default noise 1e-10 (BASQ/_parameters.py:30), but grows like sigma_f / sigma_n for
+    // clustered ones; beyond kappa_max the fp32 inputs are promoted to the all-fp64 path.
+    BASQ_TRY(kap.alloc(ctx, sizeof(unsigned long long)));
+    BASQ_CUDA(cudaMemsetAsync(kap.p, 0, sizeof(unsigned long long), ctx->stream));
+    row_l1_max_kernel<<<(unsigned)M, 256, 0, ctx->stream>>>(s->Az.as<double>(), (int)M, n_obs,
+                                                            kap.as<unsigned long long>());
+    ctx->launches++;
+    BASQ_CUDA(cudaGetLastError());
+    BASQ_CUDA(cudaMemcpyAsync(&s->kappa, kap.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    BASQ_CUDA(cudaStreamSynchronize(ctx->stream));  // also: KzX goes out of scope
+    BASQ_CHECK(isfinite(s->kappa), BASQ_ERR_NUMERIC, "the GP caches contain non-finite values (K_ZX W)");
+    ctx->last_kappa = s->kappa;
+    if (desc->dtype == BASQ_F32 && ctx->kappa_max > 0.0 && s->kappa > ctx->kappa_max) {
+      // promote: fp64 copies of X, Z, Xobs, then the same construction with dtype = F64
+      const int d = desc->d;
+      auto widen = [&](const void* src, int64_t rows, DevBuf* dst) -> int {
+        BASQ_TRY(dst->alloc(ctx, sizeof(double) * (size_t)std::max<int64_t>(rows, 1) * d));
+        if (rows > 0) {
+          f32_to_f64_kernel<<<(unsigned)ceil_div64(rows * d, 256), 256, 0, ctx->stream>>>((const float*)src, rows * d,
+                                                                                           dst->as<double>());
+          ctx->launches++;
+          BASQ_CUDA(cudaGetLastError());
+        }
+        return BASQ_OK;
+      };
+      BASQ_TRY(widen(X, N_loc, &s->X64));
+      BASQ_TRY(widen(Z, M, &s->Z64));
+      BASQ_TRY(widen(desc->Xobs, n_obs, &s->Xobs64));
+      s->lm.zz.release(); s->lm.b.release(); s->lm.lmA.release();
+      s->lmobs.zz.release(); s->lmobs.b.release(); s->lmobs.lmA.release();
+      s->Az.release();
+      basq_kernel_desc d64 = *desc;
+      d64.dtype = BASQ_F64;
+      d64.Xobs = s->Xobs64.p;
+      s->promoted = true;
+      ctx->promotions++;
+      return session_create_impl(ctx, &d64, s->X64.p, N_loc, N_glob, idx_base, s->Z64.p, M, U, q, mu, S_override, s);
+    }
+  }
+
   // per-landmark and per-point factors of the warped kernels
   DevBuf sx;
   const bool has_factor = (mode == BASQ_WSABI_L || mode == BASQ_WSABI_M || mode == BASQ_MMLT_G);
@@ -228,21 +307,12 @@ int session_create_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
                                                                                 s->Mtot, s->sz.as<double>());
     ctx->launches++;
   }
-  if (mode != BASQ_PLAIN) {
-    // Az = K(Z, Xobs) W   (BASQ/_gp.py:270-273: KxX @ woodbury_inv)
-    DevBuf KzX;
-    BASQ_TRY(KzX.alloc(ctx, sizeof(double) * (size_t)M * n_obs));
-    BASQ_TRY(s->Az.alloc(ctx, sizeof(double) * (size_t)M * n_obs));
-    BASQ_TRY(base_gram(ctx, s->kp, s->lm.view(0, (int)M), desc->Xobs, n_obs, KzX.as<double>(), n_obs));
-    BASQ_TRY(dgemm(ctx, false, false, (int)M, n_obs, n_obs, 1.0, KzX.as<double>(), n_obs, desc->W, n_obs, 0.0,
-                   s->Az.as<double>(), n_obs));
-    if (augment) {
-      // U'[:, M:] = -(U diag(sz)) Az : the posterior-covariance correction folded into the projection
-      BASQ_TRY(dgemm(ctx, false, false, q, n_obs, (int)M, -1.0, s->Uprime.as<double>(), s->Mtot, s->Az.as<double>(),
-                     n_obs, 0.0, s->Uprime.as<double>() + M, s->Mtot));
-      s->Az.release();
-    }
-    BASQ_CUDA(cudaStreamSynchronize(ctx->stream));  // KzX goes out of scope
+  if (augment) {
+    // U'[:, M:] = -(U diag(sz)) Az : the posterior-covariance correction folded into the projection
+    BASQ_TRY(dgemm(ctx, false, false, q, n_obs, (int)M, -1.0, s->Uprime.as<double>(), s->Mtot, s->Az.as<double>(),
+                   n_obs, 0.0, s->Uprime.as<double>() + M, s->Mtot));
+    BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    s->Az.release();
   }
 
   // candidate records
@@ -728,18 +798,30 @@ int basq_ctx_create(int device, void* stream, basq_ctx** out) {
     return BASQ_ERR_CUDA;
   }
   {
-    // keep freed scratch in the stream-ordered pool instead of returning it to the driver
-    cudaMemPool_t pool = nullptr;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
-      uint64_t keep = UINT64_MAX;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    // Private stream-ordered pool (the device's default pool is left untouched: it is shared with
+    // whatever else lives in the process).  Freed scratch stays cached in it across the pass loop;
+    // every top-level call trims it back to pool_keep bytes before returning (basq_ctx_trim).
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    if (cudaMemPoolCreate(&c->pool, &props) != cudaSuccess) {
+      delete c;
+      set_error("cudaMemPoolCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return BASQ_ERR_CUDA;
     }
-    (void)cudaGetLastError();
+    uint64_t hold = UINT64_MAX;  // inside a call nothing goes back to the driver
+    cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &hold);
+    c->pool_keep = 8ull << 30;
+    if (const char* t = getenv("BASQ_POOL_KEEP_MB")) c->pool_keep = (uint64_t)strtoull(t, nullptr, 10) << 20;
   }
   { const char* t = getenv("BASQ_TRACE"); c->trace = t && t[0] == '1'; }
   { const char* t = getenv("BASQ_CAR_GENERAL"); c->force_general_car = t && t[0] == '1'; }
   { const char* t = getenv("BASQ_NYSTROM_FP64"); c->no_tensor_nystrom = t && t[0] == '1'; }
   { const char* t = getenv("BASQ_SETSUM_SCALAR"); c->scalar_setsum = t && t[0] == '1'; }
+  { const char* t = getenv("BASQ_F32_KAPPA_MAX"); if (t) c->kappa_max = atof(t); }
   *out = c;
   return BASQ_OK;
 }
@@ -748,10 +830,36 @@ void basq_ctx_destroy(basq_ctx* ctx) {
   if (!ctx) return;
   ctx->resolve_spans();
   for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
+  if (ctx->pool) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemPoolDestroy(ctx->pool);
+  }
+  (void)cudaGetLastError();
   delete ctx;
 }
 
+int basq_ctx_trim(basq_ctx* ctx, int64_t keep_bytes) {
+  BASQ_CHECK(ctx, BASQ_ERR_INVALID, "ctx is NULL");
+  if (!ctx->pool) return BASQ_OK;
+  const uint64_t keep = keep_bytes < 0 ? ctx->pool_keep : (uint64_t)keep_bytes;
+  uint64_t reserved = 0;
+  cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+  if (reserved > keep) {
+    BASQ_CUDA(cudaStreamSynchronize(ctx->stream));  // pending stream-ordered frees become releasable
+    BASQ_CUDA(cudaMemPoolTrimTo(ctx->pool, (size_t)keep));
+  }
+  return BASQ_OK;
+}
+
 int64_t basq_ctx_launch_count(const basq_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int basq_ctx_conditioning(basq_ctx* ctx, double kappa_max, double* last_kappa_host, int64_t* promotions_host) {
+  BASQ_CHECK(ctx, BASQ_ERR_INVALID, "ctx is NULL");
+  if (kappa_max >= 0.0) ctx->kappa_max = kappa_max;
+  if (last_kappa_host) *last_kappa_host = ctx->last_kappa;
+  if (promotions_host) *promotions_host = ctx->promotions;
+  return BASQ_OK;
+}
 int64_t basq_ctx_pair_evals(const basq_ctx* ctx) { return ctx ? ctx->pair_evals : 0; }
 
 int basq_ctx_profile(basq_ctx* ctx, int enable) {
@@ -802,7 +910,9 @@ int basq_gram(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_
   BASQ_CHECK(ctx && desc && X && Y && out, BASQ_ERR_INVALID, "basq_gram: NULL argument");
   BASQ_CHECK(a >= 1 && b >= 1, BASQ_ERR_INVALID, "basq_gram: empty operand");
   BASQ_CUDA(cudaSetDevice(ctx->device));
-  return basq::gram_matrix(ctx, desc, X, a, Y, b, out, false);
+  const int rc = basq::gram_matrix(ctx, desc, X, a, Y, b, out, false);
+  basq_ctx_trim(ctx, -1);
+  return rc;
 }
 
 }  // extern "C"
@@ -852,10 +962,11 @@ int basq::gram_matrix(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X
       BASQ_TRY(warp_factor(ctx, desc, kp, lmobs.view(), X, a, fx.as<double>()));
       BASQ_TRY(warp_factor(ctx, desc, kp, lmobs.view(), Y, b, fy.as<double>()));
     }
-    if (warped || desc->diag_add != 0.0) {
+    const double pre_add = desc->noise_diag ? desc->noise : 0.0;
+    if (warped || desc->diag_add != 0.0 || pre_add != 0.0) {
       const int64_t tot = a * b;
       warp_gram_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, ctx->stream>>>(
-          out, a, b, warped ? mode : BASQ_PRED_COV, fx.as<double>(), fy.as<double>(), desc->diag_add);
+          out, a, b, warped ? mode : BASQ_PRED_COV, fx.as<double>(), fy.as<double>(), pre_add, desc->diag_add);
       ctx->launches++;
       BASQ_CUDA(cudaGetLastError());
     }
@@ -863,7 +974,7 @@ int basq::gram_matrix(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X
   } else if (desc->diag_add != 0.0) {
     const int64_t tot = a * b;
     warp_gram_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, ctx->stream>>>(out, a, b, BASQ_PLAIN, nullptr, nullptr,
-                                                                             desc->diag_add);
+                                                                             0.0, desc->diag_add);
     ctx->launches++;
     BASQ_CUDA(cudaGetLastError());
   }
@@ -910,7 +1021,9 @@ int basq_nystrom_basis(basq_ctx* ctx, const basq_kernel_desc* desc, const void* 
                        const double* Omega, int niter, double* U_out, double* S_out) {
   BASQ_CHECK(ctx && desc && Z && Omega && U_out, BASQ_ERR_INVALID, "basq_nystrom_basis: NULL argument");
   BASQ_CUDA(cudaSetDevice(ctx->device));
-  return nystrom_basis(ctx, desc, Z, M, q, Omega, niter, U_out, S_out);
+  const int rc = nystrom_basis(ctx, desc, Z, M, q, Omega, niter, U_out, S_out);
+  basq_ctx_trim(ctx, -1);
+  return rc;
 }
 
 int basq_features(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t N, const void* Z, int64_t M,
@@ -928,7 +1041,11 @@ int basq_features(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, in
     BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   BASQ_TRY(session_create_impl(ctx, desc, X, N, N, 0, Z, M, U, q, ones.as<double>(), 4, s.get()));
-  return session_features(s.get(), Phi_out);
+  const int rc = session_features(s.get(), Phi_out);
+  s.reset();
+  ones.release();
+  basq_ctx_trim(ctx, -1);
+  return rc;
 }
 
 int basq_car(basq_ctx* ctx, double* A, int n, int S, int lda, double* omega_out, int* n_kept_host) {
@@ -950,7 +1067,9 @@ int basq_recombine(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, i
                    const double* U, int q, const double* mu, int64_t* idx_out, double* w_out, int* n_out_host) {
   BASQ_CHECK(ctx, BASQ_ERR_INVALID, "ctx is NULL");
   BASQ_CUDA(cudaSetDevice(ctx->device));
-  return recombine_impl(ctx, desc, X, N, Z, M, U, q, mu, idx_out, w_out, n_out_host);
+  const int rc = recombine_impl(ctx, desc, X, N, Z, M, U, q, mu, idx_out, w_out, n_out_host);
+  basq_ctx_trim(ctx, -1);
+  return rc;
 }
 
 int basq_recombine_objective(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t N, const void* Z,
@@ -958,7 +1077,9 @@ int basq_recombine_objective(basq_ctx* ctx, const basq_kernel_desc* desc, const 
                              double* w_out, int* n_out_host) {
   BASQ_CHECK(ctx && obj, BASQ_ERR_INVALID, "basq_recombine_objective: NULL argument");
   BASQ_CUDA(cudaSetDevice(ctx->device));
-  return recombine_impl(ctx, desc, X, N, Z, M, U, q, mu, idx_out, w_out, n_out_host, obj);
+  const int rc = recombine_impl(ctx, desc, X, N, Z, M, U, q, mu, idx_out, w_out, n_out_host, obj);
+  basq_ctx_trim(ctx, -1);
+  return rc;
 }
 
 int basq_car_objective(basq_ctx* ctx, double* A, int n, int C, int lda, double* omega_out) {
@@ -976,10 +1097,10 @@ int basq_session_set_objective(basq_session* s, const double* obj) {
   return BASQ_OK;
 }
 
-int basq_recombine_host(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X_host, int64_t N,
-                        const void* Z_host, int64_t M, const double* U_host, int q, const double* Omega_host,
-                        int niter, const double* mu_host, int64_t* idx_out_host, double* w_out_host,
-                        int* n_out_host) {
+static int recombine_host_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X_host, int64_t N,
+                               const void* Z_host, int64_t M, const double* U_host, int q, const double* Omega_host,
+                               int niter, const double* mu_host, int64_t* idx_out_host, double* w_out_host,
+                               int* n_out_host) {
   BASQ_CHECK(ctx && desc && X_host && Z_host && idx_out_host && w_out_host && n_out_host, BASQ_ERR_INVALID,
              "basq_recombine_host: NULL argument");
   BASQ_CHECK(U_host || Omega_host, BASQ_ERR_INVALID, "basq_recombine_host: need U_host or Omega_host");
@@ -1061,6 +1182,16 @@ int basq_recombine_host(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
   return BASQ_OK;
 }
 
+int basq_recombine_host(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X_host, int64_t N,
+                        const void* Z_host, int64_t M, const double* U_host, int q, const double* Omega_host,
+                        int niter, const double* mu_host, int64_t* idx_out_host, double* w_out_host,
+                        int* n_out_host) {
+  const int rc = recombine_host_impl(ctx, desc, X_host, N, Z_host, M, U_host, q, Omega_host, niter, mu_host,
+                                     idx_out_host, w_out_host, n_out_host);
+  if (ctx) basq_ctx_trim(ctx, -1);
+  return rc;
+}
+
 int basq_session_create(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t N_loc, int64_t N_glob,
                         int64_t idx_base, const void* Z, int64_t M, const double* U, int q, const double* mu,
                         basq_session** out) {
@@ -1074,7 +1205,12 @@ int basq_session_create(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
   return BASQ_OK;
 }
 
-void basq_session_destroy(basq_session* s) { delete s; }
+void basq_session_destroy(basq_session* s) {
+  if (!s) return;
+  basq_ctx* ctx = s->ctx;
+  delete s;
+  if (ctx) basq_ctx_trim(ctx, -1);
+}
 
 int basq_session_count(const basq_session* s, int64_t* R_loc_host) {
   BASQ_CHECK(s && R_loc_host, BASQ_ERR_INVALID, "NULL argument");

@@ -59,22 +59,18 @@ __global__ void sample_mvn_kernel(MvnDev p, uint64_t seed, int64_t offset, int64
     philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)blk, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const T u0 = ((T)(r[2 * h] >> 8) + (T)0.5) * (T)5.9604644775390625e-08;      // 2^-24
-      const T u1 = ((T)(r[2 * h + 1] >> 8) + (T)0.5) * (T)5.9604644775390625e-08;
-      T s, c;
-      if (sizeof(T) == 4) {
-        float sf, cf;
-        sincospif(2.f * (float)u1, &sf, &cf);
-        s = sf; c = cf;
-      } else {
-        double sd, cd;
-        sincospi(2.0 * (double)u1, &sd, &cd);
-        s = sd; c = cd;
-      }
-      const T rad = sizeof(T) == 4 ? (T)sqrtf(-2.f * logf((float)u0)) : (T)sqrt(-2.0 * log((double)u0));
+      // Box-Muller in fp64 for both dtypes: (k + 0.5) 2^-24 is exact there and lies strictly inside
+      // (0, 1) (in fp32 half of the 24-bit draws would lose the + 0.5 to rounding and u could reach 1);
+      // the fp32 stream is the rounded fp64 stream.  5e7 double log / sincospi per 1e7 x 10 candidates
+      // are ~1 ms - the kernel stays bound by its N d stores.
+      const double u0 = ((double)(r[2 * h] >> 8) + 0.5) * 5.9604644775390625e-08;      // 2^-24
+      const double u1 = ((double)(r[2 * h + 1] >> 8) + 0.5) * 5.9604644775390625e-08;
+      double sd, cd;
+      sincospi(2.0 * u1, &sd, &cd);
+      const double rad = sqrt(-2.0 * log(u0));
       const int k = blk * 4 + 2 * h;
-      if (k < p.d) z[k] = rad * c;
-      if (k + 1 < p.d) z[k + 1] = rad * s;
+      if (k < p.d) z[k] = (T)(rad * cd);
+      if (k + 1 < p.d) z[k + 1] = (T)(rad * sd);
     }
   }
   // x = mean + L z
@@ -168,7 +164,9 @@ __global__ void scale_or_fill_kernel(double* __restrict__ w, int64_t N, const do
 // Sequential importance resampling without replacement (torch.multinomial(weights, n), as
 // UncertaintySampler.SIR, BASQ/_sampler.py:104-118) as an exponential race (Efraimidis-Spirakis):
 // key_i = -log(u_i) / w_i with u_i uniform; the n smallest keys, in increasing order, are distributed
-// like n successive draws proportional to the remaining weights.  u_i = Philox(seed; i), top 24 bits.
+// like n successive draws proportional to the remaining weights.  u_i = Philox(seed; i): a 53-bit
+// uniform from two output words ((r0 >> 5) 2^26 + (r1 >> 6) + 0.5) 2^-53, so that the keys of 1e7+
+// candidates are distinct and their gaps resolved (a 24-bit uniform has 1.6e7 values in all).
 // This kernel appends every (key, index) with key < cut to out (unordered; the host sorts the few
 // survivors) and counts them.
 __global__ void sir_keys_kernel(const double* __restrict__ w, int64_t N, uint64_t seed, double cut, int64_t cap,
@@ -181,7 +179,7 @@ __global__ void sir_keys_kernel(const double* __restrict__ w, int64_t N, uint64_
   uint32_t r[4];
   philox4x32_10((uint32_t)i, (uint32_t)((uint64_t)i >> 32), 0u, 0x53495200u /* "SIR" stream */, (uint32_t)seed,
                 (uint32_t)(seed >> 32), r);
-  const double u = ((double)(r[0] >> 8) + 0.5) * 5.9604644775390625e-08;
+  const double u = ((double)(r[0] >> 5) * 67108864.0 + (double)(r[1] >> 6) + 0.5) * 1.1102230246251565e-16;  // 2^-53
   const double key = -log(u) / wi;
   if (key < cut) {
     const unsigned long long slot = atomicAdd(count, 1ull);

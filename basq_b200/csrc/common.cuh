@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -50,6 +51,11 @@ enum Phase { PH_PREP = 0, PH_SETSUM = 1, PH_PROJ = 2, PH_CAR = 3, PH_APPLY = 4, 
 struct basq_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // Private stream-ordered pool: scratch freed by the library stays cached here (no driver calls in the
+  // pass loop) without touching the device's default pool, which other code in the process may share.
+  // basq_ctx_trim / the end of every top-level call release everything above pool_keep bytes.
+  cudaMemPool_t pool = nullptr;
+  uint64_t pool_keep = 0;
   int num_sms = 0;
   size_t smem_optin = 0;
   int64_t launches = 0;
@@ -59,6 +65,11 @@ struct basq_ctx {
   bool force_general_car = false;  // BASQ_CAR_GENERAL=1: always use the global-memory kernel (tests)
   bool scalar_setsum = false;      // BASQ_SETSUM_SCALAR=1: CUDA-core set-sum kernel for fp32 too (A/B timing)
   bool no_tensor_nystrom = false;  // BASQ_NYSTROM_FP64=1: fp64 GEMMs in the Nystrom iteration for fp32 kernels too (A/B)
+  // fp32 inputs are promoted to the fp64 path when max_m |(K_ZX W)_m|_1 exceeds kappa_max (api.cu:
+  // session_create_impl); BASQ_F32_KAPPA_MAX overrides, 0 disables
+  double kappa_max = 64.0;
+  double last_kappa = 0.0;
+  int64_t promotions = 0;
   bool trace = false;      // BASQ_TRACE=1: wall-clock trace points on stderr (synchronising)
   double trace_t0 = 0.0;
   double phase_ms[basq::PH_COUNT] = {0};
@@ -96,13 +107,22 @@ namespace basq {
 
 // RAII phase timer (only active when ctx->profile): records a start/stop event pair on the context's
 // stream without synchronising; basq_ctx_profile_read resolves them.  Nested timers are ignored.
+// Every outermost phase is also an NVTX range ("basq:<phase>", visible to Nsight Systems / ncu --nvtx).
+static inline const char* phase_name(int ph) {
+  static const char* const names[PH_COUNT] = {"basq:prepare", "basq:set_sum", "basq:projection", "basq:caratheodory",
+                                              "basq:apply", "basq:nystrom", "basq:gp_predict", "basq:other"};
+  return (ph >= 0 && ph < PH_COUNT) ? names[ph] : "basq:?";
+}
 struct PhaseTimer {
   basq_ctx* ctx;
   int phase;
   bool active;
+  bool outer;
   cudaEvent_t e0 = nullptr;
   PhaseTimer(basq_ctx* c, int ph) : ctx(c), phase(ph) {
-    active = (ctx->timer_depth++ == 0) && ctx->profile;
+    outer = (ctx->timer_depth++ == 0);
+    if (outer) nvtxRangePushA(phase_name(ph));
+    active = outer && ctx->profile;
     if (active) {
       e0 = ctx->take_event();
       cudaEventRecord(e0, ctx->stream);
@@ -110,6 +130,7 @@ struct PhaseTimer {
   }
   ~PhaseTimer() {
     ctx->timer_depth--;
+    if (outer) nvtxRangePop();
     if (active) {
       cudaEvent_t e1 = ctx->take_event();
       cudaEventRecord(e1, ctx->stream);
@@ -118,10 +139,10 @@ struct PhaseTimer {
   }
 };
 
-// Device buffer with RAII, carved from the device's stream-ordered memory pool on the context's
-// stream (cudaMallocAsync / cudaFreeAsync; the pool's release threshold is raised at context
-// creation, so in steady state neither call reaches the driver or synchronises the device - the
-// round loop allocates and frees scratch every round).  Everything the library launches runs on
+// Device buffer with RAII, carved from the context's private stream-ordered memory pool on the
+// context's stream (cudaMallocFromPoolAsync / cudaFreeAsync; the pool keeps freed blocks, so in
+// steady state neither call reaches the driver or synchronises the device - the round loop
+// allocates and frees scratch every round).  Everything the library launches runs on
 // that one stream, so a freed block may be handed to the next allocation without a fence.
 struct DevBuf {
   void* p = nullptr;
@@ -140,9 +161,9 @@ struct DevBuf {
     release();
     if (n == 0) n = 16;
     stream = ctx->stream;
-    cudaError_t e = cudaMallocAsync(&p, n, stream);
+    cudaError_t e = ctx->pool ? cudaMallocFromPoolAsync(&p, n, ctx->pool, stream) : cudaMallocAsync(&p, n, stream);
     if (e != cudaSuccess) {
-      set_error("cudaMallocAsync(%zu bytes) failed: %s", n, cudaGetErrorString(e));
+      set_error("stream-ordered allocation of %zu bytes failed: %s", n, cudaGetErrorString(e));
       p = nullptr;
       (void)cudaGetLastError();
       return BASQ_ERR_CUDA;

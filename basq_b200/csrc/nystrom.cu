@@ -514,7 +514,7 @@ int nystrom_basis(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, in
   // the captured trace tr(U K U^T) agrees to 9 digits with the fully re-orthonormalised run
   // (1530.730019 vs 1530.730022); at d = 2 (spread 1e-8) the skip would double the approximation
   // error, and the criterion keeps every orthonormalisation.  BASQ_NYS_ORTH_MID=1 forces them all.
-  static const bool force_mid = [] { const char* e = getenv("BASQ_NYS_ORTH_MID"); return e && e[0] == '1'; }();
+  const bool force_mid = [] { const char* e = getenv("BASQ_NYS_ORTH_MID"); return e && e[0] == '1'; }();  // read per call (tests toggle it)
   bool skip_mid = false;
   if (!force_mid && niter > 0) {
     diag_spread_kernel<<<1, 256, 0, ctx->stream>>>(ws.linv.as<double>(), q, q, ws.scal.as<double>());

@@ -81,8 +81,7 @@ def predict_mean(test_x, model):
 def predictive_covariance(x, y, model, add_noise_diag=False):
     """K_xy - K_xX W K_Xy - BASQ/_gp.py:259-277 (add_noise_diag=True adds its lik_var diagonal)."""
     spec = spec_from_model(model, _lib.PRED_COV)
-    if add_noise_diag:
-        spec.diag_add = spec.noise
+    spec.noise_diag = bool(add_noise_diag)
     return ops.gram(spec, x, y).to(x.dtype)
 
 

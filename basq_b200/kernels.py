@@ -44,7 +44,8 @@ class KernelSpec:
     outputscale: float
     noise: float = 0.0
     mean_const: float = 0.0
-    diag_add: float = 0.0           # BASQ/_gp.py:275-276 "+ lik_var" quirk / wsabi jitter (Gram only)
+    diag_add: float = 0.0           # wsabi / mmlt jitter: added to the Gram diagonal after the warping
+    noise_diag: bool = False        # BASQ/_gp.py:275-276 "+ lik_var" on the covariance diagonal, before warping
     Xobs: Optional[torch.Tensor] = None
     W: Optional[torch.Tensor] = None      # (K_XX + noise I)^-1
     alpha: Optional[torch.Tensor] = None  # mean cache
@@ -69,6 +70,7 @@ class KernelSpec:
         for i in range(d):
             desc.lengthscale[i] = float(ls[i])
         desc.noise, desc.mean_const, desc.diag_add = float(self.noise), float(self.mean_const), float(self.diag_add)
+        desc.noise_diag = 1 if self.noise_diag else 0
         keep = []
         if self.mode != _lib.PLAIN or self.Xobs is not None:
             if self.Xobs is None or self.W is None or self.alpha is None:
@@ -146,8 +148,7 @@ def describe_kernel(kernel) -> KernelSpec:
         if flag is None:
             flag = type(owner).__module__.split(".")[0] == "BASQ"
         spec = spec_from_model(owner.model, mode, offset=float(getattr(owner, "alpha", 0.0) or 0.0))
-        if flag:
-            diag += spec.noise
+        spec.noise_diag = bool(flag)
         if name in ("wsabil_kernel", "wsabim_kernel", "gspace_kernel"):
             diag += float(getattr(owner, "jitter", 0.0) or 0.0)
         spec.diag_add = diag

@@ -50,10 +50,11 @@ def gp_predict(kernel, X, space=0, want_var=True, device=None):
 
 
 def nystrom_basis(kernel, Z, q, omega=None, niter=2, device=None, want_S=True):
-    """(S, U): Ritz values and an orthonormal basis U [q, M] of the randomised range of K(Z, Z)
-    (ker_svd_sparsify, BASQ/_rchq.py:28-31).  omega [M, q] defaults to torch.randn on the device,
-    consuming torch's global RNG exactly where torch.svd_lowrank would.  want_S=False skips the
-    Ritz values (the reference discards them, BASQ/_rchq.py:36) and returns S = None."""
+    """(S, U): U [q, M] is an orthonormal basis of the randomised range of K(Z, Z) (ker_svd_sparsify,
+    BASQ/_rchq.py:28-31) - an arbitrary basis of that span, not the singular vectors (recombination
+    only depends on the span); S [q] holds the Rayleigh quotients u_i^T K u_i of its rows, unordered.
+    omega [M, q] defaults to torch.randn on the device, consuming torch's global RNG exactly where
+    torch.svd_lowrank would.  want_S=False skips S (the reference discards it, BASQ/_rchq.py:36)."""
     spec, ctx, device, dtype = _common(kernel, Z, device)
     Zd = _prep(Z, device, dtype)
     M = len(Zd)
@@ -155,8 +156,26 @@ def recombine_host(kernel, X_host, Z_host, q, U_host=None, omega_host=None, mu_h
     device = torch.device(device)
     ctx = _lib.context_for(device)
     dtype = X_host.dtype
-    assert X_host.device.type == "cpu" and Z_host.device.type == "cpu"
-    X_host, Z_host = X_host.contiguous(), Z_host.contiguous()
+    if dtype not in (torch.float32, torch.float64):
+        raise TypeError(f"recombine_host: candidates must be float32 or float64, not {dtype}")
+    if X_host.device.type != "cpu" or Z_host.device.type != "cpu":
+        raise ValueError("recombine_host takes HOST tensors (use recombine for device tensors)")
+    if X_host.dim() != 2 or Z_host.dim() != 2 or Z_host.shape[1] != X_host.shape[1]:
+        raise ValueError(f"recombine_host: X {tuple(X_host.shape)} and Z {tuple(Z_host.shape)} must be [N, d] and [M, d]")
+    # the C call copies raw bytes with the descriptor's element size: every buffer must have it
+    X_host, Z_host = X_host.contiguous(), Z_host.to(dtype).contiguous()
+    N, M = len(X_host), len(Z_host)
+    if U_host is None and omega_host is None:
+        raise ValueError("recombine_host needs U_host [q, M] or omega_host [M, q]")
+    if U_host is not None and tuple(U_host.shape) != (q, M):
+        raise ValueError(f"U_host has shape {tuple(U_host.shape)}, expected {(q, M)}")
+    if omega_host is not None and tuple(omega_host.shape) != (M, q):
+        raise ValueError(f"omega_host has shape {tuple(omega_host.shape)}, expected {(M, q)}")
+    if mu_host is not None and tuple(mu_host.shape) != (N,):
+        raise ValueError(f"mu_host has shape {tuple(mu_host.shape)}, expected {(N,)}")
+    for name, t in (("U_host", U_host), ("omega_host", omega_host), ("mu_host", mu_host)):
+        if t is not None and t.device.type != "cpu":
+            raise ValueError(f"{name} must be a host tensor")
     desc, keep = spec.to_desc(X_host.shape[1], device, dtype)
     idx = torch.empty(q + 1, dtype=torch.int64)
     w = torch.empty(q + 1, dtype=torch.float64)
@@ -294,3 +313,11 @@ class Session:
         k = C.c_int(0)
         _lib.check(_lib.lib.basq_session_result(self.handle, idx.data_ptr(), w.data_ptr(), self.n, C.byref(k)))
         return idx[: k.value], w[: k.value]
+
+
+def release_memory(device=None, keep_bytes: int = 0):
+    """Hand the scratch memory cached by the library's private CUDA pools back to the driver (all
+    contexts of `device`, or of every device)."""
+    for (index, _stream), ctx in list(_lib._contexts.items()):
+        if device is None or torch.device(device).index in (None, index):
+            ctx.trim(keep_bytes)

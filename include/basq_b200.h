@@ -62,10 +62,12 @@ typedef struct basq_kernel_desc {
   double lengthscale[BASQ_MAX_DIM];  /* per-dimension lengthscale (replicate a scalar) */
   double noise;                      /* likelihood.noise (sigma_n^2) */
   double mean_const;                 /* ConstantMean constant (0 for ZeroMean) */
-  double diag_add;                   /* added to the first min(a,b) diagonal entries by basq_gram
-                                        (BASQ/_gp.py:275-276 quirk / wsabi jitter); 0 = off */
+  double diag_add;                   /* jitter added to the first min(a,b) diagonal entries of basq_gram's
+                                        result AFTER the warping (BASQ/_wsabi.py:222-224); 0 = off */
   int32_t n_obs;                     /* GP observations; 0 for BASQ_PLAIN */
-  int32_t reserved;
+  int32_t noise_diag;                /* != 0: basq_gram adds `noise` to the first min(a,b) diagonal entries of
+                                        the posterior covariance BEFORE any warping - the "+ lik_var" of
+                                        BASQ/_gp.py:275-276 (SOBER/_gp.py:297-304 dropped it) */
   const void* Xobs;                  /* [n_obs, d] in dtype */
   const double* W;                   /* [n_obs, n_obs] (K_XX + sigma_n^2 I)^-1, fp64 (BASQ/_gp.py:233-256) */
   const double* alpha;               /* [n_obs] mean cache (K_XX + sigma_n^2 I)^-1 (y - c), fp64 */
@@ -77,6 +79,21 @@ const char* basq_last_error(void);
 /* stream: a cudaStream_t (0 = the legacy default stream). */
 int basq_ctx_create(int device, void* stream, basq_ctx** out);
 void basq_ctx_destroy(basq_ctx* ctx);
+/* Scratch memory: every ctx owns a private stream-ordered CUDA memory pool (the device's default pool
+   is never touched), which caches freed blocks so that the pass loop does not reach the driver.  Every
+   top-level call trims the pool back to the context's keep size before it returns (default 8 GiB,
+   environment BASQ_POOL_KEEP_MB); basq_ctx_trim(ctx, keep_bytes) does so on demand (keep_bytes < 0:
+   the context's keep size; 0: hand everything back, e.g. before another library needs the memory). */
+int basq_ctx_trim(basq_ctx* ctx, int64_t keep_bytes);
+/* Conditioning guard of the fp32 path.  A posterior-covariance kernel evaluates
+   C(z, x) = k(z, x) - (K_ZX W) k(Xobs, x): an evaluation error eps of the kernel values (fp32: ~2e-7
+   relative) reaches C as eps * |(K_ZX W)_m|_1 * outputscale.  kappa = max_m |(K_ZX W)_m|_1 is computed
+   when a session is created (basq_recombine*, basq_features, basq_session_create); fp32 inputs with
+   kappa > kappa_max (default 64, i.e. ~1e-5 of the outputscale; environment BASQ_F32_KAPPA_MAX; 0 = never)
+   are promoted to the all-fp64 path inside the call - the reference's default likelihood noise 1e-10
+   (BASQ/_parameters.py:30) makes such GPs easy to produce in low dimension.  kappa_max < 0 leaves the
+   threshold unchanged; the outputs (may be NULL) report the last kappa and the number of promotions. */
+int basq_ctx_conditioning(basq_ctx* ctx, double kappa_max, double* last_kappa_host, int64_t* promotions_host);
 /* number of kernels this library has launched on ctx so far (bench.py's gpu_launches) */
 int64_t basq_ctx_launch_count(const basq_ctx* ctx);
 /* kernel evaluations k(z, x) performed by the set-sum kernel on ctx so far (roofline accounting) */
@@ -101,8 +118,11 @@ int basq_gp_predict(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, 
 
 /* ---- Nystrom eigenbasis: ker_svd_sparsify, BASQ/_rchq.py:28-31 ------------------------------ */
 /* Randomised range finder (Halko alg. 4.4, niter subspace iterations, as torch.svd_lowrank) on
-   K(Z,Z) with the caller's Gaussian test matrix Omega[M,q] (fp64), followed by a Rayleigh-Ritz
-   rotation.  U_out[q,M] has orthonormal rows; S_out[q] (may be NULL) the Ritz values, descending. */
+   K(Z,Z) with the caller's Gaussian test matrix Omega[M,q] (fp64).  U_out[q,M] has orthonormal rows
+   spanning the captured range - an arbitrary orthonormal basis of it, NOT the singular vectors: no
+   final rotation is applied, because recombination only depends on span(U) (the reference discards
+   the singular values, BASQ/_rchq.py:36).  S_out[q] (may be NULL) receives the Rayleigh quotients
+   u_i^T K u_i of the rows, unordered; do not truncate U by them. */
 int basq_nystrom_basis(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, int64_t M,
                        int q, const double* Omega, int niter, double* U_out, double* S_out);
 

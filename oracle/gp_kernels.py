@@ -35,7 +35,7 @@ def base_kernel(x, y, family, lengthscale, outputscale, nu=2.5):
              nu=1.5: 1 + sqrt3 r ; nu=2.5: 1 + sqrt5 r + 5/3 r^2
     ``lengthscale`` is a scalar or a length-d vector (ARD).
     """
-    ls = torch.as_tensor(lengthscale, dtype=x.dtype).reshape(1, -1)
+    ls = torch.as_tensor(lengthscale, dtype=x.dtype, device=x.device).reshape(1, -1)
     r2 = _sq_dist(x / ls, y / ls)
     if family == "rbf":
         return outputscale * torch.exp(-0.5 * r2)
@@ -80,7 +80,7 @@ class ScaleKernel:
     def forward(self, x, y):
         fam = "rbf" if isinstance(self.base_kernel, RBFKernel) else "matern"
         return base_kernel(
-            x, y, fam, self.base_kernel.lengthscale.to(x.dtype).reshape(-1),
+            x, y, fam, self.base_kernel.lengthscale.to(x).reshape(-1),
             float(self.outputscale), nu=getattr(self.base_kernel, "nu", 2.5),
         )
 
@@ -110,6 +110,14 @@ class ExactGP:
         )
 
     def eval(self):
+        return self
+
+    def to(self, device):
+        """Move the observations and caches (used by bench.py's torch-on-GPU baseline leg)."""
+        self.train_inputs = (self.train_inputs[0].to(device),)
+        self.train_targets = self.train_targets.to(device)
+        ps = self.prediction_strategy
+        ps.covar_cache, ps.mean_cache = ps.covar_cache.to(device), ps.mean_cache.to(device)
         return self
 
 
@@ -144,7 +152,7 @@ def predictive_covariance(x, y, model, add_noise_diag=False):
     cov = Kxy - KxX @ W @ KXy
     if add_noise_diag:
         k = min(len(x), len(y))
-        ii = torch.arange(k)
+        ii = torch.arange(k, device=cov.device)
         cov[ii, ii] = cov[ii, ii] + float(noise)
     return cov.to(dt)
 

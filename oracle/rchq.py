@@ -1,4 +1,5 @@
-"""Oracle restatement (torch CPU) of the reference's kernel recombination, ``BASQ/_rchq.py``.
+"""Oracle restatement (plain torch ops; CPU, or the inputs' device) of the reference's kernel
+recombination, ``BASQ/_rchq.py``.
 
 TEST INFRASTRUCTURE - see ``oracle/__init__.py``.  PINNED: checked against outputs of the
 reference's own ``BASQ/_rchq.py`` (imported from the read-only reference tree by
@@ -20,12 +21,12 @@ def caratheodory(X, mu):
     ratio-test eliminations (:146-171).
     """
     S = X.shape[0]
-    A = torch.cat([torch.ones(S, 1, dtype=X.dtype), X], dim=1)
+    A = torch.cat([torch.ones(S, 1, dtype=X.dtype, device=X.device), X], dim=1)
     n = A.shape[1]
     _, _, Vh = torch.linalg.svd(A.T)
     Phi = Vh[n:, :].T.contiguous()
     mu = mu.clone()
-    inf = torch.tensor(float("inf"), dtype=X.dtype)
+    inf = torch.tensor(float("inf"), dtype=X.dtype, device=X.device)
     for _ in range(S - n):
         phi = Phi[:, 0]
         pos = phi > 0
@@ -56,9 +57,9 @@ def tchernychova_lyons(samp, U, pt_nys, kernel, mu=None, chunk=1):
     N = len(samp)
     q, M = U.shape
     S = 2 * (q + 1)
-    dt = U.dtype
-    mu = torch.full((N,), 1.0 / N, dtype=dt) if mu is None else mu.to(dt).clone()
-    alive = torch.arange(N)[mu != 0]
+    dt, dev = U.dtype, samp.device
+    mu = torch.full((N,), 1.0 / N, dtype=dt, device=dev) if mu is None else mu.to(dt).clone()
+    alive = torch.arange(N, device=dev)[mu != 0]
 
     while True:
         R = len(alive)
@@ -76,7 +77,7 @@ def tchernychova_lyons(samp, U, pt_nys, kernel, mu=None, chunk=1):
         E = R // S                                                  # :76-78
         body = alive[: E * S].reshape(E, S)
         tail = alive[E * S:]
-        G = torch.zeros(M, S, dtype=dt)
+        G = torch.zeros(M, S, dtype=dt, device=dev)
         for e0 in range(0, E, chunk):                               # :81-86
             e1 = min(E, e0 + chunk)
             ids = body[e0:e1].reshape(-1)
@@ -90,7 +91,7 @@ def tchernychova_lyons(samp, U, pt_nys, kernel, mu=None, chunk=1):
         bary = bary / mass.unsqueeze(1)                             # :101
 
         w, keep = caratheodory(bary, mass.clone())                  # :103-105
-        scale = torch.zeros(S, dtype=dt)
+        scale = torch.zeros(S, dtype=dt, device=dev)
         scale[keep] = w / mass[keep]
         mu[body.reshape(-1)] = (mu[body] * scale.unsqueeze(0)).reshape(-1)   # :107-115
         last_kept = bool(scale[-1] > 0)

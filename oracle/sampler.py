@@ -114,7 +114,8 @@ def sir_indices(weights, n_return, seed=0):
     key[:, 0] = np.uint32(seed & 0xFFFFFFFF)
     key[:, 1] = np.uint32((seed >> 32) & 0xFFFFFFFF)
     r = philox4x32_10(ctr, key)
-    u = ((r[:, 0] >> np.uint32(8)).astype(np.float64) + 0.5) * 2.0 ** -24
+    u = ((r[:, 0] >> np.uint32(5)).astype(np.float64) * 2.0 ** 26
+         + (r[:, 1] >> np.uint32(6)).astype(np.float64) + 0.5) * 2.0 ** -53      # 53-bit uniform in (0, 1)
     with np.errstate(divide="ignore"):
         keys = np.where(w > 0, -np.log(u) / np.where(w > 0, w, 1.0), np.inf)
     order = np.lexsort((np.arange(N), keys))

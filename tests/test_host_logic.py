@@ -37,8 +37,12 @@ def test_describe_reference_kernel_objects():
             W, Xobs, _ = ogp.get_cov_cache(m)
             assert torch.allclose(spec.W, W) and spec.Xobs is Xobs
     assert kernels.describe_kernel(ogp.WsabiGP(m, alpha=0.2).wsabil_kernel).offset == 0.2
-    assert kernels.describe_kernel(ogp.VanillaGP(m, add_noise_diag=True).predictive_kernel).diag_add == pytest.approx(1e-4)
-    assert kernels.describe_kernel(ogp.VanillaGP(m).predictive_kernel).diag_add == 0.0
+    quirk = kernels.describe_kernel(ogp.VanillaGP(m, add_noise_diag=True).predictive_kernel)
+    assert quirk.noise_diag and quirk.diag_add == 0.0 and quirk.noise == pytest.approx(1e-4)
+    assert not kernels.describe_kernel(ogp.VanillaGP(m).predictive_kernel).noise_diag
+    # the noise enters the covariance before the warping, the jitter after it (BASQ/_wsabi.py:216-224)
+    wm = kernels.describe_kernel(ogp.WsabiGP(m, jitter=1e-3, add_noise_diag=True).wsabim_kernel)
+    assert wm.noise_diag and wm.diag_add == pytest.approx(1e-3)
     mat = _model(family="matern")
     assert kernels.describe_kernel(mat.covar_module.forward).family == _lib.MATERN25
 
@@ -160,3 +164,31 @@ def test_bench_reference_arm_contract():
         assert key in line, key
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+    # same `config` keys as our arm (the driver compares them), the bounded sample is named beside the number
+    assert set(line["config"]) == {"workload", "N_total", "parallelism", "l2_policy"}
+    assert "N=2000" in line["cpu_baseline"]["sample"] and line["cpu_baseline"]["cores"] >= 1
+    ex = line["extrapolation"]
+    assert ex["N_full"] == 10_000_000 and ex["n_large"] == 2000 and ex["seconds_full"] > 0
+
+
+def test_bench_reference_arm_uses_all_threads_under_torchrun_env():
+    """torch.distributed.run exports OMP_NUM_THREADS=1; the CPU arm must still use every host core, and
+    ranks other than 0 exit without work."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    args = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "20",
+            "--warmup", "0", "--cpu-sample", "2000", "--M", "200", "--n", "40", "--n-obs", "22", "--cpu-budget", "5"]
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    out = subprocess.run(args, capture_output=True, text=True, timeout=300, cwd=root, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    cores = len(os.sched_getaffinity(0))
+    assert line["cpu_baseline"]["cores"] == cores and line["n_gpus"] == 2
+    assert line["config"]["parallelism"] == "dp2" and 1 <= line["steps"] <= 20
+    assert "N=2000" in line["cpu_baseline"]["sample"]          # the sample is never shrunk by --steps
+    env["RANK"] = "1"
+    out = subprocess.run(args, capture_output=True, text=True, timeout=300, cwd=root, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
