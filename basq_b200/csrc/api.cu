@@ -156,6 +156,8 @@ struct basq_session {
   // fp32 inputs whose posterior correction would amplify the fp32 kernel noise beyond tolerance are
   // promoted to the all-fp64 path (session_create_impl): fp64 copies of the inputs live here
   DevBuf X64, Z64, Xobs64;
+  NlOperands nlop;  // tensor-core path of the non-linear modes (fp32 records)
+  bool use_nls = false;
   bool promoted = false;
   double kappa = 0.0;
   int64_t idx_base = 0;
@@ -187,6 +189,8 @@ int session_set_sums(basq_session* s, int64_t off, int S, int64_t p_lo, int64_t 
     a.accumulate = false;
     return set_sums(ctx, s->kp, a);
   }
+  if (s->use_nls)
+    return nls_set_sums(ctx, s->kp, s->nl, &s->nlop, s->pool, s->lm.view(), s->lmobs.view(), off, S, p_lo, p_hi, G, ldg);
   // non-linear kernels need C_h(z_m, x_p) = k(z_m, x_p) - (K_ZX W) k(Xobs, x_p) per pair: build the
   // correction for a chunk of points with two GEMM-shaped steps, then accumulate.
   const int n_obs = s->desc.n_obs;
@@ -321,7 +325,13 @@ int session_create_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
                          !nonlin, &s->pool));
 
   s->ldg = 0;  // G and the rank table are sized by the first pass (session_reserve_cells)
-  if (nonlin) {
+  { const char* t = getenv("BASQ_NLSUM"); ctx->no_nlsum = t && t[0] == '0'; }  // read per session (A/B tests toggle it)
+  s->use_nls = nonlin && desc->dtype == BASQ_F32 && !ctx->no_nlsum;
+  if (s->use_nls) {
+    // fp32 records: the pairwise correction runs on the tensor cores (nlsum.cuh)
+    BASQ_TRY(nls_prepare(ctx, s->kp, s->Az.as<double>(), (int)M, n_obs, s->sz.as<double>(), &s->nlop));
+    s->Az.release();
+  } else if (nonlin) {
     // points per chunk of the pairwise correction: corrT [P, M] may take up to 2 GB, so that a chunk
     // spans many cells of a refined pass (every chunk re-reads the G columns it touches)
     int64_t P = (int64_t)(2048ll << 20) / (8ll * std::max<int64_t>(M, n_obs));
@@ -814,7 +824,7 @@ int basq_ctx_create(int device, void* stream, basq_ctx** out) {
     }
     uint64_t hold = UINT64_MAX;  // inside a call nothing goes back to the driver
     cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &hold);
-    c->pool_keep = 8ull << 30;
+    c->pool_keep = 24ull << 30;
     if (const char* t = getenv("BASQ_POOL_KEEP_MB")) c->pool_keep = (uint64_t)strtoull(t, nullptr, 10) << 20;
   }
   { const char* t = getenv("BASQ_TRACE"); c->trace = t && t[0] == '1'; }

@@ -18,8 +18,10 @@ import sys
 
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "basq_b200")
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "_build")
-LIB = os.path.join(HERE, "libbasq_b200.so")
+# BASQ_BUILD_LIB / BASQ_BUILD_OBJ: build a development copy elsewhere (load it with BASQ_B200_LIB) while
+# the in-tree library stays untouched, e.g. while a GPU run that snapshots the tree is queued
+OBJ = os.environ.get("BASQ_BUILD_OBJ") or os.path.join(HERE, "_build")
+LIB = os.environ.get("BASQ_BUILD_LIB") or os.path.join(HERE, "libbasq_b200.so")
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -66,10 +68,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-ldl"]
+    tmp = LIB + ".tmp"
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs, "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)   # atomic: a snapshot of the tree never sees a half-written library
     with open(stamp, "w") as f:
         f.write(dig)
     return LIB

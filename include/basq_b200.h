@@ -81,7 +81,8 @@ int basq_ctx_create(int device, void* stream, basq_ctx** out);
 void basq_ctx_destroy(basq_ctx* ctx);
 /* Scratch memory: every ctx owns a private stream-ordered CUDA memory pool (the device's default pool
    is never touched), which caches freed blocks so that the pass loop does not reach the driver.  Every
-   top-level call trims the pool back to the context's keep size before it returns (default 8 GiB,
+   top-level call trims the pool back to the context's keep size before it returns (default 24 GiB -
+   the working set of a 1e7-candidate call stays cached, re-growing the pool costs ~100 ms -,
    environment BASQ_POOL_KEEP_MB); basq_ctx_trim(ctx, keep_bytes) does so on demand (keep_bytes < 0:
    the context's keep size; 0: hand everything back, e.g. before another library needs the memory). */
 int basq_ctx_trim(basq_ctx* ctx, int64_t keep_bytes);
