@@ -65,6 +65,7 @@ struct basq_ctx {
   bool force_general_car = false;  // BASQ_CAR_GENERAL=1: always use the global-memory kernel (tests)
   bool scalar_setsum = false;      // BASQ_SETSUM_SCALAR=1: CUDA-core set-sum kernel for fp32 too (A/B timing)
   bool no_tensor_nystrom = false;  // BASQ_NYSTROM_FP64=1: fp64 GEMMs in the Nystrom iteration for fp32 kernels too (A/B)
+  bool no_gpvar = false;           // BASQ_GPVAR=0: chunked fp64-GEMM posterior variance for fp32 inputs too (A/B)
   bool no_nlsum = false;           // BASQ_NLSUM=0: chunked fp64-GEMM path for the non-linear modes in fp32 too (A/B)
   // fp32 inputs are promoted to the fp64 path when max_m |(K_ZX W)_m|_1 exceeds kappa_max (api.cu:
   // session_create_impl); BASQ_F32_KAPPA_MAX overrides, 0 disables
@@ -418,6 +419,10 @@ int nls_prepare(basq_ctx* ctx, const KParams& kp, const double* Az, int M, int n
                 NlOperands* op);
 int nls_set_sums(basq_ctx* ctx, const KParams& kp, int nl, NlOperands* op, const RecPool& pool, const LmView& lmz,
                  const LmView& lmobs, int64_t off, int S, int64_t p_lo, int64_t p_hi, double* G, int64_t ldg);
+
+// gpvar.cu: fused posterior variance on the tensor cores (fp32 inputs)
+int gp_variance_tc(basq_ctx* ctx, const basq_kernel_desc* desc, const KParams& kp, const LmView& lmobs, const void* X,
+                   int64_t N, double* var_out);
 
 // dgemm.cu
 int dgemm(basq_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const double* A, int64_t lda,

@@ -259,6 +259,8 @@ int gp_predict_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const KParams& 
   PhaseTimer timer(ctx, PH_GP);
   if (mean_out) BASQ_TRY(landmark_dot(ctx, kp, lmobs, desc->alpha, desc->mean_const, X, N, mean_out));
   if (!var_out || N == 0) return BASQ_OK;
+  { const char* t = getenv("BASQ_GPVAR"); ctx->no_gpvar = t && t[0] == '0'; }
+  if (desc->dtype == BASQ_F32 && !ctx->no_gpvar) return gp_variance_tc(ctx, desc, kp, lmobs, X, N, var_out);
   const int n_obs = desc->n_obs;
   // chunk so that V and Y (n_obs x P fp64 each) stay around 512 MB (large GEMMs: fewer, fuller waves)
   int64_t P = (int64_t)(512ll << 20) / (8ll * n_obs);

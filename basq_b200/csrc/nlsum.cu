@@ -11,58 +11,6 @@ namespace basq {
 
 namespace {
 
-// one block per landmark row: r_m = 2^(13 - floor(log2 max_o |Az[m, o]|)), so that the scaled row lies in
-// [2^13, 2^14); ainv[m] = 1 / (r_m * kx_scale) (a power of two, exact).  Rows beyond M get 0.
-__global__ void az_rowscale_kernel(const double* __restrict__ Az, int M, int n_obs, float kx_scale, int rows_pad,
-                                   float* __restrict__ rscale, float* __restrict__ ainv) {
-  __shared__ double sh[256];
-  const int m = blockIdx.x;
-  double mx = 0.0;
-  if (m < M)
-    for (int o = threadIdx.x; o < n_obs; o += blockDim.x) mx = fmax(mx, fabs(Az[(int64_t)m * n_obs + o]));
-  sh[threadIdx.x] = mx;
-  __syncthreads();
-  for (int w = 128; w > 0; w >>= 1) {
-    if ((int)threadIdx.x < w) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + w]);
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    float r = 0.f, inv = 0.f;
-    if (m < M) {
-      int e = 0;
-      if (sh[0] > 0.0 && isfinite(sh[0])) e = 13 - ilogb(sh[0]);
-      e = max(-40, min(40, e));  // a row this small contributes nothing; keep every factor a normal float
-      r = ldexpf(1.f, e);
-      inv = 1.f / (r * kx_scale);
-    }
-    rscale[m] = r;
-    ainv[m] = inv;
-  }
-}
-
-// one thread per (landmark tile, K chunk of 8, row): 8 scaled values -> fp16 hi / lo, 16-byte stores
-__global__ void az_split_kernel(const double* __restrict__ Az, int M, int n_obs, int KP, int n_mtiles,
-                                const float* __restrict__ rscale, __half* __restrict__ azh, __half* __restrict__ azl) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int KC = KP / 8;
-  if (t >= (int64_t)n_mtiles * KC * 128) return;
-  const int r = (int)(t % 128);
-  const int kc = (int)((t / 128) % KC);
-  const int mt = (int)(t / (128 * (int64_t)KC));
-  const int m = mt * 128 + r;
-  __half h[8], l[8];
-  const double rs = m < M ? (double)rscale[m] : 0.0;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int o = kc * 8 + e;
-    const double x = (m < M && o < n_obs) ? Az[(int64_t)m * n_obs + o] * rs : 0.0;
-    h[e] = __double2half(x);
-    l[e] = __double2half(x - (double)__half2float(h[e]));   // residual against the fp64 value: ~22 bits in hi + lo
-  }
-  reinterpret_cast<uint4*>(azh)[t] = *reinterpret_cast<const uint4*>(h);
-  reinterpret_cast<uint4*>(azl)[t] = *reinterpret_cast<const uint4*>(l);
-}
-
 __global__ void d2f_kernel(const double* __restrict__ in, int n, float* __restrict__ out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) out[t] = (float)in[t];
@@ -101,12 +49,12 @@ int nls_prepare(basq_ctx* ctx, const KParams& kp, const double* Az, int M, int n
   BASQ_TRY(op->szf.alloc(ctx, sizeof(float) * M));
   DevBuf rscale;
   BASQ_TRY(rscale.alloc(ctx, sizeof(float) * op->n_mtiles * 128));
-  az_rowscale_kernel<<<op->n_mtiles * 128, 256, 0, ctx->stream>>>(Az, M, n_obs, op->kx_scale, op->n_mtiles * 128,
-                                                                  rscale.as<float>(), op->ainv.as<float>());
+  rowscale16_kernel<256><<<op->n_mtiles * 128, 256, 0, ctx->stream>>>(Az, M, n_obs, n_obs, op->kx_scale,
+                                                                      rscale.as<float>(), op->ainv.as<float>());
   const int64_t tot = (int64_t)op->n_mtiles * (op->KP / 8) * 128;
-  az_split_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, ctx->stream>>>(Az, M, n_obs, op->KP, op->n_mtiles,
-                                                                          rscale.as<float>(), op->azh.as<__half>(),
-                                                                          op->azl.as<__half>());
+  split16_kernel<128><<<(unsigned)ceil_div64(tot, 256), 256, 0, ctx->stream>>>(Az, M, n_obs, n_obs, op->KP, op->n_mtiles,
+                                                                              rscale.as<float>(), op->azh.as<__half>(),
+                                                                              op->azl.as<__half>());
   d2f_kernel<<<ceil_div(M, 256), 256, 0, ctx->stream>>>(sz, M, op->szf.as<float>());
   ctx->launches += 3;
   BASQ_CUDA(cudaGetLastError());

@@ -459,6 +459,64 @@ __global__ void __launch_bounds__(NLS_NT) kxgen_kernel(const KxDev a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp64 matrix -> row-scaled fp16 hi / lo operand tiles (Az here, T = tril(W + W^T) in gpvar.cuh)
+// ---------------------------------------------------------------------------------------------
+// one block per row: r = 2^(13 - floor(log2 max_o |A[m, o]|)), so that the scaled row lies in [2^13, 2^14);
+// inv[m] = 1 / (r * kx_scale) (a power of two, exact).  Rows beyond `rows` get 0.
+template <int THREADS>
+__global__ void rowscale16_kernel(const double* __restrict__ A, int rows, int cols, int64_t lda, float kx_scale,
+                                  float* __restrict__ rscale, float* __restrict__ inv) {
+  __shared__ double sh[THREADS];
+  const int m = blockIdx.x;
+  double mx = 0.0;
+  if (m < rows)
+    for (int o = threadIdx.x; o < cols; o += THREADS) mx = fmax(mx, fabs(A[(int64_t)m * lda + o]));
+  sh[threadIdx.x] = mx;
+  __syncthreads();
+  for (int w = THREADS / 2; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + w]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float r = 0.f, iv = 0.f;
+    if (m < rows) {
+      int e = 0;
+      if (sh[0] > 0.0 && isfinite(sh[0])) e = 13 - ilogb(sh[0]);
+      e = max(-40, min(40, e));  // a row this small contributes nothing; keep every factor a normal float
+      r = ldexpf(1.f, e);
+      iv = 1.f / (r * kx_scale);
+    }
+    rscale[m] = r;
+    inv[m] = iv;
+  }
+}
+
+// one thread per (row tile, K chunk of 8, row): 8 scaled values -> fp16 hi / lo, 16-byte stores into
+// [tile][KP / 8][TILE_ROWS][8 halves]
+template <int TILE_ROWS>
+__global__ void split16_kernel(const double* __restrict__ A, int rows, int cols, int64_t lda, int KP, int n_tiles,
+                               const float* __restrict__ rscale, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int KC = KP / 8;
+  if (t >= (int64_t)n_tiles * KC * TILE_ROWS) return;
+  const int r = (int)(t % TILE_ROWS);
+  const int kc = (int)((t / TILE_ROWS) % KC);
+  const int mt = (int)(t / (TILE_ROWS * (int64_t)KC));
+  const int m = mt * TILE_ROWS + r;
+  __half h[8], l[8];
+  const double rs = m < rows ? (double)rscale[m] : 0.0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int o = kc * 8 + e;
+    const double x = (m < rows && o < cols) ? A[(int64_t)m * lda + o] * rs : 0.0;
+    h[e] = __double2half(x);
+    l[e] = __double2half(x - (double)__half2float(h[e]));   // residual against the fp64 value: ~22 bits in hi + lo
+  }
+  reinterpret_cast<uint4*>(hi)[t] = *reinterpret_cast<const uint4*>(h);
+  reinterpret_cast<uint4*>(lo)[t] = *reinterpret_cast<const uint4*>(l);
+}
+
 // launchers, one translation unit per (family, non-linearity): nlsum_inst_*.cu
 template <int FAM, int DP, int NL>
 int launch_nlsum_dp(basq_ctx* ctx, const NlsDev& dev, int mode) {
