@@ -1,5 +1,5 @@
-// Host side of the fused posterior-variance kernel (gpvar.cuh): T = tril(W + W^T) as row-scaled fp16
-// hi / lo tiles, the observation pack, chunking over the candidates.
+// Host side of the fused posterior-variance kernel (gpvar.cuh): L^-1 recovered from W as row-scaled fp16
+// hi / lo tiles, chunking over the candidates.
 #include <math.h>
 
 #include <algorithm>
@@ -8,48 +8,16 @@
 
 namespace basq {
 
-namespace {
+// nystrom.cu
+int spd_inverse_factor(basq_ctx* ctx, const double* A, int n, double* Linv_out);
 
-// T[i, j] = 2 W[i, j] (j < i), W[i, i] (j == i), 0 (j > i):  v^T W v = sum_i v_i (T v)_i for symmetric W
-__global__ void tri_fold16_kernel(const double* __restrict__ W, int n, double* __restrict__ T) {
+namespace {
+__global__ void zero_upper_kernel(double* __restrict__ A, int n) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (int64_t)n * n) return;
-  const int i = (int)(t / n), j = (int)(t % n);
-  T[t] = j < i ? W[t] + W[(int64_t)j * n + i] : (j == i ? W[t] : 0.0);
+  if ((int)(t % n) > (int)(t / n)) A[t] = 0.0;
 }
-
-template <int DP>
-int obspack_dp(basq_ctx* ctx, const float* ozz, const float* obz, const float* tinv, int n_obs, int KP,
-               unsigned char* pack) {
-  obspack_kernel<DP><<<ceil_div(KP, 128), 128, 0, ctx->stream>>>(ozz, obz, tinv, n_obs, KP, pack);
-  ctx->launches++;
-  BASQ_CUDA(cudaGetLastError());
-  return BASQ_OK;
-}
-
-int obr_of(int dp) { return ((dp + 2) * 4 + 15) / 16 * 16; }
-int ppf_of(int dp) { return (dp + 1 + 3) / 4 * 4; }
-
 }  // namespace
-
-int launch_obspack(basq_ctx* ctx, int dp, const float* ozz, const float* obz, const float* tinv, int n_obs, int KP,
-                   unsigned char* pack, int* obr_out) {
-  if (obr_out) *obr_out = obr_of(dp);
-  switch (dp) {
-    case 2: return obspack_dp<2>(ctx, ozz, obz, tinv, n_obs, KP, pack);
-    case 4: return obspack_dp<4>(ctx, ozz, obz, tinv, n_obs, KP, pack);
-    case 6: return obspack_dp<6>(ctx, ozz, obz, tinv, n_obs, KP, pack);
-    case 8: return obspack_dp<8>(ctx, ozz, obz, tinv, n_obs, KP, pack);
-    case 10: return obspack_dp<10>(ctx, ozz, obz, tinv, n_obs, KP, pack);
-    case 12: return obspack_dp<12>(ctx, ozz, obz, tinv, n_obs, KP, pack);
-    case 16: return obspack_dp<16>(ctx, ozz, obz, tinv, n_obs, KP, pack);
-    case 20: return obspack_dp<20>(ctx, ozz, obz, tinv, n_obs, KP, pack);
-    case 24: return obspack_dp<24>(ctx, ozz, obz, tinv, n_obs, KP, pack);
-    case 32: return obspack_dp<32>(ctx, ozz, obz, tinv, n_obs, KP, pack);
-  }
-  set_error("gpvar: no kernel compiled for padded dimension %d", dp);
-  return BASQ_ERR_UNSUPPORTED;
-}
 
 // var_out[N] = sigma_f^2 + sigma_n^2 - k_x^T W k_x for fp32 candidates X [N, d]
 int gp_variance_tc(basq_ctx* ctx, const basq_kernel_desc* desc, const KParams& kp, const LmView& lmobs, const void* X,
@@ -57,27 +25,36 @@ int gp_variance_tc(basq_ctx* ctx, const basq_kernel_desc* desc, const KParams& k
   BASQ_CHECK(desc->dtype == BASQ_F32 && lmobs.dtype == BASQ_F32, BASQ_ERR_INVALID, "gpvar: fp32 inputs only");
   const int n_obs = desc->n_obs;
   const int KP = ceil_div(n_obs, GPV_NT) * GPV_NT;
+  BASQ_CHECK(KP <= GpvCfg::MAX_KP, BASQ_ERR_UNSUPPORTED, "gpvar: more than %d observations", GpvCfg::MAX_KP);
   const int n_ct = KP / GPV_NT;
   const float kx_scale = ldexpf(1.f, NLS_KX_SHIFT - (int)ceil(log2(kp.outputscale)));
-  DevBuf T, rscale, tinv, th, tl, pack;
-  BASQ_TRY(T.alloc(ctx, sizeof(double) * (size_t)n_obs * n_obs));
+  // W = C C^T -> C^-1 ; K = W^-1 = C^-T C^-1 = L L^T -> L^-1 : W = L^-T L^-1, k^T W k = |L^-1 k|^2
+  DevBuf Cinv, Kmat, Linv;
+  BASQ_TRY(Cinv.alloc(ctx, sizeof(double) * (size_t)n_obs * n_obs));
+  BASQ_TRY(Kmat.alloc(ctx, sizeof(double) * (size_t)n_obs * n_obs));
+  BASQ_TRY(Linv.alloc(ctx, sizeof(double) * (size_t)n_obs * n_obs));
+  BASQ_TRY(spd_inverse_factor(ctx, desc->W, n_obs, Cinv.as<double>()));
+  const unsigned nn_grid = (unsigned)ceil_div64((int64_t)n_obs * n_obs, 256);
+  zero_upper_kernel<<<nn_grid, 256, 0, ctx->stream>>>(Cinv.as<double>(), n_obs);
+  ctx->launches++;
+  BASQ_TRY(dgemm(ctx, true, false, n_obs, n_obs, n_obs, 1.0, Cinv.as<double>(), n_obs, Cinv.as<double>(), n_obs, 0.0,
+                 Kmat.as<double>(), n_obs));
+  BASQ_TRY(spd_inverse_factor(ctx, Kmat.as<double>(), n_obs, Linv.as<double>()));
+  zero_upper_kernel<<<nn_grid, 256, 0, ctx->stream>>>(Linv.as<double>(), n_obs);
+  ctx->launches++;
+  DevBuf rscale, tinv, th, tl;
   BASQ_TRY(rscale.alloc(ctx, sizeof(float) * KP));
   BASQ_TRY(tinv.alloc(ctx, sizeof(float) * KP));
   const size_t t_halves = (size_t)n_ct * (KP / 8) * GPV_NT * 8;
   BASQ_TRY(th.alloc(ctx, t_halves * 2));
   BASQ_TRY(tl.alloc(ctx, t_halves * 2));
-  BASQ_TRY(pack.alloc(ctx, (size_t)KP * obr_of(kp.dp)));
-  tri_fold16_kernel<<<(unsigned)ceil_div64((int64_t)n_obs * n_obs, 256), 256, 0, ctx->stream>>>(desc->W, n_obs,
-                                                                                              T.as<double>());
-  rowscale16_kernel<256><<<KP, 256, 0, ctx->stream>>>(T.as<double>(), n_obs, n_obs, n_obs, kx_scale, rscale.as<float>(),
+  rowscale16_kernel<256><<<KP, 256, 0, ctx->stream>>>(Linv.as<double>(), n_obs, n_obs, n_obs, kx_scale, rscale.as<float>(),
                                                       tinv.as<float>());
   const int64_t tot = (int64_t)n_ct * (KP / 8) * GPV_NT;
   split16_kernel<GPV_NT><<<(unsigned)ceil_div64(tot, 256), 256, 0, ctx->stream>>>(
-      T.as<double>(), n_obs, n_obs, n_obs, KP, n_ct, rscale.as<float>(), th.as<__half>(), tl.as<__half>());
-  ctx->launches += 3;
+      Linv.as<double>(), n_obs, n_obs, n_obs, KP, n_ct, rscale.as<float>(), th.as<__half>(), tl.as<__half>());
+  ctx->launches += 2;
   BASQ_CUDA(cudaGetLastError());
-  BASQ_TRY(launch_obspack(ctx, kp.dp, reinterpret_cast<const float*>(lmobs.zz), lmobs.b, tinv.as<float>(), n_obs, KP,
-                          pack.as<unsigned char>(), nullptr));
   // chunk of candidates: the kx operand (4 B x KP per candidate) takes at most ~2 GB
   static const int64_t budget = [] {
     const char* e = getenv("BASQ_GPV_CHUNK_MB");
@@ -85,12 +62,15 @@ int gp_variance_tc(basq_ctx* ctx, const basq_kernel_desc* desc, const KParams& k
   }();
   int64_t P = std::max<int64_t>(GPV_MT, budget / (4ll * KP) / GPV_MT * GPV_MT);
   P = std::min<int64_t>(P, ceil_div64(N, GPV_MT) * GPV_MT);
-  DevBuf kxh, kxl, ppack;
+  DevBuf kxh, kxl;
   BASQ_TRY(kxh.alloc(ctx, (size_t)P * KP * 2));
   BASQ_TRY(kxl.alloc(ctx, (size_t)P * KP * 2));
-  BASQ_TRY(ppack.alloc(ctx, sizeof(float) * (size_t)P * ppf_of(kp.dp)));
+  BASQ_CHECK((size_t)GpvCfg::SMEM_BYTES <= ctx->smem_optin, BASQ_ERR_UNSUPPORTED,
+             "gpvar: kernel needs %d B shared memory (limit %zu)", GpvCfg::SMEM_BYTES, ctx->smem_optin);
+  BASQ_CUDA(cudaFuncSetAttribute(gpvar_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GpvCfg::SMEM_BYTES));
   for (int64_t p0 = 0; p0 < N; p0 += P) {
     const int64_t cnt = std::min<int64_t>(P, N - p0);
+    const int n_ptiles = (int)ceil_div64(cnt, GPV_MT);
     KxpDev kx;
     kx.X = reinterpret_cast<const float*>(X) + p0 * desc->d;
     kx.n_points = cnt;
@@ -101,23 +81,24 @@ int gp_variance_tc(basq_ctx* ctx, const basq_kernel_desc* desc, const KParams& k
     kx.kx_scale = kx_scale;
     kx.kxh = kxh.as<__half>();
     kx.kxl = kxl.as<__half>();
-    kx.ppack = ppack.as<float>();
+    switch (kp.family) {
+      case BASQ_RBF: BASQ_TRY(launch_kxgen_points_rbf(ctx, kp, kx, n_ptiles)); break;
+      case BASQ_MATERN15: BASQ_TRY(launch_kxgen_points_m15(ctx, kp, kx, n_ptiles)); break;
+      default: BASQ_TRY(launch_kxgen_points_m25(ctx, kp, kx, n_ptiles)); break;
+    }
     GpvDev d;
     d.kxh = kx.kxh; d.kxl = kx.kxl;
     d.th = th.as<__half>(); d.tl = tl.as<__half>();
-    d.obspack = pack.as<unsigned char>();
-    d.ppack = kx.ppack;
+    d.tinv = tinv.as<float>();
     d.KP = KP;
-    d.n_ptiles = (int)ceil_div64(cnt, GPV_MT);
+    d.n_ptiles = n_ptiles;
     d.n_points = cnt;
     d.os_f = kp.os_f;
     d.base = desc->outputscale + desc->noise;
     d.var_out = var_out + p0;
-    switch (kp.family) {
-      case BASQ_RBF: BASQ_TRY(launch_gpvar_rbf(ctx, kp, kx, d)); break;
-      case BASQ_MATERN15: BASQ_TRY(launch_gpvar_m15(ctx, kp, kx, d)); break;
-      default: BASQ_TRY(launch_gpvar_m25(ctx, kp, kx, d)); break;
-    }
+    gpvar_kernel<0><<<std::min(ctx->num_sms, n_ptiles), NLS_THREADS, GpvCfg::SMEM_BYTES, ctx->stream>>>(d);
+    ctx->launches++;
+    BASQ_CUDA(cudaGetLastError());
   }
   BASQ_CUDA(cudaStreamSynchronize(ctx->stream));  // scratch goes out of scope
   return BASQ_OK;

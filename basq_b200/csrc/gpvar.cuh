@@ -5,22 +5,24 @@
 //    BASQ/_sampler.py:194-217; wsabim_predict, BASQ/_wsabi.py:265-277; gspace_predict,
 //    SOBER/BASQ/_scale_mmlt.py:211-223; lfi, SOBER/_pi.py:121-139)
 //
-// k^T W k = sum_o k_o (T k)_o with T = tril(W + W^T) (diagonal taken once): the contraction T k over a
-// tile of 128 candidates is a GEMM whose result never leaves the SM:
-//   D[p, o] = sum_{o' <= o} kx[p, o'] T[o, o']      tcgen05.mma kind::f16, M = 128 candidates (TMEM
+// "Batched triangular solves": with W = L^-T L^-1 (L the Cholesky factor of K_XX + sigma_n^2 I, recovered
+// from W on the device, gpvar.cu) the quadratic form is |L^-1 k_x|^2, and v = L^-1 k_x over a tile of 128
+// candidates is a GEMM against the explicit lower-triangular L^-1 whose result never leaves the SM:
+//   D[p, o] = sum_{o' <= o} kx[p, o'] Linv[o, o']   tcgen05.mma kind::f16, M = 128 candidates (TMEM
 //                                                   lanes), N = 256 observations, fp16 hi / lo split
 //                                                   operands, three products (fp32 accuracy), the K
 //                                                   loop stops at the diagonal block (half the flop);
-//   epilogue: thread = candidate; for every observation column k(xobs_o, x_p) is recomputed on the
-//             FMA / MUFU pipes (the candidate's coordinates live in registers, the observation's arrive
-//             as broadcast shared-memory loads), multiplied with D[p, o] and accumulated in fp64;
+//   epilogue: thread = candidate, sum_o D[p, o]^2 in fp32 blocks of 32, fp64 across blocks;
 //             var = sigma_f^2 + sigma_n^2 - sum.
+// Why L^-1 and not W: the rounding of a reduced-precision contraction scales with |M| |k|, and
+// |k|^T |W| |k| reaches 1e4 on the benchmark GP (1002 observations in 10-D, cond 1.5e4) where
+// 2 |v|^T |L^-1| |k| stays below 1e2: the T = tril(W + W^T) form measured 3e-3 absolute error, this one 1e-5.
 // Nothing of size n_obs x P is written to HBM in fp64 (round 1: V, Y = 4 x 8 B x n_obs per candidate);
 // the only staged operand is kx itself as fp16 hi / lo (4 B x n_obs per candidate, written once by
 // kxgen_points_kernel, read back through L2 by cp.async.bulk).
 //
-// CTA = 11 warps as nlsum_kernel: warp 8 streams operand stages, warp 9 issues the MMAs, warp 10 streams
-// the observation pack of a column tile, warps 0-7 are the epilogue (two column halves per lane quarter).
+// CTA = 11 warps as nlsum_kernel: warp 8 streams operand stages, warp 9 issues the MMAs, warps 0-7 are
+// the epilogue (two column halves per lane quarter); warp 10 idles.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -38,9 +40,8 @@ constexpr int GPV_STAGE_BYTES = 2 * GPV_A_PIECE + 2 * GPV_B_PIECE;
 
 struct GpvDev {
   const __half* kxh; const __half* kxl;   // [n_ptiles][KP / 8][128][8]
-  const __half* th; const __half* tl;     // [KP / 256][KP / 8][256][8]  T rows scaled per row
-  const unsigned char* obspack;           // [KP / 256][256][OBR]: zz[DP], b, 1 / (row scale * kx scale)
-  const float* ppack;                     // [n_ptiles * 128][PPF]: a, x'[DP] of every candidate of the chunk
+  const __half* th; const __half* tl;     // [KP / 256][KP / 8][256][8]  L^-1 rows scaled per row
+  const float* tinv;                      // [KP] 1 / (row scale * kx scale)
   int KP;                                 // n_obs padded to a multiple of 256
   int n_ptiles;
   int64_t n_points;                       // candidates in this chunk
@@ -49,35 +50,31 @@ struct GpvDev {
   double* var_out;                        // [n_points]
 };
 
-template <int DP>
 struct GpvCfg {
-  static constexpr int OBR = ((DP + 2) * 4 + 15) / 16 * 16;   // bytes per observation in the pack
-  static constexpr int PPF = (DP + 1 + 3) / 4 * 4;            // floats per candidate in ppack
-  static constexpr int OBS_BYTES = GPV_NT * OBR;
-  static constexpr int NSTAGE = 3;
+  static constexpr int NSTAGE = 4;
+  static constexpr int MAX_KP = 4096;                          // observations (padded) the tinv table holds
   static constexpr int OFF_STAGE = 0;
-  static constexpr int OFF_OBS = NSTAGE * GPV_STAGE_BYTES;
-  static constexpr int OFF_COMB = OFF_OBS + 2 * OBS_BYTES;
+  static constexpr int OFF_TINV = NSTAGE * GPV_STAGE_BYTES;
+  static constexpr int OFF_COMB = OFF_TINV + MAX_KP * 4;
   static constexpr int OFF_BAR = OFF_COMB + 128 * 8;
   static constexpr int SMEM_BYTES = OFF_BAR + 256;
   static_assert(SMEM_BYTES <= 227 * 1024, "gpvar: shared memory budget");
 };
 
-template <int FAM, int DP>
+template <int VARIANT>   // a template only so that the header can be included from several translation units
 __global__ void __launch_bounds__(NLS_THREADS, 1) gpvar_kernel(const GpvDev a) {
-  using Cfg = GpvCfg<DP>;
-  constexpr int NSTAGE = Cfg::NSTAGE, OBR = Cfg::OBR, NT = GPV_NT;
+  using Cfg = GpvCfg;
+  constexpr int NSTAGE = Cfg::NSTAGE, NT = GPV_NT;
   extern __shared__ __align__(1024) unsigned char smem_gpv[];
   unsigned char* const smem = smem_gpv;
-  unsigned char* sObs = smem + Cfg::OFF_OBS;
+  float* sTinv = reinterpret_cast<float*>(smem + Cfg::OFF_TINV);
   double* sComb = reinterpret_cast<double*>(smem + Cfg::OFF_COMB);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* s_full = bars;
   uint64_t* s_empty = bars + NSTAGE;
   uint64_t* t_full = bars + 2 * NSTAGE;
   uint64_t* t_empty = t_full + 2;
-  uint64_t* o_full = t_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -88,10 +85,10 @@ __global__ void __launch_bounds__(NLS_THREADS, 1) gpvar_kernel(const GpvDev a) {
     for (int b = 0; b < 2; ++b) {
       mma::mbar_init(&t_full[b], 1);
       mma::mbar_init(&t_empty[b], NLS_EPI_WARPS);
-      mma::mbar_init(&o_full[b], 1);
     }
     mma::fence_barrier_init();
   }
+  for (int o = tid; o < a.KP; o += NLS_THREADS) sTinv[o] = a.tinv[o];
   if (warp == NLS_EPI_WARPS + 1) mma::tmem_alloc(tmem_slot, 512);
   mma::tc_fence_before();
   __syncthreads();
@@ -105,44 +102,26 @@ __global__ void __launch_bounds__(NLS_THREADS, 1) gpvar_kernel(const GpvDev a) {
     // ======================================================================== epilogue
     const int quarter = warp & 3, half = warp >> 2;
     const int row = quarter * 32 + lane;
-    uint32_t tc = 0, items_done = 0;
-    for (int item = blockIdx.x; item < a.n_ptiles; item += gridDim.x, ++items_done) {
+    uint32_t tc = 0;
+    for (int item = blockIdx.x; item < a.n_ptiles; item += gridDim.x) {
       const int64_t p = (int64_t)item * GPV_MT + row;
-      float xr[DP];
-      float pa = 0.f;
-      {
-        const float* pp = a.ppack + (size_t)p * Cfg::PPF;   // padded tiles are fully written by kxgen_points
-        pa = pp[0];
-#pragma unroll
-        for (int i = 0; i < DP; ++i) xr[i] = pp[1 + i];
-      }
       double acc = 0.0;
       for (int c = 0; c < n_ctiles; ++c, ++tc) {
         const uint32_t buf = tc & 1u, ph = (tc >> 1) & 1u;
-        mma::mbar_wait(&o_full[buf], ph);
         mma::mbar_wait(&t_full[buf], ph);
         mma::tc_fence_after();
-        const unsigned char* obs = sObs + buf * Cfg::OBS_BYTES;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * NT + half * (NT / 2);
+        const float* ti = sTinv + c * NT + half * (NT / 2);
 #pragma unroll 1
         for (int cb = 0; cb < NT / 2; cb += 32) {
           uint32_t v[32];
           mma::tmem_ld32(taddr + cb, v);
           mma::tmem_ld_wait();
-          float part = 0.f;   // 32 terms in fp32 (each ~1e-7 accurate), widened once per block
+          float part = 0.f;   // 32 squares in fp32, widened once per block
 #pragma unroll
           for (int cc = 0; cc < 32; ++cc) {
-            const unsigned char* ob = obs + (half * (NT / 2) + cb + cc) * OBR;
-            constexpr int NF4 = OBR / 16;
-            float f[NF4 * 4];   // zz[DP], b, tinv, pad
-#pragma unroll
-            for (int q4 = 0; q4 < NF4; ++q4) {
-              const float4 w4 = *reinterpret_cast<const float4*>(ob + q4 * 16);
-              f[q4 * 4 + 0] = w4.x; f[q4 * 4 + 1] = w4.y; f[q4 * 4 + 2] = w4.z; f[q4 * 4 + 3] = w4.w;
-            }
-            const float k = pair_eval_f32<FAM, DP>(xr, pa, f, f[DP], a.os_f);
-            const float corr = __fmul_rn(__uint_as_float(v[cc]), f[DP + 1]);
-            part = __fmaf_rn(k, corr, part);
+            const float vo = __fmul_rn(__uint_as_float(v[cc]), ti[cb + cc]);
+            part = __fmaf_rn(vo, vo, part);
           }
           acc += (double)part;
         }
@@ -216,19 +195,6 @@ __global__ void __launch_bounds__(NLS_THREADS, 1) gpvar_kernel(const GpvDev a) {
         }
       }
     }
-  } else {
-    // ======================================================================== observation-pack producer
-    if (lane == 0) {
-      uint32_t tc = 0;
-      for (int item = blockIdx.x; item < a.n_ptiles; item += gridDim.x) {
-        for (int c = 0; c < n_ctiles; ++c, ++tc) {
-          const uint32_t buf = tc & 1u;
-          mma::mbar_wait(&t_empty[buf], ((tc >> 1) & 1u) ^ 1u);
-          mma::mbar_expect_tx(&o_full[buf], Cfg::OBS_BYTES);
-          mma::bulk_g2s(sObs + buf * Cfg::OBS_BYTES, a.obspack + (size_t)c * Cfg::OBS_BYTES, Cfg::OBS_BYTES, &o_full[buf]);
-        }
-      }
-    }
   }
 
   mma::tc_fence_before();
@@ -239,8 +205,8 @@ __global__ void __launch_bounds__(NLS_THREADS, 1) gpvar_kernel(const GpvDev a) {
   }
 }
 
-// k(Xobs, x) of a chunk of raw candidates as the A operand ([tile of 128][KP / 8][128][8] fp16 hi / lo)
-// plus the prepared coordinates of every candidate; one CTA per tile, one thread per candidate.
+// k(Xobs, x) of a chunk of raw candidates as the A operand ([tile of 128][KP / 8][128][8] fp16 hi / lo);
+// one CTA per tile, one thread per candidate.
 struct KxpDev {
   const float* X;          // [n_points, d] raw candidates of the chunk
   int64_t n_points;
@@ -248,12 +214,11 @@ struct KxpDev {
   int n_obs, KP;
   float kx_scale;
   __half* kxh; __half* kxl;
-  float* ppack;
 };
 
 template <int FAM, int DP>
 __global__ void __launch_bounds__(GPV_MT) kxgen_points_kernel(KParams kp, const KxpDev a) {
-  constexpr int OB = 64, PPF = GpvCfg<DP>::PPF;
+  constexpr int OB = 64;
   __shared__ __align__(16) float s_oz[OB * DP];
   __shared__ float s_ob[OB];
   const int tile = blockIdx.x, r = threadIdx.x;
@@ -270,12 +235,6 @@ __global__ void __launch_bounds__(GPV_MT) kxgen_points_kernel(KParams kp, const 
 #pragma unroll
     for (int i = 0; i < DP; ++i) x[i] = xl[i];
     pa = point_a_term(kp, nrm);
-  }
-  {
-    float* pp = a.ppack + (size_t)p * PPF;
-    pp[0] = pa;
-#pragma unroll
-    for (int i = 0; i < DP; ++i) pp[1 + i] = x[i];
   }
   const size_t a_tile = (size_t)(a.KP / 8) * GPV_MT * 8;
   uint4* oh = reinterpret_cast<uint4*>(a.kxh + (size_t)tile * a_tile) + r;
@@ -313,57 +272,34 @@ __global__ void __launch_bounds__(GPV_MT) kxgen_points_kernel(KParams kp, const 
 }
 
 template <int FAM, int DP>
-int launch_gpvar_dp(basq_ctx* ctx, const KParams& kp, const KxpDev& kx, const GpvDev& dev) {
-  using Cfg = GpvCfg<DP>;
-  BASQ_CHECK((size_t)Cfg::SMEM_BYTES <= ctx->smem_optin, BASQ_ERR_UNSUPPORTED,
-             "gpvar: kernel needs %d B shared memory (limit %zu)", Cfg::SMEM_BYTES, ctx->smem_optin);
-  if (dev.n_ptiles <= 0) return BASQ_OK;
-  kxgen_points_kernel<FAM, DP><<<dev.n_ptiles, GPV_MT, 0, ctx->stream>>>(kp, kx);
-  BASQ_CUDA(cudaFuncSetAttribute(gpvar_kernel<FAM, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  const int grid = std::min(ctx->num_sms, dev.n_ptiles);
-  gpvar_kernel<FAM, DP><<<grid, NLS_THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(dev);
-  ctx->launches += 2;
+int launch_kxgen_points_dp(basq_ctx* ctx, const KParams& kp, const KxpDev& kx, int n_ptiles) {
+  if (n_ptiles <= 0) return BASQ_OK;
+  kxgen_points_kernel<FAM, DP><<<n_ptiles, GPV_MT, 0, ctx->stream>>>(kp, kx);
+  ctx->launches++;
   BASQ_CUDA(cudaGetLastError());
   return BASQ_OK;
 }
 
 template <int FAM>
-int launch_gpvar_family(basq_ctx* ctx, const KParams& kp, const KxpDev& kx, const GpvDev& dev) {
+int launch_kxgen_points_family(basq_ctx* ctx, const KParams& kp, const KxpDev& kx, int n_ptiles) {
   switch (kp.dp) {
-    case 2: return launch_gpvar_dp<FAM, 2>(ctx, kp, kx, dev);
-    case 4: return launch_gpvar_dp<FAM, 4>(ctx, kp, kx, dev);
-    case 6: return launch_gpvar_dp<FAM, 6>(ctx, kp, kx, dev);
-    case 8: return launch_gpvar_dp<FAM, 8>(ctx, kp, kx, dev);
-    case 10: return launch_gpvar_dp<FAM, 10>(ctx, kp, kx, dev);
-    case 12: return launch_gpvar_dp<FAM, 12>(ctx, kp, kx, dev);
-    case 16: return launch_gpvar_dp<FAM, 16>(ctx, kp, kx, dev);
-    case 20: return launch_gpvar_dp<FAM, 20>(ctx, kp, kx, dev);
-    case 24: return launch_gpvar_dp<FAM, 24>(ctx, kp, kx, dev);
-    case 32: return launch_gpvar_dp<FAM, 32>(ctx, kp, kx, dev);
+    case 2: return launch_kxgen_points_dp<FAM, 2>(ctx, kp, kx, n_ptiles);
+    case 4: return launch_kxgen_points_dp<FAM, 4>(ctx, kp, kx, n_ptiles);
+    case 6: return launch_kxgen_points_dp<FAM, 6>(ctx, kp, kx, n_ptiles);
+    case 8: return launch_kxgen_points_dp<FAM, 8>(ctx, kp, kx, n_ptiles);
+    case 10: return launch_kxgen_points_dp<FAM, 10>(ctx, kp, kx, n_ptiles);
+    case 12: return launch_kxgen_points_dp<FAM, 12>(ctx, kp, kx, n_ptiles);
+    case 16: return launch_kxgen_points_dp<FAM, 16>(ctx, kp, kx, n_ptiles);
+    case 20: return launch_kxgen_points_dp<FAM, 20>(ctx, kp, kx, n_ptiles);
+    case 24: return launch_kxgen_points_dp<FAM, 24>(ctx, kp, kx, n_ptiles);
+    case 32: return launch_kxgen_points_dp<FAM, 32>(ctx, kp, kx, n_ptiles);
   }
   set_error("gpvar: no kernel compiled for padded dimension %d", kp.dp);
   return BASQ_ERR_UNSUPPORTED;
 }
 
-template <int DP>
-__global__ void obspack_kernel(const float* __restrict__ ozz, const float* __restrict__ obz,
-                               const float* __restrict__ tinv, int n_obs, int KP, unsigned char* __restrict__ pack) {
-  constexpr int OBR = GpvCfg<DP>::OBR;
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= KP) return;
-  float* f = reinterpret_cast<float*>(pack + (size_t)o * OBR);
-  for (int i = 0; i < OBR / 4; ++i) f[i] = 0.f;
-  if (o < n_obs) {
-    for (int i = 0; i < DP; ++i) f[i] = ozz[(size_t)o * DP + i];
-    f[DP] = obz[o];
-    f[DP + 1] = tinv[o];
-  }
-}
-
-int launch_gpvar_rbf(basq_ctx*, const KParams&, const KxpDev&, const GpvDev&);
-int launch_gpvar_m15(basq_ctx*, const KParams&, const KxpDev&, const GpvDev&);
-int launch_gpvar_m25(basq_ctx*, const KParams&, const KxpDev&, const GpvDev&);
-int launch_obspack(basq_ctx* ctx, int dp, const float* ozz, const float* obz, const float* tinv, int n_obs, int KP,
-                   unsigned char* pack, int* obr_out);
+int launch_kxgen_points_rbf(basq_ctx*, const KParams&, const KxpDev&, int);
+int launch_kxgen_points_m15(basq_ctx*, const KParams&, const KxpDev&, int);
+int launch_kxgen_points_m25(basq_ctx*, const KParams&, const KxpDev&, int);
 
 }  // namespace basq

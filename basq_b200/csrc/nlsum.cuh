@@ -83,10 +83,14 @@ struct NlsCfg {
   static constexpr int RB = ((24 + 4 * DP) + 15) / 16 * 16;
   static constexpr int REC_BYTES = NLS_NT * RB;
   static constexpr int COMB_BYTES = 2 * 128 * NLS_JT * 8;  // double-buffered hand-over of the column halves
-  static constexpr int NSTAGE = (3 * NLS_STAGE_BYTES + 2 * REC_BYTES + COMB_BYTES + 256 <= 227 * 1024) ? 3 : 2;
+  // operand ring as deep as shared memory allows: the stream needs 64 B/clk per SM from L2, and every stage
+  // in flight hides another 768 tensor-pipe cycles of its latency (the records of a tile are single-buffered:
+  // they are needed only when the tile's MMAs have finished, long after the previous tile's epilogue)
+  static constexpr int FIXED = REC_BYTES + COMB_BYTES + 256;
+  static constexpr int NSTAGE = (4 * NLS_STAGE_BYTES + FIXED <= 227 * 1024) ? 4 : ((3 * NLS_STAGE_BYTES + FIXED <= 227 * 1024) ? 3 : 2);
   static constexpr int OFF_STAGE = 0;
   static constexpr int OFF_REC = NSTAGE * NLS_STAGE_BYTES;
-  static constexpr int OFF_COMB = OFF_REC + 2 * REC_BYTES;
+  static constexpr int OFF_COMB = OFF_REC + REC_BYTES;
   static constexpr int OFF_BAR = OFF_COMB + COMB_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256;
   static_assert(SMEM_BYTES <= 227 * 1024, "nlsum: shared memory budget");
@@ -148,9 +152,10 @@ __global__ void __launch_bounds__(NLS_THREADS, 1) nlsum_kernel(const NlsDev a) {
   uint64_t* s_full = bars;                 // [NSTAGE]
   uint64_t* s_empty = bars + NSTAGE;       // [NSTAGE]
   uint64_t* t_full = bars + 2 * NSTAGE;    // [2] accumulator ready
-  uint64_t* t_empty = t_full + 2;          // [2] accumulator + record buffer drained by the epilogue
-  uint64_t* r_full = t_empty + 2;          // [2] records landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_full + 2);
+  uint64_t* t_empty = t_full + 2;          // [2] accumulator drained by the epilogue
+  uint64_t* r_full = t_empty + 2;          // [1] records landed
+  uint64_t* r_empty = r_full + 1;          // [1] records consumed by the epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_empty + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -161,8 +166,9 @@ __global__ void __launch_bounds__(NLS_THREADS, 1) nlsum_kernel(const NlsDev a) {
     for (int b = 0; b < 2; ++b) {
       mma::mbar_init(&t_full[b], 1);
       mma::mbar_init(&t_empty[b], NLS_EPI_WARPS);
-      mma::mbar_init(&r_full[b], 1);
     }
+    mma::mbar_init(r_full, 1);
+    mma::mbar_init(r_empty, NLS_EPI_WARPS);
     mma::fence_barrier_init();
   }
   if (warp == NLS_EPI_WARPS + 1) mma::tmem_alloc(tmem_slot, 512);
@@ -199,10 +205,10 @@ __global__ void __launch_bounds__(NLS_THREADS, 1) nlsum_kernel(const NlsDev a) {
       for (int jj = 0; jj < NLS_JT; ++jj) acc[jj] = 0.0;
       for (int t = 0; t < n_tiles; ++t, ++tc) {
         const uint32_t buf = tc & 1u, ph = (tc >> 1) & 1u;
-        mma::mbar_wait(&r_full[buf], ph);
+        mma::mbar_wait(r_full, tc & 1u);
         mma::mbar_wait(&t_full[buf], ph);
         mma::tc_fence_after();
-        const unsigned char* recs = sRec + buf * Cfg::REC_BYTES;
+        const unsigned char* recs = sRec;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * NT + half * (NT / 2);
 #pragma unroll 1
         for (int cb = 0; cb < NT / 2; cb += 32) {
@@ -241,7 +247,10 @@ __global__ void __launch_bounds__(NLS_THREADS, 1) nlsum_kernel(const NlsDev a) {
         }
         mma::tc_fence_before();
         __syncwarp();
-        if (lane == 0) mma::mbar_arrive(&t_empty[buf]);
+        if (lane == 0) {
+          mma::mbar_arrive(&t_empty[buf]);
+          mma::mbar_arrive(r_empty);
+        }
       }
       if (MODE == 0) {
         // combine the two column halves in a fixed order and write the item's 128 x 8 block of G
@@ -338,11 +347,10 @@ __global__ void __launch_bounds__(NLS_THREADS, 1) nlsum_kernel(const NlsDev a) {
         int n_tiles;
         nls_item_range(a, (a.jg0 + jgl) * a.JT, e_lo, n_tiles);
         for (int t = 0; t < n_tiles; ++t, ++tc) {
-          const uint32_t buf = tc & 1u;
-          mma::mbar_wait(&t_empty[buf], ((tc >> 1) & 1u) ^ 1u);
+          mma::mbar_wait(r_empty, (tc & 1u) ^ 1u);
           const size_t tile = (size_t)jgl * a.tiles_per_jg + t;
-          mma::mbar_expect_tx(&r_full[buf], Cfg::REC_BYTES);
-          mma::bulk_g2s(sRec + buf * Cfg::REC_BYTES, a.trec + tile * Cfg::REC_BYTES, Cfg::REC_BYTES, &r_full[buf]);
+          mma::mbar_expect_tx(r_full, Cfg::REC_BYTES);
+          mma::bulk_g2s(sRec, a.trec + tile * Cfg::REC_BYTES, Cfg::REC_BYTES, r_full);
         }
       }
     }

@@ -461,6 +461,27 @@ int orthonormalise(basq_ctx* ctx, OrthWs& ws, double* Y, int64_t M, int q, int p
 
 }  // namespace
 
+// Linv_out [n, n] (row-major, fp64) = L^-1 with A = L L^T for a symmetric positive definite A [n, n]:
+// the cooperative Cholesky + inverse kernels of the CholeskyQR step, on their own (gpvar.cu).
+int spd_inverse_factor(basq_ctx* ctx, const double* A, int n, double* Linv_out) {
+  BASQ_CHECK(A && Linv_out && n >= 1, BASQ_ERR_INVALID, "spd_inverse_factor: bad argument");
+  OrthWs ws;
+  BASQ_TRY(ws.gram.alloc(ctx, sizeof(double) * (size_t)n * n));
+  BASQ_TRY(ws.linv.alloc(ctx, sizeof(double) * (size_t)n * n));
+  BASQ_TRY(ws.prow.alloc(ctx, sizeof(double) * 4 * n));
+  BASQ_TRY(ws.prow2.alloc(ctx, sizeof(double) * 2 * (size_t)n * n));
+  BASQ_TRY(ws.flags.alloc(ctx, 512));
+  BASQ_CUDA(cudaMemsetAsync(ws.flags.p, 0, 512, ctx->stream));
+  BASQ_CUDA(cudaMemcpyAsync(ws.gram.p, A, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, ctx->stream));
+  BASQ_TRY(chol_inverse(ctx, ws, n, 1e-300));
+  BASQ_CUDA(cudaMemcpyAsync(Linv_out, ws.linv.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToDevice, ctx->stream));
+  int status = 0;
+  BASQ_CUDA(cudaMemcpyAsync(&status, ws.flags.as<int>() + 64, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  BASQ_CHECK(status == 0, BASQ_ERR_NUMERIC, "spd_inverse_factor: grid barrier watchdog fired in the Cholesky kernel");
+  return BASQ_OK;
+}
+
 int nystrom_basis(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, int64_t M, int q, const double* Omega,
                   int niter, double* U_out, double* S_out) {
   PhaseTimer timer(ctx, PH_NYS);
