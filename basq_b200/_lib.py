@@ -32,7 +32,7 @@ class KernelDesc(C.Structure):
         ("lengthscale", C.c_double * BASQ_MAX_DIM),
         ("noise", C.c_double), ("mean_const", C.c_double), ("diag_add", C.c_double),
         ("n_obs", C.c_int32), ("noise_diag", C.c_int32),
-        ("Xobs", C.c_void_p), ("W", C.c_void_p), ("alpha", C.c_void_p),
+        ("Xobs", C.c_void_p), ("W", C.c_void_p), ("alpha", C.c_void_p), ("Xobs_f64", C.c_void_p),
     ]
 
 

@@ -279,7 +279,13 @@ int session_create_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
       };
       BASQ_TRY(widen(X, N_loc, &s->X64));
       BASQ_TRY(widen(Z, M, &s->Z64));
-      BASQ_TRY(widen(desc->Xobs, n_obs, &s->Xobs64));
+      if (desc->Xobs_f64) {
+        BASQ_TRY(s->Xobs64.alloc(ctx, sizeof(double) * (size_t)n_obs * d));
+        BASQ_CUDA(cudaMemcpyAsync(s->Xobs64.p, desc->Xobs_f64, sizeof(double) * (size_t)n_obs * d, cudaMemcpyDeviceToDevice,
+                                  ctx->stream));
+      } else {
+        BASQ_TRY(widen(desc->Xobs, n_obs, &s->Xobs64));
+      }
       s->lm.zz.release(); s->lm.b.release(); s->lm.lmA.release();
       s->lmobs.zz.release(); s->lmobs.b.release(); s->lmobs.lmA.release();
       s->Az.release();

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define BASQ_ABI_VERSION 1
+#define BASQ_ABI_VERSION 2
 #define BASQ_MAX_DIM 32
 #define BASQ_MAX_CELL_FACTOR 16 /* cells per set in a refined pass (basq_session_pass_begin) */
 
@@ -71,6 +71,9 @@ typedef struct basq_kernel_desc {
   const void* Xobs;                  /* [n_obs, d] in dtype */
   const double* W;                   /* [n_obs, n_obs] (K_XX + sigma_n^2 I)^-1, fp64 (BASQ/_gp.py:233-256) */
   const double* alpha;               /* [n_obs] mean cache (K_XX + sigma_n^2 I)^-1 (y - c), fp64 */
+  const double* Xobs_f64;            /* optional (may be NULL): the observations in fp64, [n_obs, d].  Used when a
+                                        call with fp32 inputs is promoted to the fp64 path (basq_ctx_conditioning):
+                                        W belongs to these coordinates, not to their fp32 roundings */
 } basq_kernel_desc;
 
 /* ---- context ------------------------------------------------------------------------------ */

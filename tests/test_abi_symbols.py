@@ -24,13 +24,13 @@ def test_header_symbols_exported():
         assert hasattr(_lib.lib, n), f"{n} declared in include/basq_b200.h but not exported"
     # and the binding covers all of them
     assert set(names) == set(_lib.SYMBOLS)
-    assert _lib.lib.basq_abi_version() == 1
+    assert _lib.lib.basq_abi_version() == 2
 
 
 def test_struct_layout_matches_header():
     from basq_b200 import _lib
     # 4 x int32, double, 32 doubles, 3 doubles, 2 x int32, 3 pointers
-    assert ctypes.sizeof(_lib.KernelDesc) == 16 + 8 + 8 * 32 + 24 + 8 + 24
+    assert ctypes.sizeof(_lib.KernelDesc) == 16 + 8 + 8 * 32 + 24 + 8 + 32
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")

@@ -89,7 +89,9 @@ def _free_port():
 def _worker(rank, world, port, N, weighted, out_path):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
+    # file-based rendezvous: no race for a TCP port between bind-and-release and the store's own bind
+    dist.init_process_group("gloo", init_method=f"file://{out_path}.rdzv", rank=rank, world_size=world)
     try:
         torch.set_num_threads(2)
         g = torch.Generator().manual_seed(123)
