@@ -815,8 +815,11 @@ int basq_ctx_create(int device, void* stream, basq_ctx** out) {
   }
   {
     // Private stream-ordered pool (the device's default pool is left untouched: it is shared with
-    // whatever else lives in the process).  Freed scratch stays cached in it across the pass loop;
-    // every top-level call trims it back to pool_keep bytes before returning (basq_ctx_trim).
+    // whatever else lives in the process).  Freed scratch stays cached in it across the pass loop and
+    // across calls; basq_ctx_trim hands it back on request.  Automatic trimming at the end of every
+    // top-level call is opt-in (BASQ_POOL_KEEP_MB): with a 24 GiB keep size the 2-GPU bench showed
+    // sporadic 150-800 ms stalls per step, because legs with different buffer sizes fragment the pool past
+    // the threshold and every trim is followed by a re-growth at driver speed.
     cudaMemPoolProps props;
     memset(&props, 0, sizeof(props));
     props.allocType = cudaMemAllocationTypePinned;
@@ -830,7 +833,7 @@ int basq_ctx_create(int device, void* stream, basq_ctx** out) {
     }
     uint64_t hold = UINT64_MAX;  // inside a call nothing goes back to the driver
     cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &hold);
-    c->pool_keep = 24ull << 30;
+    c->pool_keep = UINT64_MAX;   // no automatic trim
     if (const char* t = getenv("BASQ_POOL_KEEP_MB")) c->pool_keep = (uint64_t)strtoull(t, nullptr, 10) << 20;
   }
   { const char* t = getenv("BASQ_TRACE"); c->trace = t && t[0] == '1'; }
@@ -858,6 +861,7 @@ int basq_ctx_trim(basq_ctx* ctx, int64_t keep_bytes) {
   BASQ_CHECK(ctx, BASQ_ERR_INVALID, "ctx is NULL");
   if (!ctx->pool) return BASQ_OK;
   const uint64_t keep = keep_bytes < 0 ? ctx->pool_keep : (uint64_t)keep_bytes;
+  if (keep == UINT64_MAX) return BASQ_OK;
   uint64_t reserved = 0;
   cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
   if (reserved > keep) {

@@ -389,13 +389,20 @@ def run_ours(a, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    debug = os.environ.get("BASQ_BENCH_DEBUG") == "1"
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         out = None
-        for _ in range(steps):
+        for i in range(steps):
+            t0 = time.perf_counter()
             out = fn()
+            if debug:   # per-step wall clock (synchronising: diagnostic runs only)
+                torch.cuda.synchronize(dev)
+                print(f"[bench debug] rank {rank} {fn.__name__} step {i}: {1e3 * (time.perf_counter() - t0):.1f} ms",
+                      file=sys.stderr, flush=True)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)

@@ -83,11 +83,13 @@ const char* basq_last_error(void);
 int basq_ctx_create(int device, void* stream, basq_ctx** out);
 void basq_ctx_destroy(basq_ctx* ctx);
 /* Scratch memory: every ctx owns a private stream-ordered CUDA memory pool (the device's default pool
-   is never touched), which caches freed blocks so that the pass loop does not reach the driver.  Every
-   top-level call trims the pool back to the context's keep size before it returns (default 24 GiB -
-   the working set of a 1e7-candidate call stays cached, re-growing the pool costs ~100 ms -,
-   environment BASQ_POOL_KEEP_MB); basq_ctx_trim(ctx, keep_bytes) does so on demand (keep_bytes < 0:
-   the context's keep size; 0: hand everything back, e.g. before another library needs the memory). */
+   is never touched), which caches freed blocks so that neither the pass loop nor the next call reaches
+   the driver (a 1e7-candidate call holds 7-10 GB).  basq_ctx_trim(ctx, keep_bytes) hands the cache back
+   to the driver down to keep_bytes (0: everything) - call it when other CUDA code in the process needs
+   the memory, e.g. between the BASQ iteration and the GP refit.  keep_bytes < 0 applies the context's
+   automatic keep size, which every top-level call also applies before it returns; it is unlimited (no
+   automatic trim) unless the environment sets BASQ_POOL_KEEP_MB - trimming after every call was measured
+   to cost sporadic 150-800 ms re-growth stalls per step.  basq_ctx_destroy releases the pool. */
 int basq_ctx_trim(basq_ctx* ctx, int64_t keep_bytes);
 /* Conditioning guard of the fp32 path.  A posterior-covariance kernel evaluates
    C(z, x) = k(z, x) - (K_ZX W) k(Xobs, x): an evaluation error eps of the kernel values (fp32: ~2e-7
