@@ -139,11 +139,56 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       : "memory");
 }
 
+// Epilogue of one 128 x 256 tile for one thread (TMEM lane = landmark row m, column half `half`):
+// correction from TMEM, k(z_m, x_p) with the library's operation sequence, C, the non-linearity, fp64
+// accumulation per set (MODE 0) or one store per column (MODE 1).
+template <int FAM, int DP, int NL, int MODE>
+__device__ __forceinline__ void nls_epilogue_tile(const NlsDev& a, const unsigned char* recs, uint32_t taddr, int half,
+                                                  const float (&zr)[DP], float bm, float szm, float ainv,
+                                                  double (&acc)[NLS_JT], int m, bool mok, int j0) {
+  constexpr int RB = NlsCfg<DP>::RB, NT = NLS_NT;
+#pragma unroll 1
+  for (int cb = 0; cb < NT / 2; cb += 32) {
+    uint32_t v[32];
+    mma::tmem_ld32(taddr + cb, v);
+    mma::tmem_ld_wait();
+    const int c0 = half * (NT / 2) + cb;
+    double out[MODE == 1 ? 32 : 1];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const unsigned char* rec = recs + (c0 + c) * RB;
+      const double2 hw = *reinterpret_cast<const double2*>(rec);   // per-point factor, weight
+      constexpr int NF4 = (RB - 16) / 16;
+      float f[NF4 * 4];                                            // [idx, a, x0, x1, ...]
+#pragma unroll
+      for (int q4 = 0; q4 < NF4; ++q4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(rec + 16 + q4 * 16);
+        f[q4 * 4 + 0] = w4.x; f[q4 * 4 + 1] = w4.y; f[q4 * 4 + 2] = w4.z; f[q4 * 4 + 3] = w4.w;
+      }
+      const float k = pair_eval_f32<FAM, DP>(&f[2], f[1], zr, bm, a.os_f);
+      const float cv = __fsub_rn(k, __fmul_rn(__uint_as_float(v[c]), ainv));
+      float val = nl_apply_f32<NL>(cv, __fmul_rn(szm, (float)hw.x));
+      val = (hw.y != 0.0) ? val : 0.f;
+      if (MODE == 0) acc[c % NLS_JT] = fma(f2d_signed(val), hw.y, acc[c % NLS_JT]);
+      else out[c] = f2d_signed(val) * hw.y;
+    }
+    if (MODE == 1 && mok) {
+      // one column = one cell: columns c0 .. c0 + 31 of this row are contiguous in G.  Only slots
+      // that hold a candidate are written (G is zeroed by the host; a group whose members wrap
+      // around the cell range spans two tiles with complementary valid slots).
+      double* dst = a.G + (int64_t)m * a.ldg + j0 + c0;
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (out[c] != 0.0) dst[c] = out[c];
+    }
+  }
+}
+
 // MODE 0: SETSUM (accumulate per set, write once per work item) ; MODE 1: GRAM (one column = one cell)
 template <int FAM, int DP, int NL, int MODE>
 __global__ void __launch_bounds__(NLS_THREADS, 1) nlsum_kernel(const NlsDev a) {
   using Cfg = NlsCfg<DP>;
-  constexpr int NSTAGE = Cfg::NSTAGE, RB = Cfg::RB, NT = NLS_NT;
+  constexpr int NSTAGE = Cfg::NSTAGE, NT = NLS_NT;
   extern __shared__ __align__(1024) unsigned char smem_nls[];
   unsigned char* const smem = smem_nls;
   unsigned char* sRec = smem + Cfg::OFF_REC;
@@ -208,43 +253,8 @@ __global__ void __launch_bounds__(NLS_THREADS, 1) nlsum_kernel(const NlsDev a) {
         mma::mbar_wait(r_full, tc & 1u);
         mma::mbar_wait(&t_full[buf], ph);
         mma::tc_fence_after();
-        const unsigned char* recs = sRec;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * NT + half * (NT / 2);
-#pragma unroll 1
-        for (int cb = 0; cb < NT / 2; cb += 32) {
-          uint32_t v[32];
-          mma::tmem_ld32(taddr + cb, v);
-          mma::tmem_ld_wait();
-          const int c0 = half * (NT / 2) + cb;
-          double out[MODE == 1 ? 32 : 1];
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const unsigned char* rec = recs + (c0 + c) * RB;
-            const double2 hw = *reinterpret_cast<const double2*>(rec);   // per-point factor, weight
-            constexpr int NF4 = (RB - 16) / 16;
-            float f[NF4 * 4];                                            // [idx, a, x0, x1, ...]
-#pragma unroll
-            for (int q4 = 0; q4 < NF4; ++q4) {
-              const float4 w4 = *reinterpret_cast<const float4*>(rec + 16 + q4 * 16);
-              f[q4 * 4 + 0] = w4.x; f[q4 * 4 + 1] = w4.y; f[q4 * 4 + 2] = w4.z; f[q4 * 4 + 3] = w4.w;
-            }
-            const float k = pair_eval_f32<FAM, DP>(&f[2], f[1], zr, bm, a.os_f);
-            const float cv = __fsub_rn(k, __fmul_rn(__uint_as_float(v[c]), ainv));
-            float val = nl_apply_f32<NL>(cv, __fmul_rn(szm, (float)hw.x));
-            val = (hw.y != 0.0) ? val : 0.f;
-            if (MODE == 0) acc[c % NLS_JT] = fma(f2d_signed(val), hw.y, acc[c % NLS_JT]);
-            else out[c] = f2d_signed(val) * hw.y;
-          }
-          if (MODE == 1 && mok) {
-            // one column = one cell: columns c0 .. c0 + 31 of this row are contiguous in G.  Only slots
-            // that hold a candidate are written (G is zeroed by the host; a group whose members wrap
-            // around the cell range spans two tiles with complementary valid slots).
-            double* dst = a.G + (int64_t)m * a.ldg + j0 + c0;
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (out[c] != 0.0) dst[c] = out[c];
-          }
-        }
+        nls_epilogue_tile<FAM, DP, NL, MODE>(a, sRec, taddr, half, zr, bm, szm, ainv, acc, m, mok, j0);
         mma::tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -377,6 +387,7 @@ struct KxDev {
   int n_obs, KP;
   float os_f;
   float kx_scale;                       // 2^(14 - ceil(log2 os))
+  int split_half;                       // 0: [tile][K / 8][256][8] ; 1: [tile][half][K / 8][128][8] (CTA pairs, nlsum2.cuh)
   __half* kxh; __half* kxl;
   unsigned char* trec;
 };
@@ -432,8 +443,11 @@ __global__ void __launch_bounds__(NLS_NT) kxgen_kernel(const KxDev a) {
     for (int i = 0; i < DP; ++i) x[i] = f[2 + i];
   }
   const size_t b_tile = (size_t)(a.KP / 8) * NLS_NT * 8;
-  uint4* oh = reinterpret_cast<uint4*>(a.kxh + (size_t)tile * b_tile) + c;   // chunk kc lies kc * 256 uint4 further
-  uint4* ol = reinterpret_cast<uint4*>(a.kxl + (size_t)tile * b_tile) + c;
+  // chunk kc lies kc * rows uint4 further (rows = 256, or 128 within the slot's half)
+  const int rows = a.split_half ? NLS_NT / 2 : NLS_NT;
+  const size_t slot0 = a.split_half ? (size_t)(c >> 7) * (b_tile / 8 / 2) + (c & 127) : (size_t)c;
+  uint4* oh = reinterpret_cast<uint4*>(a.kxh + (size_t)tile * b_tile) + slot0;
+  uint4* ol = reinterpret_cast<uint4*>(a.kxl + (size_t)tile * b_tile) + slot0;
   for (int o0 = 0; o0 < a.KP; o0 += OB) {
     __syncthreads();
     for (int i = threadIdx.x; i < OB * DP; i += NLS_NT) {
@@ -460,7 +474,7 @@ __global__ void __launch_bounds__(NLS_NT) kxgen_kernel(const KxDev a) {
         l2[u / 2] = __halves2half2(__float2half_rn(__fsub_rn(vv[0], __half2float(h0))),
                                    __float2half_rn(__fsub_rn(vv[1], __half2float(h1))));
       }
-      const size_t chunk = (size_t)(o0 / 8 + kc) * NLS_NT;
+      const size_t chunk = (size_t)(o0 / 8 + kc) * rows;
       oh[chunk] = *reinterpret_cast<const uint4*>(h2);
       ol[chunk] = *reinterpret_cast<const uint4*>(l2);
     }

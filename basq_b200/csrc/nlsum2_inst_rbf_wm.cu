@@ -1,0 +1,7 @@
+// nlsum2_kernel (CTA pairs) instantiations: rbf, WSABI-M (see nlsum2.cuh)
+#include "nlsum2.cuh"
+namespace basq {
+int launch_nlsum2_rbf_wm(basq_ctx* ctx, int dp, const NlsDev& dev) {
+  return launch_nlsum2_family<BASQ_RBF, NL_WSABIM>(ctx, dp, dev);
+}
+}  // namespace basq
