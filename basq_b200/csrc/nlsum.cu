@@ -85,8 +85,10 @@ int nls_set_sums(basq_ctx* ctx, const KParams& kp, int nl, NlOperands* op, const
   // every cell has at most one member of the range: one column per cell (GRAM); else 8 sets x 32 members
   const bool gram = (p_hi - p_lo) <= (int64_t)S;
   const int JT = gram ? NLS_NT : NLS_JT, EC = NLS_NT / JT;
-  // set sums run on CTA pairs (tcgen05 cta_group::2, nlsum2.cuh); BASQ_NLS_2CTA=0 keeps the one-CTA kernel (A/B)
-  const bool pairs = !gram && ctx->num_sms >= 2 && !([] { const char* e = getenv("BASQ_NLS_2CTA"); return e && e[0] == '0'; }());
+  // BASQ_NLS_2CTA=1: set sums on CTA pairs (tcgen05 cta_group::2, nlsum2.cuh).  Measured slower than the
+  // one-CTA kernel (684 vs 625 ms for the config-5 sweep: tensor pipe 52 % vs 66 % active - the cross-CTA
+  // full / empty hand-shake costs more than the halved B stream saves), so it stays opt-in.
+  const bool pairs = !gram && ctx->num_sms >= 2 && ([] { const char* e = getenv("BASQ_NLS_2CTA"); return e && e[0] == '1'; }());
   const int n_jg_total = ceil_div(S, JT);
   // tile stride: an upper bound of any group's tile count
   const int64_t e_hi_max = (p_hi - 1 + off) / S + 1;

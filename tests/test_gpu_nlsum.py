@@ -54,13 +54,15 @@ def test_features_vs_oracle_and_pairwise_path(lib, monkeypatch, name, family, nu
     assert float((Phi_old - ref).abs().max()) < 3e-4 * scale
 
 
+@pytest.mark.parametrize("pairs", ["0", "1"])
 @pytest.mark.parametrize("name", ["wsabim", "mmlt"])
-def test_set_sums_match_summed_features(lib, monkeypatch, name):
+def test_set_sums_match_summed_features(lib, monkeypatch, name, pairs):
     """SETSUM mode (8 sets x 32 members per tile, several tiles per set, ragged tails) equals the sum of
     the GRAM-mode features of the same candidates to fp64 accumulation accuracy: both evaluate the same
     fp32 kernel values, so a rule built from the sweeps preserves the library's features to 1e-8."""
     _, _lib, gp, ops, *_ = lib
     monkeypatch.setenv("BASQ_NLSUM", "1")
+    monkeypatch.setenv("BASQ_NLS_2CTA", pairs)     # "1": the CTA-pair kernel (tcgen05 cta_group::2, opt-in)
     d, n_obs, M, N, n = 10, 130, 300, 40_000, 20
     model = ogp.make_gp(d, n_obs, lengthscale=2.5, noise=1e-3, seed=3, log_targets=(name == "mmlt"))
     kern = _kern(model, name)
