@@ -55,6 +55,31 @@ int gp_variance_tc(basq_ctx* ctx, const basq_kernel_desc* desc, const KParams& k
       Linv.as<double>(), n_obs, n_obs, n_obs, KP, n_ct, rscale.as<float>(), th.as<__half>(), tl.as<__half>());
   ctx->launches += 2;
   BASQ_CUDA(cudaGetLastError());
+  // Fused kernel (default): kernel values are generated on the SM, nothing is staged in HBM.
+  // BASQ_GPVAR_FUSED=0: the two-kernel version below (k(Xobs, X) staged as an fp16 operand), kept for A/B.
+  const bool fused = !([] { const char* e = getenv("BASQ_GPVAR_FUSED"); return e && e[0] == '0'; }());
+  if (fused) {
+    GpfDev f;
+    f.X = reinterpret_cast<const float*>(X);
+    f.n_points = N;
+    f.n_ptiles = (int)ceil_div64(N, GPV_MT);
+    f.ozz = reinterpret_cast<const float*>(lmobs.zz);
+    f.obz = lmobs.b;
+    f.n_obs = n_obs;
+    f.KP = KP;
+    f.kx_scale = kx_scale;
+    f.th = th.as<__half>(); f.tl = tl.as<__half>();
+    f.tinv = tinv.as<float>();
+    f.base = desc->outputscale + desc->noise;
+    f.var_out = var_out;
+    switch (kp.family) {
+      case BASQ_RBF: BASQ_TRY(launch_gpvar_fused_rbf(ctx, kp, f)); break;
+      case BASQ_MATERN15: BASQ_TRY(launch_gpvar_fused_m15(ctx, kp, f)); break;
+      default: BASQ_TRY(launch_gpvar_fused_m25(ctx, kp, f)); break;
+    }
+    BASQ_CUDA(cudaStreamSynchronize(ctx->stream));  // scratch goes out of scope
+    return BASQ_OK;
+  }
   // chunk of candidates: the kx operand (4 B x KP per candidate) takes at most ~2 GB
   static const int64_t budget = [] {
     const char* e = getenv("BASQ_GPV_CHUNK_MB");

@@ -205,6 +205,322 @@ __global__ void __launch_bounds__(NLS_THREADS, 1) gpvar_kernel(const GpvDev a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fully fused version: k(Xobs, x) never leaves the SM.  Four generator warps (one thread per candidate of
+// the tile) evaluate the kernel values of one 32-observation K block, split them into fp16 hi / lo and
+// store them straight into the A stage in the tcgen05 K-major layout; the MMA warp contracts the stage
+// against the L^-1 tiles of TWO observation column tiles at once (two 256-column accumulators = all of
+// TMEM), so a K block is generated once per pair of column tiles (1.5x the unique evaluations at four
+// column tiles; they cost a third of the MMA time and hide under it).  DRAM traffic: the candidates in
+// (4 d B each), the variances out (8 B each).
+//   warps 0-3   generators          warps 4-11  epilogue (TMEM lane quarter = warp % 4, two column halves)
+//   warp 12     L^-1 tile producer (cp.async.bulk, 64 KB stages: hi / lo of two column tiles)
+//   warp 13     TMEM allocation + tcgen05.mma issue
+// ---------------------------------------------------------------------------------------------
+constexpr int GPF_GEN_WARPS = 4, GPF_EPI_WARPS = 8;
+constexpr int GPF_THREADS = (GPF_GEN_WARPS + GPF_EPI_WARPS + 2) * 32;
+constexpr int GPF_A_STAGE = 2 * GPV_A_PIECE;          // hi + lo of one generated K block: 16 KB
+constexpr int GPF_B_STAGE = 4 * GPV_B_PIECE;          // hi + lo of two column tiles: 64 KB
+
+struct GpfDev {
+  const float* X;          // [n_points, d] raw candidates
+  int64_t n_points;
+  int n_ptiles;
+  const float* ozz; const float* obz;     // prepared observations [n_obs, DP], [n_obs]
+  int n_obs, KP;
+  float kx_scale;
+  const __half* th; const __half* tl;     // L^-1 tiles [KP / 256][KP / 8][256][8]
+  const float* tinv;                      // [KP]
+  double base;
+  double* var_out;
+};
+
+template <int DP>
+struct GpfCfg {
+  static constexpr int NA = 3, NB = 2;
+  static constexpr int OBF = DP + 1;                                 // floats per observation (zz, b)
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_B = OFF_A + NA * GPF_A_STAGE;
+  static constexpr int OFF_OBS = OFF_B + NB * GPF_B_STAGE;           // [2][32][OBF] floats
+  static constexpr int OBS_BYTES = ((2 * NLS_KB * OBF * 4) + 15) / 16 * 16;
+  static constexpr int OFF_TINV = OFF_OBS + OBS_BYTES;
+  static constexpr int OFF_COMB = OFF_TINV + GpvCfg::MAX_KP * 4;
+  static constexpr int OFF_BAR = OFF_COMB + 128 * 8;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256;
+  static_assert(SMEM_BYTES <= 227 * 1024, "gpvar (fused): shared memory budget");
+};
+
+template <int FAM, int DP>
+__global__ void __launch_bounds__(GPF_THREADS, 1) gpvar_fused_kernel(KParams kp, const GpfDev a) {
+  using Cfg = GpfCfg<DP>;
+  constexpr int NA = Cfg::NA, NB = Cfg::NB, NT = GPV_NT, OBF = Cfg::OBF;
+  extern __shared__ __align__(1024) unsigned char smem_gpf[];
+  unsigned char* const smem = smem_gpf;
+  float* sObs = reinterpret_cast<float*>(smem + Cfg::OFF_OBS);
+  float* sTinv = reinterpret_cast<float*>(smem + Cfg::OFF_TINV);
+  double* sComb = reinterpret_cast<double*>(smem + Cfg::OFF_COMB);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* a_full = bars;                 // [NA] 128 generator threads
+  uint64_t* a_empty = a_full + NA;         // [NA] MMA commit
+  uint64_t* b_full = a_empty + NA;         // [NB] tx
+  uint64_t* b_empty = b_full + NB;         // [NB] MMA commit
+  uint64_t* t_full = b_empty + NB;         // [2]
+  uint64_t* t_empty = t_full + 2;          // [2] 8 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < NA; ++s) {
+      mma::mbar_init(&a_full[s], GPF_GEN_WARPS * 32);
+      mma::mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < NB; ++s) {
+      mma::mbar_init(&b_full[s], 1);
+      mma::mbar_init(&b_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mma::mbar_init(&t_full[b], 1);
+      mma::mbar_init(&t_empty[b], GPF_EPI_WARPS);
+    }
+    mma::fence_barrier_init();
+  }
+  for (int o = tid; o < a.KP; o += GPF_THREADS) sTinv[o] = a.tinv[o];
+  if (warp == GPF_GEN_WARPS + GPF_EPI_WARPS + 1) mma::tmem_alloc(tmem_slot, 512);
+  mma::tc_fence_before();
+  __syncthreads();
+  mma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_ct = a.KP / NT;
+  const int n_sweeps = (n_ct + 1) / 2;
+  // K blocks up to the diagonal block of column tile c (L^-1 is lower triangular)
+  auto nkb_of = [&](int c) { return min(a.KP, NT * (c + 1)) / NLS_KB; };
+
+  if (warp < GPF_GEN_WARPS) {
+    // ======================================================================== generators
+    const int r = tid;   // candidate row of the tile
+    uint32_t it = 0, ob = 0;
+    for (int item = blockIdx.x; item < a.n_ptiles; item += gridDim.x) {
+      const int64_t p = (int64_t)item * GPV_MT + r;
+      const bool ok = p < a.n_points;
+      float x[DP];
+      float pa = 0.f;
+#pragma unroll
+      for (int i = 0; i < DP; ++i) x[i] = 0.f;
+      if (ok) {
+        float xl[BASQ_MAX_DIM];
+        float nrm;
+        prep_point_f32(kp, a.X + p * kp.d, xl, &nrm);
+#pragma unroll
+        for (int i = 0; i < DP; ++i) x[i] = xl[i];
+        pa = point_a_term(kp, nrm);
+      }
+      for (int sw = 0; sw < n_sweeps; ++sw) {
+        const int c_last = min(2 * sw + 1, n_ct - 1);
+        const int nkb = nkb_of(c_last);
+        for (int kb = 0; kb < nkb; ++kb, ++it, ++ob) {
+          // the K block's observations -> shared memory (double-buffered among the generator warps)
+          float* so = sObs + (ob & 1u) * (NLS_KB * OBF);
+          for (int i = r; i < NLS_KB * OBF; i += GPF_GEN_WARPS * 32) {
+            const int o = kb * NLS_KB + i / OBF, j = i % OBF;
+            so[i] = o < a.n_obs ? (j < DP ? a.ozz[(size_t)o * DP + j] : a.obz[o]) : 0.f;
+          }
+          mma::named_bar_sync(3, GPF_GEN_WARPS * 32);
+          const int s = it % NA;
+          mma::mbar_wait(&a_empty[s], ((it / NA) & 1u) ^ 1u);
+          uint4* sh = reinterpret_cast<uint4*>(smem + Cfg::OFF_A + (size_t)s * GPF_A_STAGE) + r;
+          uint4* sl = sh + GPV_A_PIECE / 16;
+#pragma unroll
+          for (int kc = 0; kc < NLS_KB / 8; ++kc) {
+            __half2 h2[4], l2[4];
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) {
+              float vv[2];
+#pragma unroll
+              for (int w = 0; w < 2; ++w) {
+                const int ol_ = kc * 8 + u + w;
+                float kv = 0.f;
+                if (ok && kb * NLS_KB + ol_ < a.n_obs)
+                  kv = pair_eval_f32<FAM, DP>(x, pa, &so[ol_ * OBF], so[ol_ * OBF + DP], kp.os_f);
+                vv[w] = __fmul_rn(kv, a.kx_scale);
+              }
+              const __half h0 = __float2half_rn(vv[0]), h1 = __float2half_rn(vv[1]);
+              h2[u / 2] = __halves2half2(h0, h1);
+              l2[u / 2] = __halves2half2(__float2half_rn(__fsub_rn(vv[0], __half2float(h0))),
+                                         __float2half_rn(__fsub_rn(vv[1], __half2float(h1))));
+            }
+            sh[kc * GPV_MT] = *reinterpret_cast<const uint4*>(h2);
+            sl[kc * GPV_MT] = *reinterpret_cast<const uint4*>(l2);
+          }
+          mma::fence_proxy_async();
+          mma::mbar_arrive(&a_full[s]);
+        }
+      }
+    }
+  } else if (warp < GPF_GEN_WARPS + GPF_EPI_WARPS) {
+    // ======================================================================== epilogue
+    const int ew = warp - GPF_GEN_WARPS;
+    const int quarter = warp & 3, half = ew >> 2;   // TMEM lanes 32 (warp % 4) .. + 31
+    const int row = quarter * 32 + lane;
+    uint32_t use[2] = {0u, 0u};
+    for (int item = blockIdx.x; item < a.n_ptiles; item += gridDim.x) {
+      const int64_t p = (int64_t)item * GPV_MT + row;
+      double acc = 0.0;
+      for (int sw = 0; sw < n_sweeps; ++sw) {
+        for (int i = 0; i < 2; ++i) {
+          const int c = 2 * sw + i;
+          if (c >= n_ct) break;
+          mma::mbar_wait(&t_full[i], use[i] & 1u);
+          mma::tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + i * NT + half * (NT / 2);
+          const float* ti = sTinv + c * NT + half * (NT / 2);
+#pragma unroll 1
+          for (int cb = 0; cb < NT / 2; cb += 32) {
+            uint32_t v[32];
+            mma::tmem_ld32(taddr + cb, v);
+            mma::tmem_ld_wait();
+            float part = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) {
+              const float vo = __fmul_rn(__uint_as_float(v[cc]), ti[cb + cc]);
+              part = __fmaf_rn(vo, vo, part);
+            }
+            acc += (double)part;
+          }
+          mma::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mma::mbar_arrive(&t_empty[i]);
+          ++use[i];
+        }
+      }
+      if (half == 1) sComb[row] = acc;
+      mma::named_bar_sync(1, GPF_EPI_WARPS * 32);
+      if (half == 0 && p < a.n_points) a.var_out[p] = a.base - (acc + sComb[row]);
+      mma::named_bar_sync(2, GPF_EPI_WARPS * 32);
+    }
+  } else if (warp == GPF_GEN_WARPS + GPF_EPI_WARPS) {
+    // ======================================================================== L^-1 tile producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      const size_t b_tile = (size_t)(a.KP / 8) * NT * 8;
+      for (int item = blockIdx.x; item < a.n_ptiles; item += gridDim.x) {
+        for (int sw = 0; sw < n_sweeps; ++sw) {
+          const int c0 = 2 * sw, c1 = min(2 * sw + 1, n_ct - 1);
+          const int nkb0 = nkb_of(c0), nkb = nkb_of(c1);
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = it % NB;
+            mma::mbar_wait(&b_empty[s], ((it / NB) & 1u) ^ 1u);
+            unsigned char* st = smem + Cfg::OFF_B + (size_t)s * GPF_B_STAGE;
+            const bool two = (c1 != c0), first = kb < nkb0;
+            const int n_pieces = (first ? 2 : 0) + (two ? 2 : 0);
+            mma::mbar_expect_tx(&b_full[s], n_pieces * GPV_B_PIECE);
+            const size_t ko = (size_t)kb * (GPV_B_PIECE / 2);
+            if (first) {
+              mma::bulk_g2s(st, a.th + c0 * b_tile + ko, GPV_B_PIECE, &b_full[s]);
+              mma::bulk_g2s(st + GPV_B_PIECE, a.tl + c0 * b_tile + ko, GPV_B_PIECE, &b_full[s]);
+            }
+            if (two) {
+              mma::bulk_g2s(st + 2 * GPV_B_PIECE, a.th + c1 * b_tile + ko, GPV_B_PIECE, &b_full[s]);
+              mma::bulk_g2s(st + 3 * GPV_B_PIECE, a.tl + c1 * b_tile + ko, GPV_B_PIECE, &b_full[s]);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ======================================================================== MMA issuer
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+    uint32_t ita = 0, itb = 0, use[2] = {0u, 0u};
+    for (int item = blockIdx.x; item < a.n_ptiles; item += gridDim.x) {
+      for (int sw = 0; sw < n_sweeps; ++sw) {
+        const int c0 = 2 * sw, c1 = min(2 * sw + 1, n_ct - 1);
+        const bool two = (c1 != c0);
+        const int nkb0 = nkb_of(c0), nkb = nkb_of(c1);
+        mma::mbar_wait(&t_empty[0], (use[0] & 1u) ^ 1u);
+        if (two) mma::mbar_wait(&t_empty[1], (use[1] & 1u) ^ 1u);
+        mma::tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb, ++ita, ++itb) {
+          const int sa = ita % NA, sb = itb % NB;
+          mma::mbar_wait(&a_full[sa], (ita / NA) & 1u);
+          mma::mbar_wait(&b_full[sb], (itb / NB) & 1u);
+          mma::tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sta = mma::smem_u32(smem + Cfg::OFF_A + (size_t)sa * GPF_A_STAGE);
+            const uint32_t stb = mma::smem_u32(smem + Cfg::OFF_B + (size_t)sb * GPF_B_STAGE);
+            const uint32_t ahi = sta, alo = sta + GPV_A_PIECE;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              if (i == 0 ? kb >= nkb0 : !two) continue;
+              const uint32_t bhi = stb + (2 * i) * GPV_B_PIECE, blo = bhi + GPV_B_PIECE;
+              const uint32_t d = tmem_base + i * NT;
+#pragma unroll
+              for (int pr = 0; pr < 3; ++pr) {
+                const uint32_t aa = (pr == 0) ? alo : ahi;
+                const uint32_t bb = (pr == 1) ? blo : bhi;
+#pragma unroll
+                for (int ks = 0; ks < NLS_KB / 16; ++ks) {
+                  const uint64_t ad = mma::smem_desc(aa + ks * 2 * (GPV_MT * 16), GPV_MT * 16, 128);
+                  const uint64_t bd = mma::smem_desc(bb + ks * 2 * (NT * 16), NT * 16, 128);
+                  umma_f16(d, ad, bd, IDESC, (kb > 0 || pr > 0 || ks > 0) ? 1u : 0u);
+                }
+              }
+            }
+            mma::umma_commit(&a_empty[sa]);
+            mma::umma_commit(&b_empty[sb]);
+            if (kb == nkb0 - 1) mma::umma_commit(&t_full[0]);
+            if (two && kb == nkb - 1) mma::umma_commit(&t_full[1]);
+          }
+          __syncwarp();
+        }
+        ++use[0];
+        if (two) ++use[1];
+      }
+    }
+  }
+
+  mma::tc_fence_before();
+  __syncthreads();
+  if (warp == GPF_GEN_WARPS + GPF_EPI_WARPS + 1) {
+    mma::tc_fence_after();
+    mma::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int FAM, int DP>
+int launch_gpvar_fused_dp(basq_ctx* ctx, const KParams& kp, const GpfDev& dev) {
+  using Cfg = GpfCfg<DP>;
+  BASQ_CHECK((size_t)Cfg::SMEM_BYTES <= ctx->smem_optin, BASQ_ERR_UNSUPPORTED,
+             "gpvar: kernel needs %d B shared memory (limit %zu)", Cfg::SMEM_BYTES, ctx->smem_optin);
+  if (dev.n_ptiles <= 0) return BASQ_OK;
+  BASQ_CUDA(cudaFuncSetAttribute(gpvar_fused_kernel<FAM, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  gpvar_fused_kernel<FAM, DP><<<std::min(ctx->num_sms, dev.n_ptiles), GPF_THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(kp, dev);
+  ctx->launches++;
+  BASQ_CUDA(cudaGetLastError());
+  return BASQ_OK;
+}
+
+template <int FAM>
+int launch_gpvar_fused_family(basq_ctx* ctx, const KParams& kp, const GpfDev& dev) {
+  switch (kp.dp) {
+    case 2: return launch_gpvar_fused_dp<FAM, 2>(ctx, kp, dev);
+    case 4: return launch_gpvar_fused_dp<FAM, 4>(ctx, kp, dev);
+    case 6: return launch_gpvar_fused_dp<FAM, 6>(ctx, kp, dev);
+    case 8: return launch_gpvar_fused_dp<FAM, 8>(ctx, kp, dev);
+    case 10: return launch_gpvar_fused_dp<FAM, 10>(ctx, kp, dev);
+    case 12: return launch_gpvar_fused_dp<FAM, 12>(ctx, kp, dev);
+    case 16: return launch_gpvar_fused_dp<FAM, 16>(ctx, kp, dev);
+    case 20: return launch_gpvar_fused_dp<FAM, 20>(ctx, kp, dev);
+    case 24: return launch_gpvar_fused_dp<FAM, 24>(ctx, kp, dev);
+    case 32: return launch_gpvar_fused_dp<FAM, 32>(ctx, kp, dev);
+  }
+  set_error("gpvar: no kernel compiled for padded dimension %d", kp.dp);
+  return BASQ_ERR_UNSUPPORTED;
+}
+
+int launch_gpvar_fused_rbf(basq_ctx*, const KParams&, const GpfDev&);
+int launch_gpvar_fused_m15(basq_ctx*, const KParams&, const GpfDev&);
+int launch_gpvar_fused_m25(basq_ctx*, const KParams&, const GpfDev&);
+
 // k(Xobs, x) of a chunk of raw candidates as the A operand ([tile of 128][KP / 8][128][8] fp16 hi / lo);
 // one CTA per tile, one thread per candidate.
 struct KxpDev {

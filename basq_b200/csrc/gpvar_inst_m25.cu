@@ -1,7 +1,10 @@
-// kxgen_points_kernel instantiations: m25 (see gpvar.cuh)
+// gpvar_fused_kernel / kxgen_points_kernel instantiations: m25 (see gpvar.cuh)
 #include "gpvar.cuh"
 namespace basq {
 int launch_kxgen_points_m25(basq_ctx* ctx, const KParams& kp, const KxpDev& kx, int n_ptiles) {
   return launch_kxgen_points_family<BASQ_MATERN25>(ctx, kp, kx, n_ptiles);
+}
+int launch_gpvar_fused_m25(basq_ctx* ctx, const KParams& kp, const GpfDev& dev) {
+  return launch_gpvar_fused_family<BASQ_MATERN25>(ctx, kp, dev);
 }
 }  // namespace basq
