@@ -206,18 +206,19 @@ __global__ void __launch_bounds__(NLS_THREADS, 1) gpvar_kernel(const GpvDev a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fully fused version: k(Xobs, x) never leaves the SM.  Four generator warps (one thread per candidate of
+// Fully fused version: k(Xobs, x) never leaves the SM.  Eight generator warps (two threads per candidate of
 // the tile) evaluate the kernel values of one 32-observation K block, split them into fp16 hi / lo and
 // store them straight into the A stage in the tcgen05 K-major layout; the MMA warp contracts the stage
 // against the L^-1 tiles of TWO observation column tiles at once (two 256-column accumulators = all of
 // TMEM), so a K block is generated once per pair of column tiles (1.5x the unique evaluations at four
 // column tiles; they cost a third of the MMA time and hide under it).  DRAM traffic: the candidates in
 // (4 d B each), the variances out (8 B each).
-//   warps 0-3   generators          warps 4-11  epilogue (TMEM lane quarter = warp % 4, two column halves)
-//   warp 12     L^-1 tile producer (cp.async.bulk, 64 KB stages: hi / lo of two column tiles)
-//   warp 13     TMEM allocation + tcgen05.mma issue
+//   warps 0-7   generators (measured: four warps generate as slowly as the MMAs run; eight hide under them)
+//   warps 8-15  epilogue (TMEM lane quarter = warp % 4, two column halves)
+//   warp 16     L^-1 tile producer (cp.async.bulk, 64 KB stages: hi / lo of two column tiles)
+//   warp 17     TMEM allocation + tcgen05.mma issue
 // ---------------------------------------------------------------------------------------------
-constexpr int GPF_GEN_WARPS = 4, GPF_EPI_WARPS = 8;
+constexpr int GPF_GEN_WARPS = 8, GPF_EPI_WARPS = 8;   // two generator threads per candidate row (16 of a K block's 32 observations each)
 constexpr int GPF_THREADS = (GPF_GEN_WARPS + GPF_EPI_WARPS + 2) * 32;
 constexpr int GPF_A_STAGE = 2 * GPV_A_PIECE;          // hi + lo of one generated K block: 16 KB
 constexpr int GPF_B_STAGE = 4 * GPV_B_PIECE;          // hi + lo of two column tiles: 64 KB
@@ -238,7 +239,7 @@ struct GpfDev {
 template <int DP>
 struct GpfCfg {
   static constexpr int NA = 3, NB = 2;
-  static constexpr int OBF = DP + 1;                                 // floats per observation (zz, b)
+  static constexpr int OBF = (DP + 1 + 3) / 4 * 4;                   // floats per observation (zz[DP], b, padding): 128-bit loads
   static constexpr int OFF_A = 0;
   static constexpr int OFF_B = OFF_A + NA * GPF_A_STAGE;
   static constexpr int OFF_OBS = OFF_B + NB * GPF_B_STAGE;           // [2][32][OBF] floats
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(GPF_THREADS, 1) gpvar_fused_kernel(KParams kp,
 
   if (warp < GPF_GEN_WARPS) {
     // ======================================================================== generators
-    const int r = tid;   // candidate row of the tile
+    const int r = tid & (GPV_MT - 1), part = tid >> 7;   // candidate row of the tile, half of the K block
     uint32_t it = 0, ob = 0;
     for (int item = blockIdx.x; item < a.n_ptiles; item += gridDim.x) {
       const int64_t p = (int64_t)item * GPV_MT + r;
@@ -321,9 +322,9 @@ __global__ void __launch_bounds__(GPF_THREADS, 1) gpvar_fused_kernel(KParams kp,
         for (int kb = 0; kb < nkb; ++kb, ++it, ++ob) {
           // the K block's observations -> shared memory (double-buffered among the generator warps)
           float* so = sObs + (ob & 1u) * (NLS_KB * OBF);
-          for (int i = r; i < NLS_KB * OBF; i += GPF_GEN_WARPS * 32) {
+          for (int i = tid; i < NLS_KB * OBF; i += GPF_GEN_WARPS * 32) {
             const int o = kb * NLS_KB + i / OBF, j = i % OBF;
-            so[i] = o < a.n_obs ? (j < DP ? a.ozz[(size_t)o * DP + j] : a.obz[o]) : 0.f;
+            so[i] = (o < a.n_obs && j <= DP) ? (j < DP ? a.ozz[(size_t)o * DP + j] : a.obz[o]) : 0.f;
           }
           mma::named_bar_sync(3, GPF_GEN_WARPS * 32);
           const int s = it % NA;
@@ -331,7 +332,8 @@ __global__ void __launch_bounds__(GPF_THREADS, 1) gpvar_fused_kernel(KParams kp,
           uint4* sh = reinterpret_cast<uint4*>(smem + Cfg::OFF_A + (size_t)s * GPF_A_STAGE) + r;
           uint4* sl = sh + GPV_A_PIECE / 16;
 #pragma unroll
-          for (int kc = 0; kc < NLS_KB / 8; ++kc) {
+          for (int kq = 0; kq < NLS_KB / 16; ++kq) {
+            const int kc = part * (NLS_KB / 16) + kq;
             __half2 h2[4], l2[4];
 #pragma unroll
             for (int u = 0; u < 8; u += 2) {
@@ -339,15 +341,25 @@ __global__ void __launch_bounds__(GPF_THREADS, 1) gpvar_fused_kernel(KParams kp,
 #pragma unroll
               for (int w = 0; w < 2; ++w) {
                 const int ol_ = kc * 8 + u + w;
-                float kv = 0.f;
-                if (ok && kb * NLS_KB + ol_ < a.n_obs)
-                  kv = pair_eval_f32<FAM, DP>(x, pa, &so[ol_ * OBF], so[ol_ * OBF + DP], kp.os_f);
+                // the observation's coordinates arrive as broadcast 128-bit loads (scalar loads made the
+                // generators LSU-bound: 11 wavefronts per evaluation next to the MMAs' own operand reads)
+                float zo[OBF];
+#pragma unroll
+                for (int q4 = 0; q4 < OBF / 4; ++q4) {
+                  const float4 w4 = *reinterpret_cast<const float4*>(&so[ol_ * OBF + q4 * 4]);
+                  zo[q4 * 4 + 0] = w4.x; zo[q4 * 4 + 1] = w4.y; zo[q4 * 4 + 2] = w4.z; zo[q4 * 4 + 3] = w4.w;
+                }
+                float kv = pair_eval_f32<FAM, DP>(x, pa, zo, zo[DP], kp.os_f);
+                kv = (ok && kb * NLS_KB + ol_ < a.n_obs) ? kv : 0.f;
                 vv[w] = __fmul_rn(kv, a.kx_scale);
               }
-              const __half h0 = __float2half_rn(vv[0]), h1 = __float2half_rn(vv[1]);
-              h2[u / 2] = __halves2half2(h0, h1);
-              l2[u / 2] = __halves2half2(__float2half_rn(__fsub_rn(vv[0], __half2float(h0))),
-                                         __float2half_rn(__fsub_rn(vv[1], __half2float(h1))));
+              // hi = the value truncated to 11 significant bits (a mask, exactly representable in fp16), lo =
+              // the exact fp32 remainder rounded to fp16; packed pair conversions only (scalar
+              // float <-> half conversions share the 16-lane pipe of the ex2 and made it the bound)
+              const float t0 = __uint_as_float(__float_as_uint(vv[0]) & 0xFFFFE000u);
+              const float t1 = __uint_as_float(__float_as_uint(vv[1]) & 0xFFFFE000u);
+              h2[u / 2] = __floats2half2_rn(t0, t1);
+              l2[u / 2] = __floats2half2_rn(__fsub_rn(vv[0], t0), __fsub_rn(vv[1], t1));
             }
             sh[kc * GPV_MT] = *reinterpret_cast<const uint4*>(h2);
             sl[kc * GPV_MT] = *reinterpret_cast<const uint4*>(l2);
