@@ -421,8 +421,9 @@ int nls_set_sums(basq_ctx* ctx, const KParams& kp, int nl, NlOperands* op, const
                  const LmView& lmobs, int64_t off, int S, int64_t p_lo, int64_t p_hi, double* G, int64_t ldg);
 
 // gpvar.cu: fused posterior variance on the tensor cores (fp32 inputs)
+// mean_out != NULL: the fused kernel also writes the posterior mean (*mean_done tells whether it did)
 int gp_variance_tc(basq_ctx* ctx, const basq_kernel_desc* desc, const KParams& kp, const LmView& lmobs, const void* X,
-                   int64_t N, double* var_out);
+                   int64_t N, double* var_out, double* mean_out = nullptr, bool* mean_done = nullptr);
 
 // dgemm.cu
 int dgemm(basq_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const double* A, int64_t lda,

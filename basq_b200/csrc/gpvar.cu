@@ -21,7 +21,8 @@ __global__ void zero_upper_kernel(double* __restrict__ A, int n) {
 
 // var_out[N] = sigma_f^2 + sigma_n^2 - k_x^T W k_x for fp32 candidates X [N, d]
 int gp_variance_tc(basq_ctx* ctx, const basq_kernel_desc* desc, const KParams& kp, const LmView& lmobs, const void* X,
-                   int64_t N, double* var_out) {
+                   int64_t N, double* var_out, double* mean_out, bool* mean_done) {
+  if (mean_done) *mean_done = false;
   BASQ_CHECK(desc->dtype == BASQ_F32 && lmobs.dtype == BASQ_F32, BASQ_ERR_INVALID, "gpvar: fp32 inputs only");
   const int n_obs = desc->n_obs;
   const int KP = ceil_div(n_obs, GPV_NT) * GPV_NT;
@@ -72,6 +73,10 @@ int gp_variance_tc(basq_ctx* ctx, const basq_kernel_desc* desc, const KParams& k
     f.tinv = tinv.as<float>();
     f.base = desc->outputscale + desc->noise;
     f.var_out = var_out;
+    f.alpha = desc->alpha;          // the posterior mean rides along: its kernel values are the same ones
+    f.mean_c0 = desc->mean_const;
+    f.mean_out = mean_out;
+    if (mean_done) *mean_done = mean_out != nullptr;
     switch (kp.family) {
       case BASQ_RBF: BASQ_TRY(launch_gpvar_fused_rbf(ctx, kp, f)); break;
       case BASQ_MATERN15: BASQ_TRY(launch_gpvar_fused_m15(ctx, kp, f)); break;

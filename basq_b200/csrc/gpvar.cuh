@@ -215,13 +215,13 @@ __global__ void __launch_bounds__(NLS_THREADS, 1) gpvar_kernel(const GpvDev a) {
 // (4 d B each), the variances out (8 B each).
 //   warps 0-7   generators (measured: four warps generate as slowly as the MMAs run; eight hide under them)
 //   warps 8-15  epilogue (TMEM lane quarter = warp % 4, two column halves)
-//   warp 16     L^-1 tile producer (cp.async.bulk, 64 KB stages: hi / lo of two column tiles)
+//   warp 16     L^-1 tile producer (cp.async.bulk, 32 KB units: hi / lo of one column tile's K block)
 //   warp 17     TMEM allocation + tcgen05.mma issue
 // ---------------------------------------------------------------------------------------------
 constexpr int GPF_GEN_WARPS = 8, GPF_EPI_WARPS = 8;   // two generator threads per candidate row (16 of a K block's 32 observations each)
 constexpr int GPF_THREADS = (GPF_GEN_WARPS + GPF_EPI_WARPS + 2) * 32;
 constexpr int GPF_A_STAGE = 2 * GPV_A_PIECE;          // hi + lo of one generated K block: 16 KB
-constexpr int GPF_B_STAGE = 4 * GPV_B_PIECE;          // hi + lo of two column tiles: 64 KB
+constexpr int GPF_B_STAGE = 2 * GPV_B_PIECE;          // hi + lo of ONE column tile's K block: 32 KB
 
 struct GpfDev {
   const float* X;          // [n_points, d] raw candidates
@@ -234,19 +234,26 @@ struct GpfDev {
   const float* tinv;                      // [KP]
   double base;
   double* var_out;
+  const double* alpha;                    // [n_obs] mean cache, or NULL
+  double mean_c0;                         // mean constant
+  double* mean_out;                       // [n_points] posterior mean c0 + sum_o alpha_o k(xobs_o, x), or NULL
 };
 
 template <int DP>
 struct GpfCfg {
-  static constexpr int NA = 3, NB = 2;
+  // L^-1 pieces stream from L2 at the chip-wide cap (43 B/clk per SM): five 32 KB units in flight cover
+  // ~3800 tensor-pipe cycles of latency (two 64 KB stages covered 1536 and left the pipe 47 % busy)
+  static constexpr int NA = 2, NB = 5;
   static constexpr int OBF = (DP + 1 + 3) / 4 * 4;                   // floats per observation (zz[DP], b, padding): 128-bit loads
   static constexpr int OFF_A = 0;
   static constexpr int OFF_B = OFF_A + NA * GPF_A_STAGE;
   static constexpr int OFF_OBS = OFF_B + NB * GPF_B_STAGE;           // [2][32][OBF] floats
   static constexpr int OBS_BYTES = ((2 * NLS_KB * OBF * 4) + 15) / 16 * 16;
-  static constexpr int OFF_TINV = OFF_OBS + OBS_BYTES;
+  static constexpr int OFF_ALPHA = OFF_OBS + OBS_BYTES;               // [2][32] doubles (mean cache of a K block)
+  static constexpr int OFF_TINV = OFF_ALPHA + 2 * NLS_KB * 8;
   static constexpr int OFF_COMB = OFF_TINV + GpvCfg::MAX_KP * 4;
-  static constexpr int OFF_BAR = OFF_COMB + 128 * 8;
+  static constexpr int OFF_MEAN = OFF_COMB + 128 * 8;                 // [128] doubles: second generator thread's part
+  static constexpr int OFF_BAR = OFF_MEAN + 128 * 8;
   static constexpr int SMEM_BYTES = OFF_BAR + 256;
   static_assert(SMEM_BYTES <= 227 * 1024, "gpvar (fused): shared memory budget");
 };
@@ -259,9 +266,11 @@ __global__ void __launch_bounds__(GPF_THREADS, 1) gpvar_fused_kernel(KParams kp,
   unsigned char* const smem = smem_gpf;
   float* sObs = reinterpret_cast<float*>(smem + Cfg::OFF_OBS);
   float* sTinv = reinterpret_cast<float*>(smem + Cfg::OFF_TINV);
+  double* sAlpha = reinterpret_cast<double*>(smem + Cfg::OFF_ALPHA);
+  double* sMean = reinterpret_cast<double*>(smem + Cfg::OFF_MEAN);
   double* sComb = reinterpret_cast<double*>(smem + Cfg::OFF_COMB);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-  uint64_t* a_full = bars;                 // [NA] 128 generator threads
+  uint64_t* a_full = bars;                 // [NA] generator threads
   uint64_t* a_empty = a_full + NA;         // [NA] MMA commit
   uint64_t* b_full = a_empty + NA;         // [NB] tx
   uint64_t* b_empty = b_full + NB;         // [NB] MMA commit
@@ -300,7 +309,15 @@ __global__ void __launch_bounds__(GPF_THREADS, 1) gpvar_fused_kernel(KParams kp,
   if (warp < GPF_GEN_WARPS) {
     // ======================================================================== generators
     const int r = tid & (GPV_MT - 1), part = tid >> 7;   // candidate row of the tile, half of the K block
+    constexpr int OBS_PER_THREAD = (NLS_KB * OBF + GPF_GEN_WARPS * 32 - 1) / (GPF_GEN_WARPS * 32);
     uint32_t it = 0, ob = 0;
+    for (int i = tid; i < NLS_KB * OBF; i += GPF_GEN_WARPS * 32) {   // K block 0 -> buffer 0
+      const int o = i / OBF, j = i % OBF;
+      sObs[i] = (o < a.n_obs && j <= DP) ? (j < DP ? a.ozz[(size_t)o * DP + j] : a.obz[o]) : 0.f;
+    }
+    const bool want_mean = a.mean_out != nullptr;
+    if (want_mean && tid < NLS_KB) sAlpha[tid] = tid < a.n_obs ? a.alpha[tid] : 0.0;
+    mma::named_bar_sync(3, GPF_GEN_WARPS * 32);
     for (int item = blockIdx.x; item < a.n_ptiles; item += gridDim.x) {
       const int64_t p = (int64_t)item * GPV_MT + r;
       const bool ok = p < a.n_points;
@@ -316,17 +333,29 @@ __global__ void __launch_bounds__(GPF_THREADS, 1) gpvar_fused_kernel(KParams kp,
         for (int i = 0; i < DP; ++i) x[i] = xl[i];
         pa = point_a_term(kp, nrm);
       }
+      double msum = 0.0;   // posterior mean: accumulated in the last sweep, which visits every K block
       for (int sw = 0; sw < n_sweeps; ++sw) {
         const int c_last = min(2 * sw + 1, n_ct - 1);
         const int nkb = nkb_of(c_last);
+        const bool acc_mean = want_mean && sw == n_sweeps - 1;
         for (int kb = 0; kb < nkb; ++kb, ++it, ++ob) {
-          // the K block's observations -> shared memory (double-buffered among the generator warps)
-          float* so = sObs + (ob & 1u) * (NLS_KB * OBF);
-          for (int i = tid; i < NLS_KB * OBF; i += GPF_GEN_WARPS * 32) {
-            const int o = kb * NLS_KB + i / OBF, j = i % OBF;
-            so[i] = (o < a.n_obs && j <= DP) ? (j < DP ? a.ozz[(size_t)o * DP + j] : a.obz[o]) : 0.f;
+          // The NEXT K block's observations are fetched into registers now and stored to the other
+          // shared-memory buffer after this block's evaluations (an unprefetched fetch exposed ~800 cycles
+          // of global-load latency per K block: long-scoreboard stalls, tensor pipe 47 % busy).  The
+          // sequence of K blocks restarts at 0 with every sweep, so the block after the last one is block 0.
+          const float* so = sObs + (ob & 1u) * (NLS_KB * OBF);
+          float* so_next = sObs + ((ob + 1u) & 1u) * (NLS_KB * OBF);
+          const int kb_next = (kb + 1 < nkb) ? kb + 1 : 0;
+          float pre[OBS_PER_THREAD];
+#pragma unroll
+          for (int u = 0; u < OBS_PER_THREAD; ++u) {
+            const int i = tid + u * (GPF_GEN_WARPS * 32);
+            const int o = kb_next * NLS_KB + i / OBF, j = i % OBF;
+            pre[u] = (i < NLS_KB * OBF && o < a.n_obs && j <= DP) ? (j < DP ? a.ozz[(size_t)o * DP + j] : a.obz[o]) : 0.f;
           }
-          mma::named_bar_sync(3, GPF_GEN_WARPS * 32);
+          const double* sal = sAlpha + (ob & 1u) * NLS_KB;
+          double pre_alpha = 0.0;
+          if (want_mean && tid < NLS_KB && kb_next * NLS_KB + tid < a.n_obs) pre_alpha = a.alpha[kb_next * NLS_KB + tid];
           const int s = it % NA;
           mma::mbar_wait(&a_empty[s], ((it / NA) & 1u) ^ 1u);
           uint4* sh = reinterpret_cast<uint4*>(smem + Cfg::OFF_A + (size_t)s * GPF_A_STAGE) + r;
@@ -351,6 +380,7 @@ __global__ void __launch_bounds__(GPF_THREADS, 1) gpvar_fused_kernel(KParams kp,
                 }
                 float kv = pair_eval_f32<FAM, DP>(x, pa, zo, zo[DP], kp.os_f);
                 kv = (ok && kb * NLS_KB + ol_ < a.n_obs) ? kv : 0.f;
+                if (acc_mean) msum = fma(f2d_pos(kv), sal[ol_], msum);   // padded observations carry alpha = 0
                 vv[w] = __fmul_rn(kv, a.kx_scale);
               }
               // hi = the value truncated to 11 significant bits (a mask, exactly representable in fp16), lo =
@@ -366,7 +396,21 @@ __global__ void __launch_bounds__(GPF_THREADS, 1) gpvar_fused_kernel(KParams kp,
           }
           mma::fence_proxy_async();
           mma::mbar_arrive(&a_full[s]);
+#pragma unroll
+          for (int u = 0; u < OBS_PER_THREAD; ++u) {
+            const int i = tid + u * (GPF_GEN_WARPS * 32);
+            if (i < NLS_KB * OBF) so_next[i] = pre[u];
+          }
+          if (want_mean && tid < NLS_KB) sAlpha[((ob + 1u) & 1u) * NLS_KB + tid] = pre_alpha;
+          mma::named_bar_sync(3, GPF_GEN_WARPS * 32);
         }
+      }
+      if (want_mean) {
+        // the two generator threads of a row each summed half of every K block's observations
+        if (part == 1) sMean[r] = msum;
+        mma::named_bar_sync(3, GPF_GEN_WARPS * 32);
+        if (part == 0 && ok) a.mean_out[p] = a.mean_c0 + (msum + sMean[r]);
+        mma::named_bar_sync(3, GPF_GEN_WARPS * 32);
       }
     }
   } else if (warp < GPF_GEN_WARPS + GPF_EPI_WARPS) {
@@ -419,21 +463,20 @@ __global__ void __launch_bounds__(GPF_THREADS, 1) gpvar_fused_kernel(KParams kp,
         for (int sw = 0; sw < n_sweeps; ++sw) {
           const int c0 = 2 * sw, c1 = min(2 * sw + 1, n_ct - 1);
           const int nkb0 = nkb_of(c0), nkb = nkb_of(c1);
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
-            const int s = it % NB;
-            mma::mbar_wait(&b_empty[s], ((it / NB) & 1u) ^ 1u);
-            unsigned char* st = smem + Cfg::OFF_B + (size_t)s * GPF_B_STAGE;
-            const bool two = (c1 != c0), first = kb < nkb0;
-            const int n_pieces = (first ? 2 : 0) + (two ? 2 : 0);
-            mma::mbar_expect_tx(&b_full[s], n_pieces * GPV_B_PIECE);
+          for (int kb = 0; kb < nkb; ++kb) {
+            const bool two = (c1 != c0);
             const size_t ko = (size_t)kb * (GPV_B_PIECE / 2);
-            if (first) {
-              mma::bulk_g2s(st, a.th + c0 * b_tile + ko, GPV_B_PIECE, &b_full[s]);
-              mma::bulk_g2s(st + GPV_B_PIECE, a.tl + c0 * b_tile + ko, GPV_B_PIECE, &b_full[s]);
-            }
-            if (two) {
-              mma::bulk_g2s(st + 2 * GPV_B_PIECE, a.th + c1 * b_tile + ko, GPV_B_PIECE, &b_full[s]);
-              mma::bulk_g2s(st + 3 * GPV_B_PIECE, a.tl + c1 * b_tile + ko, GPV_B_PIECE, &b_full[s]);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              if (i == 0 ? kb >= nkb0 : !two) continue;
+              const int c = i == 0 ? c0 : c1;
+              const int s = it % NB;
+              mma::mbar_wait(&b_empty[s], ((it / NB) & 1u) ^ 1u);
+              unsigned char* st = smem + Cfg::OFF_B + (size_t)s * GPF_B_STAGE;
+              mma::mbar_expect_tx(&b_full[s], GPF_B_STAGE);
+              mma::bulk_g2s(st, a.th + c * b_tile + ko, GPV_B_PIECE, &b_full[s]);
+              mma::bulk_g2s(st + GPV_B_PIECE, a.tl + c * b_tile + ko, GPV_B_PIECE, &b_full[s]);
+              ++it;
             }
           }
         }
@@ -451,19 +494,19 @@ __global__ void __launch_bounds__(GPF_THREADS, 1) gpvar_fused_kernel(KParams kp,
         mma::mbar_wait(&t_empty[0], (use[0] & 1u) ^ 1u);
         if (two) mma::mbar_wait(&t_empty[1], (use[1] & 1u) ^ 1u);
         mma::tc_fence_after();
-        for (int kb = 0; kb < nkb; ++kb, ++ita, ++itb) {
-          const int sa = ita % NA, sb = itb % NB;
+        for (int kb = 0; kb < nkb; ++kb, ++ita) {
+          const int sa = ita % NA;
           mma::mbar_wait(&a_full[sa], (ita / NA) & 1u);
-          mma::mbar_wait(&b_full[sb], (itb / NB) & 1u);
-          mma::tc_fence_after();
-          if (lane == 0) {
-            const uint32_t sta = mma::smem_u32(smem + Cfg::OFF_A + (size_t)sa * GPF_A_STAGE);
-            const uint32_t stb = mma::smem_u32(smem + Cfg::OFF_B + (size_t)sb * GPF_B_STAGE);
-            const uint32_t ahi = sta, alo = sta + GPV_A_PIECE;
+          const uint32_t sta = mma::smem_u32(smem + Cfg::OFF_A + (size_t)sa * GPF_A_STAGE);
+          const uint32_t ahi = sta, alo = sta + GPV_A_PIECE;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              if (i == 0 ? kb >= nkb0 : !two) continue;
-              const uint32_t bhi = stb + (2 * i) * GPV_B_PIECE, blo = bhi + GPV_B_PIECE;
+          for (int i = 0; i < 2; ++i) {
+            if (i == 0 ? kb >= nkb0 : !two) continue;
+            const int sb = itb % NB;
+            mma::mbar_wait(&b_full[sb], (itb / NB) & 1u);
+            mma::tc_fence_after();
+            if (lane == 0) {
+              const uint32_t bhi = mma::smem_u32(smem + Cfg::OFF_B + (size_t)sb * GPF_B_STAGE), blo = bhi + GPV_B_PIECE;
               const uint32_t d = tmem_base + i * NT;
 #pragma unroll
               for (int pr = 0; pr < 3; ++pr) {
@@ -476,9 +519,13 @@ __global__ void __launch_bounds__(GPF_THREADS, 1) gpvar_fused_kernel(KParams kp,
                   umma_f16(d, ad, bd, IDESC, (kb > 0 || pr > 0 || ks > 0) ? 1u : 0u);
                 }
               }
+              mma::umma_commit(&b_empty[sb]);
             }
+            __syncwarp();
+            ++itb;
+          }
+          if (lane == 0) {
             mma::umma_commit(&a_empty[sa]);
-            mma::umma_commit(&b_empty[sb]);
             if (kb == nkb0 - 1) mma::umma_commit(&t_full[0]);
             if (two && kb == nkb - 1) mma::umma_commit(&t_full[1]);
           }

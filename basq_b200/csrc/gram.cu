@@ -257,10 +257,16 @@ int landmark_dot(basq_ctx* ctx, const KParams& kp, const LmView& lm, const doubl
 int gp_predict_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const KParams& kp, const LmView& lmobs,
                     const void* X, int64_t N, double* mean_out, double* var_out) {
   PhaseTimer timer(ctx, PH_GP);
+  { const char* t = getenv("BASQ_GPVAR"); ctx->no_gpvar = t && t[0] == '0'; }
+  if (var_out && N > 0 && desc->dtype == BASQ_F32 && !ctx->no_gpvar) {
+    // fused tensor-core kernel: variance, and the mean from the same kernel values
+    bool mean_done = false;
+    BASQ_TRY(gp_variance_tc(ctx, desc, kp, lmobs, X, N, var_out, mean_out, &mean_done));
+    if (mean_out && !mean_done) BASQ_TRY(landmark_dot(ctx, kp, lmobs, desc->alpha, desc->mean_const, X, N, mean_out));
+    return BASQ_OK;
+  }
   if (mean_out) BASQ_TRY(landmark_dot(ctx, kp, lmobs, desc->alpha, desc->mean_const, X, N, mean_out));
   if (!var_out || N == 0) return BASQ_OK;
-  { const char* t = getenv("BASQ_GPVAR"); ctx->no_gpvar = t && t[0] == '0'; }
-  if (desc->dtype == BASQ_F32 && !ctx->no_gpvar) return gp_variance_tc(ctx, desc, kp, lmobs, X, N, var_out);
   const int n_obs = desc->n_obs;
   // chunk so that V and Y (n_obs x P fp64 each) stay around 512 MB (large GEMMs: fewer, fuller waves)
   int64_t P = (int64_t)(512ll << 20) / (8ll * n_obs);
