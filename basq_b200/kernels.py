@@ -121,8 +121,23 @@ def _model_caches(model):
         model(Xobs[:1])
         ps = model.prediction_strategy
     S = ps.covar_cache
-    W = S.double() @ S.double().T
-    return Xobs, W, ps.mean_cache.double().reshape(-1)
+    return Xobs, _outer_gram(S), ps.mean_cache.double().reshape(-1)
+
+
+def _outer_gram(S):
+    """W = S S^T in fp64 (BASQ/_gp.py:251: woodbury_inv = S @ S.T).  For a CUDA tensor the product runs in
+    the library's own DMMA GEMM (basq_dgemm), not in torch.matmul / cuBLAS: the caches are rebuilt on
+    every recombination() call of a freshly updated GP, i.e. on the path this library replaces."""
+    S64 = S.detach().double().contiguous()
+    if not S64.is_cuda:
+        return S64 @ S64.T
+    import ctypes as C
+    ctx = _lib.context_for(S64.device)
+    n, r = S64.shape
+    W = torch.empty(n, n, dtype=torch.float64, device=S64.device)
+    _lib.check(_lib.lib.basq_dgemm(ctx.handle, 0, 1, n, n, r, C.c_double(1.0), S64.data_ptr(), r, S64.data_ptr(), r,
+                                   C.c_double(0.0), W.data_ptr(), n))
+    return W
 
 
 def spec_from_model(model, mode, diag_add=0.0, offset=0.0) -> KernelSpec:
