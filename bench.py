@@ -91,31 +91,78 @@ def config_of(a, world):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region, every 100 ms from a background thread.
+    In-process NVML (nvidia_ml_py) when available: forking `nvidia-smi` five times a second from every rank
+    perturbs the host-side loop of an 8-rank run (the Nystrom phase measured 36 instead of 21 ms);
+    `nvidia-smi` is the fallback.  Only rank 0 samples (it prints the line)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.stop = index, [], threading.Event()
+    def __init__(self, index, enabled=True):
+        self.index, self.rows, self.stop, self.enabled = index, [], threading.Event(), enabled
         self.t = threading.Thread(target=self._run, daemon=True)
+        self.nvml = None
+        if enabled:
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                # CUDA_VISIBLE_DEVICES may renumber the devices: resolve through the PCI address of the torch device
+                try:
+                    self.handle = self._by_bus(pynvml, index)
+                except Exception:
+                    self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+                self.nvml = pynvml
+            except Exception:
+                self.nvml = None
+
+    @staticmethod
+    def _by_bus(pynvml, index):
+        p = torch.cuda.get_device_properties(index)
+        want = (int(p.pci_domain_id), int(p.pci_bus_id), int(p.pci_device_id))
+        for i in range(pynvml.nvmlDeviceGetCount()):
+            h = pynvml.nvmlDeviceGetHandleByIndex(i)
+            info = pynvml.nvmlDeviceGetPciInfo(h)
+            if (int(info.domain), int(info.bus), int(info.device)) == want:
+                return h
+        return pynvml.nvmlDeviceGetHandleByIndex(index)
+
+    def _sample_nvml(self):
+        n, h = self.nvml, self.handle
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        pw = n.nvmlDeviceGetPowerUsage(h) / 1e3
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        r = int(get(h))
+        bit = lambda name, alt: int(getattr(n, name, getattr(n, alt, 0)))
+        flags = [("hw_slowdown", bit("nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown")),
+                 ("hw_thermal_slowdown", bit("nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown")),
+                 ("sw_thermal_slowdown", bit("nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown")),
+                 ("sw_power_cap", bit("nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"))]
+        return [str(sm), str(mx), f"{pw:.1f}"] + ["Active" if (m and (r & m)) else "Not Active" for _, m in flags]
 
     def _run(self):
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                    self.rows.append([c.strip() for c in out.strip().split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.1 if self.nvml is not None else 0.2)
 
     def __enter__(self):
-        self.t.start()
+        if self.enabled:
+            self.t.start()
         return self
 
     def __exit__(self, *exc):
         self.stop.set()
-        self.t.join(timeout=6)
+        if self.enabled:
+            self.t.join(timeout=6)
 
     def summary(self):
         sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
@@ -127,7 +174,8 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -448,7 +496,7 @@ def run_ours(a, rank, world, local_rank):
     ctx.profile(True)
     ctx.profile_read(reset=True)
     launches0, pe0 = ctx.launches, ctx.pair_evals
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(local_rank, enabled=(rank == 0)) as clk:
         ms_step, out = timed(step_device, a.steps)
     launches = ctx.launches - launches0
     pairs_step = (ctx.pair_evals - pe0) / a.steps
