@@ -26,6 +26,8 @@
 // Pipelines (mbarriers): B stages full/empty (3-deep ring), TMEM accumulators full/empty (2 buffers),
 // A tiles full/empty.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace basq {
@@ -46,17 +48,30 @@ struct SetSumMmaDev {
   int accumulate;
 };
 
+// BASQ_SETSUM_F16 = 1 (default): the split operands are fp16 (kind::f16, K = 16 per MMA) instead of tf32
+// (kind::tf32, K = 8): the same 11 significant bits per piece, half the bytes, 3 instead of 5 MMAs per
+// 128 x 256 tile at d = 10.  fp16's range is enough for centred, lengthscale-scaled coordinates (values
+// beyond +-6e4 are clamped: such pairs have k = 0 either way); pieces below 6e-5 lose bits to the
+// subnormal spacing 6e-8, an absolute 3e-8 |zz| per term of the argument - below its fp32 rounding.
+#ifndef BASQ_SETSUM_F16
+#define BASQ_SETSUM_F16 1
+#endif
+
 template <int DP>
 struct MmaCfg {
-  static constexpr int KA = (3 * DP + 6 + 7) / 8 * 8;  // K columns (multiple of the tf32 MMA K = 8)
-  static constexpr int NT = KA <= 40 ? 256 : 128;      // points per tile (MMA N)
-  static constexpr int MT = KA > 80 ? 1 : 2;           // landmark tiles (of 128) per work item
+  static constexpr bool F16 = BASQ_SETSUM_F16 != 0;
+  static constexpr int KSTEP = F16 ? 16 : 8;           // K of one MMA
+  static constexpr int ESZ = F16 ? 2 : 4;              // bytes per operand element
+  static constexpr int CH = 16 / ESZ;                  // elements per 16-byte K chunk
+  static constexpr int KA = (3 * DP + 6 + KSTEP - 1) / KSTEP * KSTEP;  // K columns (multiple of the MMA K)
+  static constexpr int NT = KA * ESZ <= 160 ? 256 : 128;  // points per tile (MMA N)
+  static constexpr int MT = KA * ESZ > 320 ? 1 : 2;       // landmark tiles (of 128) per work item
   static constexpr int JT = 8;                         // sets per work item
   static constexpr int EC = NT / JT;                   // set members per tile
   static constexpr int NSTAGE = 3;
   static constexpr int RB = ((24 + 4 * DP) + 15) / 16 * 16;  // record bytes (rec_bytes_f32)
-  static constexpr int A_TILE_BYTES = KA * 128 * 4;
-  static constexpr int B_STAGE_BYTES = KA * NT * 4;
+  static constexpr int A_TILE_BYTES = KA * 128 * ESZ;
+  static constexpr int B_STAGE_BYTES = KA * NT * ESZ;
   static constexpr int W_STAGE_BYTES = NT * 8;
 #ifndef BASQ_EPI_WARPS
 #define BASQ_EPI_WARPS 16
@@ -143,6 +158,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // K-major operand without swizzle, stored as [K / 4][rows][4 floats]: 8-row core matrices are
 // contiguous (SBO = 128 B), the next 16-byte K chunk lies one plane further (LBO = rows * 16 B).
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -197,6 +224,24 @@ __device__ __forceinline__ void split3(float v, float& p1, float& p2, float& p3)
   p3 = tf32_rna(__fsub_rn(r, p2));
 }
 
+// fp16 pieces of an fp32 value: hi = the value cut to 11 significant bits (exact in fp16 within its normal
+// range), lo = the remainder rounded to fp16 (sum reproduces the value to ~2^-22); values are clamped to
+// fp16's range first
+__device__ __forceinline__ float clamp_h(float v) { return fminf(fmaxf(v, -60000.f), 60000.f); }
+__device__ __forceinline__ void split2h(float v, __half& hi, __half& lo) {
+  v = clamp_h(v);
+  const float t = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  hi = __float2half_rn(t);
+  lo = __float2half_rn(__fsub_rn(v, __half2float(hi)));
+}
+__device__ __forceinline__ void split3h(float v, __half& p1, __half& p2, __half& p3) {
+  v = clamp_h(v);
+  p1 = __float2half_rn(v);
+  const float r = __fsub_rn(v, __half2float(p1));
+  p2 = __float2half_rn(r);
+  p3 = __float2half_rn(__fsub_rn(r, __half2float(p2)));
+}
+
 }  // namespace mma
 
 // ---------------------------------------------------------------------------------------------
@@ -211,27 +256,48 @@ __global__ void build_lmA_kernel(const float* __restrict__ zz, const float* __re
   constexpr int KA = Cfg::KA;
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= n_tiles * 128) return;
-  float vals[KA];
-#pragma unroll
-  for (int k = 0; k < KA; ++k) vals[k] = 0.f;
-  if (m < Mtot) {
-#pragma unroll
-    for (int i = 0; i < DP; ++i) {
-      const float z = zz[(int64_t)m * DP + i];
-      const float zh = mma::tf32_rna(z);
-      const float zl = mma::tf32_rna(__fsub_rn(z, zh));
-      vals[3 * i] = zh;
-      vals[3 * i + 1] = zh;
-      vals[3 * i + 2] = zl;
-    }
-    vals[3 * DP] = vals[3 * DP + 1] = vals[3 * DP + 2] = 1.f;
-    mma::split3(bz[m], vals[3 * DP + 3], vals[3 * DP + 4], vals[3 * DP + 5]);
-  }
   const int tile = m >> 7, row = m & 127;
-  float4* dst = reinterpret_cast<float4*>(lmA) + (int64_t)tile * (KA / 4) * 128 + row;
+  if constexpr (Cfg::F16) {
+    __half vals[KA];
 #pragma unroll
-  for (int kc = 0; kc < KA / 4; ++kc)
-    dst[kc * 128] = make_float4(vals[4 * kc], vals[4 * kc + 1], vals[4 * kc + 2], vals[4 * kc + 3]);
+    for (int k = 0; k < KA; ++k) vals[k] = __float2half_rn(0.f);
+    if (m < Mtot) {
+#pragma unroll
+      for (int i = 0; i < DP; ++i) {
+        __half zh, zl;
+        mma::split2h(zz[(int64_t)m * DP + i], zh, zl);
+        vals[3 * i] = zh;
+        vals[3 * i + 1] = zh;
+        vals[3 * i + 2] = zl;
+      }
+      vals[3 * DP] = vals[3 * DP + 1] = vals[3 * DP + 2] = __float2half_rn(1.f);
+      mma::split3h(bz[m], vals[3 * DP + 3], vals[3 * DP + 4], vals[3 * DP + 5]);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(lmA) + (int64_t)tile * (KA / 8) * 128 + row;
+#pragma unroll
+    for (int kc = 0; kc < KA / 8; ++kc) dst[kc * 128] = *reinterpret_cast<const uint4*>(&vals[8 * kc]);
+  } else {
+    float vals[KA];
+#pragma unroll
+    for (int k = 0; k < KA; ++k) vals[k] = 0.f;
+    if (m < Mtot) {
+#pragma unroll
+      for (int i = 0; i < DP; ++i) {
+        const float z = zz[(int64_t)m * DP + i];
+        const float zh = mma::tf32_rna(z);
+        const float zl = mma::tf32_rna(__fsub_rn(z, zh));
+        vals[3 * i] = zh;
+        vals[3 * i + 1] = zh;
+        vals[3 * i + 2] = zl;
+      }
+      vals[3 * DP] = vals[3 * DP + 1] = vals[3 * DP + 2] = 1.f;
+      mma::split3(bz[m], vals[3 * DP + 3], vals[3 * DP + 4], vals[3 * DP + 5]);
+    }
+    float4* dst = reinterpret_cast<float4*>(lmA) + (int64_t)tile * (KA / 4) * 128 + row;
+#pragma unroll
+    for (int kc = 0; kc < KA / 4; ++kc)
+      dst[kc * 128] = make_float4(vals[4 * kc], vals[4 * kc + 1], vals[4 * kc + 2], vals[4 * kc + 3]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -442,40 +508,65 @@ __global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(cons
           const int64_t e = e_lo + t * EC + ei;
           const int64_t p = (int64_t)(j0 + jj) + e * S - a.off;
           const bool ok = (j0 + jj < a.S) && (p >= a.p_lo) && (p < a.p_hi);
-          float vals[KA];
-#pragma unroll
-          for (int k = 0; k < KA; ++k) vals[k] = 0.f;
           double w = 0.0;
+          constexpr int NV = RB / 16;
+          uint4 q[NV];
+#pragma unroll
+          for (int v = 0; v < NV; ++v) q[v] = make_uint4(0u, 0u, 0u, 0u);
           if (ok) {
             const uint4* rec = reinterpret_cast<const uint4*>(a.recs + p * RB);
-            constexpr int NV = RB / 16;
-            uint4 q[NV];
 #pragma unroll
             for (int v = 0; v < NV; ++v) q[v] = __ldg(rec + v);
             w = __hiloint2double((int)q[0].y, (int)q[0].x);
-            float f[(NV - 1) * 4];  // [idx, a, x0, x1, ...]
-#pragma unroll
-            for (int v = 1; v < NV; ++v) {
-              f[(v - 1) * 4 + 0] = __uint_as_float(q[v].x);
-              f[(v - 1) * 4 + 1] = __uint_as_float(q[v].y);
-              f[(v - 1) * 4 + 2] = __uint_as_float(q[v].z);
-              f[(v - 1) * 4 + 3] = __uint_as_float(q[v].w);
-            }
-#pragma unroll
-            for (int i = 0; i < DP; ++i) {
-              const float x = f[2 + i];
-              const float xh = mma::tf32_rna(x);
-              const float xl = mma::tf32_rna(__fsub_rn(x, xh));
-              vals[3 * i] = xh;
-              vals[3 * i + 1] = xl;
-              vals[3 * i + 2] = xh;
-            }
-            mma::split3(f[1], vals[3 * DP], vals[3 * DP + 1], vals[3 * DP + 2]);
-            vals[3 * DP + 3] = vals[3 * DP + 4] = vals[3 * DP + 5] = 1.f;
           }
+          float f[(NV - 1) * 4];  // [idx, a, x0, x1, ...]
 #pragma unroll
-          for (int kc = 0; kc < KA / 4; ++kc)
-            bst[kc * NT + c] = make_float4(vals[4 * kc], vals[4 * kc + 1], vals[4 * kc + 2], vals[4 * kc + 3]);
+          for (int v = 1; v < NV; ++v) {
+            f[(v - 1) * 4 + 0] = __uint_as_float(q[v].x);
+            f[(v - 1) * 4 + 1] = __uint_as_float(q[v].y);
+            f[(v - 1) * 4 + 2] = __uint_as_float(q[v].z);
+            f[(v - 1) * 4 + 3] = __uint_as_float(q[v].w);
+          }
+          if constexpr (Cfg::F16) {
+            __half vals[KA];
+#pragma unroll
+            for (int k = 0; k < KA; ++k) vals[k] = __float2half_rn(0.f);
+            if (ok) {
+#pragma unroll
+              for (int i = 0; i < DP; ++i) {
+                __half xh, xl;
+                mma::split2h(f[2 + i], xh, xl);
+                vals[3 * i] = xh;
+                vals[3 * i + 1] = xl;
+                vals[3 * i + 2] = xh;
+              }
+              mma::split3h(f[1], vals[3 * DP], vals[3 * DP + 1], vals[3 * DP + 2]);
+              vals[3 * DP + 3] = vals[3 * DP + 4] = vals[3 * DP + 5] = __float2half_rn(1.f);
+            }
+            uint4* bst16 = reinterpret_cast<uint4*>(bst);
+#pragma unroll
+            for (int kc = 0; kc < KA / 8; ++kc) bst16[kc * NT + c] = *reinterpret_cast<const uint4*>(&vals[8 * kc]);
+          } else {
+            float vals[KA];
+#pragma unroll
+            for (int k = 0; k < KA; ++k) vals[k] = 0.f;
+            if (ok) {
+#pragma unroll
+              for (int i = 0; i < DP; ++i) {
+                const float x = f[2 + i];
+                const float xh = mma::tf32_rna(x);
+                const float xl = mma::tf32_rna(__fsub_rn(x, xh));
+                vals[3 * i] = xh;
+                vals[3 * i + 1] = xl;
+                vals[3 * i + 2] = xh;
+              }
+              mma::split3(f[1], vals[3 * DP], vals[3 * DP + 1], vals[3 * DP + 2]);
+              vals[3 * DP + 3] = vals[3 * DP + 4] = vals[3 * DP + 5] = 1.f;
+            }
+#pragma unroll
+            for (int kc = 0; kc < KA / 4; ++kc)
+              bst[kc * NT + c] = make_float4(vals[4 * kc], vals[4 * kc + 1], vals[4 * kc + 2], vals[4 * kc + 3]);
+          }
           wst[c] = w;
         }
         mma::fence_proxy_async();
@@ -484,7 +575,9 @@ __global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(cons
     }
   } else {
     // ======================================================================== MMA issuer
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+    // instruction descriptor: D fp32; A / B tf32 (format 2) or fp16 (format 0), K-major; N, M
+    constexpr uint32_t FMT = Cfg::F16 ? 0u : 2u;
+    constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
     constexpr int NABUF = Cfg::NABUF;
     uint32_t it = 0, tc = 0, ac = 0;  // ac counts the work items with tiles (= landmark tile loads)
     auto next_item = [&](int item) {  // first item >= `item` of this CTA that has tiles; n_items if none
@@ -530,10 +623,11 @@ __global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(cons
             const uint32_t a_base = mma::smem_u32(sAcur + mt * Cfg::A_TILE_BYTES);
             const uint32_t b_base = mma::smem_u32(sB + (size_t)stage * Cfg::B_STAGE_BYTES);
 #pragma unroll
-            for (int ks = 0; ks < KA / 8; ++ks) {
+            for (int ks = 0; ks < KA / Cfg::KSTEP; ++ks) {   // one MMA = two 16-byte K chunks of either type
               const uint64_t ad = mma::smem_desc(a_base + ks * 2 * (128 * 16), 128 * 16, 128);
               const uint64_t bd = mma::smem_desc(b_base + ks * 2 * (NT * 16), NT * 16, 128);
-              mma::umma_tf32(tmem_base + buf * NT, ad, bd, IDESC, ks > 0 ? 1u : 0u);
+              if (Cfg::F16) mma::umma_f16(tmem_base + buf * NT, ad, bd, IDESC, ks > 0 ? 1u : 0u);
+              else mma::umma_tf32(tmem_base + buf * NT, ad, bd, IDESC, ks > 0 ? 1u : 0u);
             }
             mma::umma_commit(&t_full[buf]);
           }
