@@ -528,24 +528,38 @@ __global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(cons
             f[(v - 1) * 4 + 3] = __uint_as_float(q[v].w);
           }
           if constexpr (Cfg::F16) {
-            __half vals[KA];
+            // pieces as floats first (hi = the value cut to 11 significant bits by a mask, lo = the exact fp32
+            // remainder), then packed pair conversions only: scalar float <-> half conversions run on the
+            // 16-lane pipe of the epilogue's ex2 - the pipe that bounds this kernel
+            float fv[KA];
 #pragma unroll
-            for (int k = 0; k < KA; ++k) vals[k] = __float2half_rn(0.f);
+            for (int k = 0; k < KA; ++k) fv[k] = 0.f;
             if (ok) {
 #pragma unroll
               for (int i = 0; i < DP; ++i) {
-                __half xh, xl;
-                mma::split2h(f[2 + i], xh, xl);
-                vals[3 * i] = xh;
-                vals[3 * i + 1] = xl;
-                vals[3 * i + 2] = xh;
+                const float x = mma::clamp_h(f[2 + i]);
+                const float xh = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+                fv[3 * i] = xh;
+                fv[3 * i + 1] = __fsub_rn(x, xh);
+                fv[3 * i + 2] = xh;
               }
-              mma::split3h(f[1], vals[3 * DP], vals[3 * DP + 1], vals[3 * DP + 2]);
-              vals[3 * DP + 3] = vals[3 * DP + 4] = vals[3 * DP + 5] = __float2half_rn(1.f);
+              const float av = mma::clamp_h(f[1]);
+              const float a1 = __uint_as_float(__float_as_uint(av) & 0xFFFFE000u);
+              const float r1 = __fsub_rn(av, a1);
+              const float a2 = __uint_as_float(__float_as_uint(r1) & 0xFFFFE000u);
+              fv[3 * DP] = a1;
+              fv[3 * DP + 1] = a2;
+              fv[3 * DP + 2] = __fsub_rn(r1, a2);
+              fv[3 * DP + 3] = fv[3 * DP + 4] = fv[3 * DP + 5] = 1.f;
             }
             uint4* bst16 = reinterpret_cast<uint4*>(bst);
 #pragma unroll
-            for (int kc = 0; kc < KA / 8; ++kc) bst16[kc * NT + c] = *reinterpret_cast<const uint4*>(&vals[8 * kc]);
+            for (int kc = 0; kc < KA / 8; ++kc) {
+              __half2 h2[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) h2[u] = __floats2half2_rn(fv[8 * kc + 2 * u], fv[8 * kc + 2 * u + 1]);
+              bst16[kc * NT + c] = *reinterpret_cast<const uint4*>(h2);
+            }
           } else {
             float vals[KA];
 #pragma unroll

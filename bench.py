@@ -333,20 +333,35 @@ def extra_configs(dev, a):
     m5l = model(10, 1002, 6, 2.5, log=True)
     run("config5_mmlt_N1e7_M1e4_n1000", spec_from_model(m5l, _lib.MMLT_G), 10, 10_000_000, 10_000, 1000, reps=1)
     # fp64 inputs (SOBER's global dtype, SOBER/_settings.py:4-11): the all-fp64 CUDA-core path
-    kern2 = spec_from_model(m2, _lib.PRED_COV)
-    X = bsampler.sample_mvn(torch.zeros(2), 2.0 * torch.eye(2), 1_000_000, seed=7, device=dev, dtype=torch.float64)
-    Om = torch.randn(10_000, 99, dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+    # (setsum_kernel<double>: direct differences, fp64 exp; bound by the fp64 pipe - DESIGN.md 4)
+    def run64(name, kern, d, N, M, n):
+        X = bsampler.sample_mvn(torch.zeros(d), 2.0 * torch.eye(d), N, seed=7, device=dev, dtype=torch.float64)
+        Om = torch.randn(M, n - 1, dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
 
-    def step64():
-        _, U = ops.nystrom_basis(kern2, X[:10_000], 99, omega=Om, want_S=False)
-        return ops.recombine(kern2, X, X[:10_000], U)
-    step64()
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    step64()
-    torch.cuda.synchronize(dev)
-    out["config2_fp64_inputs_d2_N1e6_M1e4_n100_vbq"] = {"ms": round((time.perf_counter() - t0) * 1e3, 3)}
-    del X, Om
+        def step64():
+            _, U = ops.nystrom_basis(kern, X[:M], n - 1, omega=Om, want_S=False)
+            return ops.recombine(kern, X, X[:M], U)
+        step64()
+        torch.cuda.synchronize(dev)
+        ctx.profile(True)
+        ctx.profile_read(reset=True)
+        pe0 = ctx.pair_evals
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        idx, w = step64()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        prof = ctx.profile_read(reset=True)
+        ctx.profile(False)
+        assert 1 <= len(idx) <= n and abs(float(w.sum()) - 1.0) < 1e-9
+        ss = prof["set_sum"][0]
+        out[name] = {"ms": round(e0.elapsed_time(e1), 3), "phases_ms": {k: round(v[0], 2) for k, v in prof.items() if v[0] > 0},
+                     "set_sum_pairs_per_s": (ctx.pair_evals - pe0) / (ss * 1e-3) if ss > 0 else None}
+        del X, Om
+
+    run64("config2_fp64_inputs_d2_N1e6_M1e4_n100_vbq", spec_from_model(m2, _lib.PRED_COV), 2, 1_000_000, 10_000, 100)
+    run64("config4_fp64_inputs_d20_matern52_N4e6_M5e3_n500", KernelSpec(_lib.MATERN25, _lib.PLAIN, torch.tensor([4.0]), 1.0),
+          20, 4_000_000, 5_000, 500)
     # acquisition pass of config 5: GP posterior mean + variance over 1e7 candidates, then calc_weights
     kern = spec_from_model(model(10, 1002, 5, 2.5), _lib.PRED_COV)
     X = bsampler.sample_mvn(torch.zeros(10), 2.0 * torch.eye(10), 10_000_000, seed=9, device=dev)
