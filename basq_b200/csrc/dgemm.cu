@@ -32,7 +32,13 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 // contiguous (16-byte copies) and pad the other stride to 4 (mod 16) doubles: every fragment load
 // is conflict-free.
 // ---------------------------------------------------------------------------------------------
-constexpr int PK = 16, PST = 3;
+#ifndef BASQ_DGEMM_PK
+#define BASQ_DGEMM_PK 16
+#endif
+#ifndef BASQ_DGEMM_PST
+#define BASQ_DGEMM_PST 3
+#endif
+constexpr int PK = BASQ_DGEMM_PK, PST = BASQ_DGEMM_PST;   // A/B: -DBASQ_DGEMM_PK=32
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, int bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src),

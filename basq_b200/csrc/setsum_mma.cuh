@@ -57,6 +57,13 @@ struct SetSumMmaDev {
 #define BASQ_SETSUM_F16 1
 #endif
 
+// BASQ_SETSUM_POLY_ROWS = r (0..4): of the four landmark rows a thread owns, r evaluate exp2 with a
+// degree-6 polynomial on the FMA pipe (Cody-Waite split, 1.1e-7 relative, like ex2.approx) instead of the
+// MUFU: the choice depends on the landmark only, so k(z, x) stays bit-identical across passes.
+#ifndef BASQ_SETSUM_POLY_ROWS
+#define BASQ_SETSUM_POLY_ROWS 0
+#endif
+
 template <int DP>
 struct MmaCfg {
   static constexpr bool F16 = BASQ_SETSUM_F16 != 0;
@@ -242,7 +249,32 @@ __device__ __forceinline__ void split3h(float v, __half& p1, __half& p2, __half&
   p3 = __float2half_rn(__fsub_rn(r, __half2float(p2)));
 }
 
+// 2^x on the FMA / ALU pipes: x = n + f, n = round(x), |f| <= 1/2; degree-6 minimax of 2^f (1.1e-7 relative
+// including the fp32 Horner rounding); the exponent is added to the bit pattern (n sits in the low mantissa
+// bits of x + 1.5 * 2^23).  12 instructions; no MUFU.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float r = __fadd_rn(x, 12582912.f);
+  const float f = __fsub_rn(x, __fsub_rn(r, 12582912.f));
+  float p = 0.000154697319723078f;
+  p = __fmaf_rn(p, f, 0.0013400432165225804f);
+  p = __fmaf_rn(p, f, 0.009618025602985998f);
+  p = __fmaf_rn(p, f, 0.05550327214209406f);
+  p = __fmaf_rn(p, f, 0.2402265121359483f);
+  p = __fmaf_rn(p, f, 0.6931472067106204f);
+  p = __fmaf_rn(p, f, 0.9999999999595486f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+
 }  // namespace mma
+
+// kernel value from the exponent argument: MUFU path (finish_f32) or, for RBF rows selected at compile
+// time, the FMA-pipe polynomial
+template <int FAM, bool POLY>
+__device__ __forceinline__ float finish_sel(float acc, float os_f) {
+  if (FAM == BASQ_RBF && POLY) return mma::exp2_poly(acc);
+  return finish_f32(FAM, acc, os_f);
+}
 
 // ---------------------------------------------------------------------------------------------
 // landmark operand: lmA[tile][kc][row][4] from the prepared zz [Mtot, DP] / b [Mtot]
@@ -403,10 +435,20 @@ __global__ void __launch_bounds__(MmaCfg<DP>::THREADS, 1) setsum_mma_kernel(cons
               const double2 w2 = *reinterpret_cast<const double2*>(wst + cb + 8 * k);
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
-                const float k00 = finish_f32(FAM, __uint_as_float(h ? vb[4 * k + 0] : va[4 * k + 0]), a.os_f);
-                const float k01 = finish_f32(FAM, __uint_as_float(h ? vb[4 * k + 1] : va[4 * k + 1]), a.os_f);
-                const float k10 = finish_f32(FAM, __uint_as_float(h ? vb[4 * k + 2] : va[4 * k + 2]), a.os_f);
-                const float k11 = finish_f32(FAM, __uint_as_float(h ? vb[4 * k + 3] : va[4 * k + 3]), a.os_f);
+                // row slots 2 h and 2 h + 1; the last BASQ_SETSUM_POLY_ROWS slots take the FMA-pipe exp2
+                constexpr int PR = BASQ_SETSUM_POLY_ROWS;
+                const float u00 = __uint_as_float(h ? vb[4 * k + 0] : va[4 * k + 0]);
+                const float u01 = __uint_as_float(h ? vb[4 * k + 1] : va[4 * k + 1]);
+                const float u10 = __uint_as_float(h ? vb[4 * k + 2] : va[4 * k + 2]);
+                const float u11 = __uint_as_float(h ? vb[4 * k + 3] : va[4 * k + 3]);
+                float k00, k01, k10, k11;
+                if (h == 0) {
+                  k00 = finish_sel<FAM, (PR >= 4)>(u00, a.os_f); k01 = finish_sel<FAM, (PR >= 4)>(u01, a.os_f);
+                  k10 = finish_sel<FAM, (PR >= 3)>(u10, a.os_f); k11 = finish_sel<FAM, (PR >= 3)>(u11, a.os_f);
+                } else {
+                  k00 = finish_sel<FAM, (PR >= 2)>(u00, a.os_f); k01 = finish_sel<FAM, (PR >= 2)>(u01, a.os_f);
+                  k10 = finish_sel<FAM, (PR >= 1)>(u10, a.os_f); k11 = finish_sel<FAM, (PR >= 1)>(u11, a.os_f);
+                }
                 acc[mt][2 * h][0] = fma(f2d_pos(k00), w2.x, acc[mt][2 * h][0]);
                 acc[mt][2 * h][1] = fma(f2d_pos(k01), w2.y, acc[mt][2 * h][1]);
                 acc[mt][2 * h + 1][0] = fma(f2d_pos(k10), w2.x, acc[mt][2 * h + 1][0]);
