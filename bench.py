@@ -556,6 +556,27 @@ def run_ours(a, rank, world, local_rank):
                   "what": "BASELINE config 3 as worded: 1e7 candidates in total sharded over the ranks; the Nystrom "
                           "basis and the Caratheodory levels are replicated work (Amdahl)"}
 
+    # BASELINE config 5 as worded (Tutorial 03 models on 8 x B200): 1e7 candidates in total sharded over the ranks,
+    # WSABI-M and MMLT kernels (the pairwise tensor-core set sums shard with the candidates)
+    extra_multi = None
+    if world > 1 and not a.no_extra:
+        extra_multi = {}
+        lo, hi = sharded.shard_bounds(a.N, world, rank)
+        Xs5 = X[: hi - lo]
+        for tag, mode, kw in (("wsabim", _lib.WSABI_M, {"sqrt": True}), ("mmlt", _lib.MMLT_G, {"log": True})):
+            Xo5, yo5 = make_observations(a.d, a.n_obs, seed=5 if tag == "wsabim" else 6, **kw)
+            m5 = bgp.FixedGP(Xo5.to(dev, torch.float32), yo5.to(dev), bgp.ScaleKernel(bgp.RBFKernel(a.lengthscale), 1.0),
+                             noise=a.noise)
+            k5 = spec_from_model(m5, mode)
+
+            def step5():
+                _, U = ops.nystrom_basis(k5, Z, q, omega=Omega, want_S=False)
+                return sharded.recombination_sharded(Xs5, Z, a.n, k5, a.N, lo, U)
+            step5()
+            ms5, out5 = timed(step5, 2)
+            assert 1 <= len(out5[0]) <= a.n and abs(float(out5[1].sum()) - 1.0) < 1e-9
+            extra_multi[f"config5_{tag}_N1e7_total_sharded"] = {"ms": round(ms5, 3), "points_per_s": a.N / (ms5 * 1e-3)}
+
     line = None
     if rank == 0:
         ss_ms_tot, ss_calls = prof["set_sum"]
@@ -605,6 +626,8 @@ def run_ours(a, rank, world, local_rank):
         }
         if strong is not None:
             line["strong"] = strong
+        if extra_multi:
+            line["extra"] = extra_multi
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cores = host_threads()
         n_sample = max(a.cpu_sample, 4 * a.n, a.M)

@@ -32,3 +32,14 @@ for rnd in range(2):
     v2 = run("staged", {"BASQ_GPVAR": "1", "BASQ_GPVAR_FUSED": "0"})
 v3 = run("fp64 GEMM (round 1)", {"BASQ_GPVAR": "0"}, reps=2)
 print("max |fused - staged| %.3e  |fused - fp64| %.3e" % (float((v1 - v2).abs().max()), float((v1 - v3).abs().max())))
+
+# where calc_weights spends its time (UncertaintySampler.calc_weights = moments + one elementwise pass)
+os.environ.update({"BASQ_GPVAR": "1", "BASQ_GPVAR_FUSED": "1"})
+from basq_b200 import sampler as bs
+bs.calc_weights(kern, X, ratio=0.5); torch.cuda.synchronize()
+for rep in range(2):
+    t0 = time.perf_counter(); mean, var = ops.gp_predict(kern, X, space=0, want_var=True); torch.cuda.synchronize()
+    t1 = time.perf_counter(); w = bs._weights(0, 0.5, False, mean, var, True); torch.cuda.synchronize()
+    t2 = time.perf_counter(); w2 = bs.calc_weights(kern, X, ratio=0.5); torch.cuda.synchronize()
+    t3 = time.perf_counter()
+    print(f"gp_predict {1e3*(t1-t0):.1f} ms, weights kernel + normalise {1e3*(t2-t1):.1f} ms, calc_weights (both) {1e3*(t3-t2):.1f} ms")

@@ -157,3 +157,45 @@ def test_config5_nonlinear_full_size(lib, monkeypatch, name):
     red = ops.features(kern, X[idx], Z, Us).T @ w
     res = float(torch.linalg.norm(full - red) / torch.linalg.norm(full))
     assert res < 1e-8, res
+
+
+@pytest.mark.parametrize("name", ["wsabim", "mmlt"])
+def test_sharded_sessions_match_one_session(lib, monkeypatch, name):
+    """Three rank-local sessions on one GPU (uneven shards, so that the offsets cut through set groups and
+    tiles) must produce partial systems whose sum is the single-session system, for the reference's round
+    (F = 1) and for a refined pass (F = 4), with and without wrap-around of the cells (GRAM mode)."""
+    _, _lib, gp, ops, *_ = lib
+    from basq_b200 import sharded
+    monkeypatch.setenv("BASQ_NLSUM", "1")
+    d, n_obs, M, n = 6, 70, 200, 16
+    model = ogp.make_gp(d, n_obs, lengthscale=2.0, noise=1e-3, seed=4, log_targets=(name == "mmlt"))
+    kern = _kern(model, name)
+    g = torch.Generator().manual_seed(9)
+    S = 2 * n
+    for N in (7001, 5 * S + 3, S - 5):           # many members per cell / few / fewer points than sets
+        X = (math.sqrt(2.0) * torch.randn(N, d, generator=g)).float().to(DEV)
+        Z = (math.sqrt(2.0) * torch.randn(M, d, generator=g)).float().to(DEV)
+        U = torch.linalg.qr(torch.randn(M, n - 1, generator=g, dtype=torch.float64)).Q.T.contiguous().to(DEV)
+        cuts = [0, N // 3 + 1, (2 * N) // 3 - 2, N]
+        whole = ops.Session(kern, X, Z, U, N, 0)
+        parts = [ops.Session(kern, X[cuts[i]:cuts[i + 1]], Z, U, N, cuts[i]) for i in range(3)]
+        try:
+            for F in ((1, 4) if N >= 4 * 4 * S else (1,)):
+                tree = sharded.LevelTree(S, F, N)
+                whole.pass_begin(N, 0, F)
+                for i, sp in enumerate(parts):
+                    sp.pass_begin(N, cuts[i], F)
+                A = torch.zeros(n, S, dtype=torch.float64, device=DEV)
+                whole.level(0, tree.node, tree.ppos, tree.fpar, A)
+                Asum = torch.zeros_like(A)
+                for sp in parts:
+                    Ap = torch.zeros_like(A)
+                    sp.level(0, tree.node, tree.ppos, tree.fpar, Ap)
+                    Asum += Ap
+                scale = float(A.abs().max())
+                assert float((A - Asum).abs().max()) < 1e-12 * scale, (N, F)
+                assert abs(float(A[0].sum()) - 1.0) < 1e-12
+        finally:
+            whole.close()
+            for sp in parts:
+                sp.close()
