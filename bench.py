@@ -486,18 +486,21 @@ def run_ours(a, rank, world, local_rank):
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)] if debug else None
         e0.record()
         out = None
         for i in range(steps):
-            t0 = time.perf_counter()
+            if debug:
+                marks[i].record()
             out = fn()
-            if debug:   # per-step wall clock (synchronising: diagnostic runs only)
-                torch.cuda.synchronize(dev)
-                print(f"[bench debug] rank {rank} {fn.__name__} step {i}: {1e3 * (time.perf_counter() - t0):.1f} ms",
-                      file=sys.stderr, flush=True)
+        if debug:
+            marks[steps].record()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        if debug:   # per-step device times from events recorded without synchronising (diagnostic runs)
+            per = [marks[i].elapsed_time(marks[i + 1]) for i in range(steps)]
+            print(f"[bench debug] rank {rank} {fn.__name__}: " + " ".join(f"{t:.1f}" for t in per), file=sys.stderr, flush=True)
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
