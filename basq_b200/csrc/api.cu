@@ -164,6 +164,37 @@ struct basq_session {
   bool scale_wf = true;
   std::vector<double> omega_host;
   std::vector<int> rank_host;
+  // Pinned staging ring for the small per-level host arrays (node ids, parent positions, parent factors): the
+  // H2D copies read from a slot of this ring, so the level calls return without synchronising the stream and
+  // the caller may reuse its arrays at once; a slot is reused only after the event recorded behind its copies.
+  static constexpr int STAGE_SLOTS = 8;
+  unsigned char* stage = nullptr;
+  size_t stage_slot_bytes = 0;
+  cudaEvent_t stage_ev[STAGE_SLOTS] = {nullptr};
+  int stage_next = 0;
+  ~basq_session() {
+    if (stage) {
+      if (ctx) cudaStreamSynchronize(ctx->stream);
+      cudaFreeHost(stage);
+    }
+    for (cudaEvent_t e : stage_ev)
+      if (e) cudaEventDestroy(e);
+    (void)cudaGetLastError();
+  }
+  // a free slot (ints first, doubles behind them: [S ints][S ints][S doubles])
+  int stage_take(unsigned char** slot_out, int* slot_index) {
+    if (!stage) {
+      stage_slot_bytes = (size_t)S * 16;
+      BASQ_CUDA(cudaHostAlloc((void**)&stage, stage_slot_bytes * STAGE_SLOTS, cudaHostAllocDefault));
+      for (int i = 0; i < STAGE_SLOTS; ++i) BASQ_CUDA(cudaEventCreateWithFlags(&stage_ev[i], cudaEventDisableTiming));
+    }
+    const int i = stage_next;
+    stage_next = (stage_next + 1) % STAGE_SLOTS;
+    BASQ_CUDA(cudaEventSynchronize(stage_ev[i]));   // returns at once for a never-recorded / completed event
+    *slot_out = stage + (size_t)i * stage_slot_bytes;
+    *slot_index = i;
+    return BASQ_OK;
+  }
 };
 
 namespace basq {
@@ -432,13 +463,17 @@ int session_level_fold(basq_session* s, int lvl, int K, const int* node_host, do
   BASQ_TRY(session_level_check(s, lvl, K, node_host, nullptr));
   PhaseTimer t(ctx, PH_PROJ);
   const int stride = s->S << lvl, cnt = s->pass_F >> lvl;
-  BASQ_CUDA(cudaMemcpyAsync(s->lnode.p, node_host, sizeof(int) * K, cudaMemcpyHostToDevice, ctx->stream));
+  unsigned char* slot = nullptr;
+  int si = 0;
+  BASQ_TRY(s->stage_take(&slot, &si));
+  memcpy(slot, node_host, sizeof(int) * K);
+  BASQ_CUDA(cudaMemcpyAsync(s->lnode.p, slot, sizeof(int) * K, cudaMemcpyHostToDevice, ctx->stream));
+  BASQ_CUDA(cudaEventRecord(s->stage_ev[si], ctx->stream));
   fold_cols_kernel<<<(unsigned)ceil_div64((int64_t)s->Mtot * K, 256), 256, 0, ctx->stream>>>(
       s->G.as<double>(), s->ldg, s->Mtot, K, s->lnode.as<int>(), stride, cnt, Gf_out, ld_gf);
   ctx->launches++;
   BASQ_CUDA(cudaGetLastError());
-  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));  // node_host may be reused
-  return BASQ_OK;
+  return BASQ_OK;   // no synchronisation: node_host was copied into the pinned ring
 }
 
 int session_level_project(basq_session* s, int lvl, int K, const int* node_host, const int* ppos_host,
@@ -450,9 +485,21 @@ int session_level_project(basq_session* s, int lvl, int K, const int* node_host,
   BASQ_CHECK(row0 >= 0 && nrows >= 0 && row0 + nrows <= s->Mtot, BASQ_ERR_INVALID, "level: bad landmark row range");
   const int stride = S << lvl, cnt = F >> lvl;
   PhaseTimer t(ctx, PH_PROJ);
-  BASQ_CUDA(cudaMemcpyAsync(s->lnode.p, node_host, sizeof(int) * K, cudaMemcpyHostToDevice, ctx->stream));
-  if (lvl > 0) BASQ_CUDA(cudaMemcpyAsync(s->lppos.p, ppos_host, sizeof(int) * K, cudaMemcpyHostToDevice, ctx->stream));
-  BASQ_CUDA(cudaMemcpyAsync(s->lfpar.p, fpar_host, sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    unsigned char* slot = nullptr;
+    int si = 0;
+    BASQ_TRY(s->stage_take(&slot, &si));
+    int* h_node = reinterpret_cast<int*>(slot);
+    int* h_ppos = h_node + S;
+    double* h_fpar = reinterpret_cast<double*>(slot + (size_t)S * 8);
+    memcpy(h_node, node_host, sizeof(int) * K);
+    if (lvl > 0) memcpy(h_ppos, ppos_host, sizeof(int) * K);
+    memcpy(h_fpar, fpar_host, sizeof(double) * K);
+    BASQ_CUDA(cudaMemcpyAsync(s->lnode.p, h_node, sizeof(int) * K, cudaMemcpyHostToDevice, ctx->stream));
+    if (lvl > 0) BASQ_CUDA(cudaMemcpyAsync(s->lppos.p, h_ppos, sizeof(int) * K, cudaMemcpyHostToDevice, ctx->stream));
+    BASQ_CUDA(cudaMemcpyAsync(s->lfpar.p, h_fpar, sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
+    BASQ_CUDA(cudaEventRecord(s->stage_ev[si], ctx->stream));
+  }
   BASQ_CUDA(cudaMemsetAsync(A_out, 0, sizeof(double) * (size_t)rows * S, ctx->stream));
   double* raw = s->raw[s->raw_cur].as<double>();
   const double* prev = s->raw[s->raw_cur ^ 1].as<double>();
@@ -476,8 +523,7 @@ int session_level_project(basq_session* s, int lvl, int K, const int* node_host,
       raw, prev, rows, K, lvl > 0 ? 1 : 0, s->lppos.as<int>(), s->lfpar.as<double>(), A_out, S);
   ctx->launches++;
   BASQ_CUDA(cudaGetLastError());
-  // the host arrays may be reused by the caller as soon as we return
-  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  // no synchronisation: the host arrays were copied into the pinned ring and may be reused at once
   s->raw_cur ^= 1;
   return BASQ_OK;
 }

@@ -1,11 +1,14 @@
 """Oracle restatement (torch CPU) of the kernel callables that feed recombination.
 
-TEST INFRASTRUCTURE - see ``oracle/__init__.py``.  PARITY UNPINNED for this
-module: the arithmetic belongs to gpytorch (absent here, no version pinned by the
-reference).  Each function cites the reference call site it follows; base kernels
-follow gpytorch's published ``RBFKernel`` / ``MaternKernel`` / ``ScaleKernel``
-formulas; GP caches are exact fp64 Cholesky (the reference's LOVE variance is an
-approximation of the same quantity, ``BASQ/_gp.py:228``).
+TEST INFRASTRUCTURE - see ``oracle/__init__.py``.  PINNED at the reference's call
+sites: ``oracle/make_golden_gp.py`` runs the reference's own ``predictive_covariance``,
+``WsabiGP``, ``VanillaGP``, ``ScaleMmltGP`` and ``Kernel`` code on a duck-typed
+exact-GP model and ``tests/test_oracle_golden_gp.py`` checks this module against those
+outputs.  The layer underneath belongs to gpytorch (absent here, no version pinned by
+the reference) and is restated from its published definition: base kernels follow
+``RBFKernel`` / ``MaternKernel`` / ``ScaleKernel.forward``; GP caches are exact fp64
+Cholesky (the reference's LOVE variance is an approximation of the same quantity,
+``BASQ/_gp.py:228``).  Each function cites the reference call site it follows.
 
 The stand-in classes expose the gpytorch *attribute surface* the reference
 introspects (``train_inputs``, ``likelihood.noise``, ``covar_module.outputscale``,

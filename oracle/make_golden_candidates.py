@@ -1,8 +1,7 @@
 """Golden vectors for the candidate-side stages, produced by the REFERENCE's own code where it can be
 imported here: ``SOBER/_weights.py`` (WeightsStabiliser.cleansing_weights) needs only torch.
-``BASQ/_sampler.py`` (calc_weights) and ``SOBER/_pi.py`` (lfi) import gpytorch and cannot be loaded in
-this image; their restatements in oracle/sampler.py are checked against the formulas instead
-("parity unpinned" for those two).
+``BASQ/_sampler.py`` (calc_weights) and ``SOBER/_pi.py`` (lfi) import gpytorch; they are run by
+oracle/make_golden_gp.py, which registers stand-in modules for those imports.
 
 Run in the build container only:  ``python oracle/make_golden_candidates.py``
 """

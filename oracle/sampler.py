@@ -10,8 +10,11 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import 
   VALUES are implementation-defined; what is checked against the reference's behaviour is the
   distribution (moments) and, bit-for-bit, the Philox integers.
 * ``mvn_logpdf``: prior.log_prob (torch.distributions.MultivariateNormal.log_prob).
-* ``calc_weights``: UncertaintySampler.calc_weights, BASQ/_sampler.py:190-217.
-* ``lfi``: PI_BQ.lfi, SOBER/_pi.py:121-139.
+* ``calc_weights``: UncertaintySampler.calc_weights, BASQ/_sampler.py:190-217.  Pinned by outputs of
+  that method itself (oracle/make_golden_gp.py -> tests/golden/gp_kernels.npz).
+* ``lfi``: PI_BQ.lfi, SOBER/_pi.py:121-139.  log=False pinned the same way; the reference's log=True
+  branch raises NameError (the file uses ``torch.finfo`` without importing torch), so the log form
+  follows the line as written, with the fp32 eps torch.finfo() returns by default.
 * ``cleansing_weights``: WeightsStabiliser.cleansing_weights, SOBER/_weights.py:21-38.
 """
 from __future__ import annotations
