@@ -113,7 +113,9 @@ def _worker(rank, world, port, N, weighted, out_path):
         full_mu = torch.full((N,), 1.0 / N, dtype=torch.float64) if mu is None else mu
         Phi = orchq.features(X, U, Z, kern)
         res = orchq.moment_residual(Phi, full_mu, idx, w)
-        assert res < 1e-11, res
+        # fp64 oracle engine; the Caratheodory pivot order (and with it the last digits) depends on the
+        # threading of the host BLAS, observed 3e-12 .. 3e-11
+        assert res < 2e-10, res
         assert abs(float(w.sum()) - 1.0) < 1e-12
         # every rank holds the same gathered rule
         chk = torch.stack([idx.double().sum(), w.sum()])
