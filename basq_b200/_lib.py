@@ -79,6 +79,8 @@ def _load():
         "basq_session_level_project": (I, [P, I, I, P, P, P, P, L, I, I, P]),
         "basq_session_apply_cells": (I, [P, L, L, I, P, C.POINTER(L)]),
         "basq_sample_mvn": (I, [P, C.c_uint64, L, L, I, I, P, P, P]),
+        "basq_standard_normals": (I, [P, C.c_uint64, L, L, I, P]),
+        "basq_ctx_set_seed": (I, [P, C.c_uint64]),
         "basq_mvn_logpdf": (I, [P, P, L, I, I, P, P, P]),
         "basq_candidate_weights": (I, [P, I, D, I, P, P, L, I, P]),
         "basq_cleanse_weights": (I, [P, P, L, D]),
@@ -127,6 +129,10 @@ class Context:
     def trim(self, keep_bytes: int = 0):
         """Hand the context's cached scratch memory back to the driver (down to keep_bytes)."""
         check(lib.basq_ctx_trim(self.handle, int(keep_bytes)))
+
+    def set_seed(self, seed: int):
+        """Key of the library's own Gaussian draws (basq_ctx_set_seed)."""
+        check(lib.basq_ctx_set_seed(self.handle, int(seed) & 0xFFFFFFFFFFFFFFFF))
 
     def conditioning(self, kappa_max: float = -1.0):
         """(last kappa = max_m |(K_ZX W)_m|_1, number of fp32 -> fp64 promotions so far); a non-negative

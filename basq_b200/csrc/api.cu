@@ -919,6 +919,13 @@ int basq_ctx_trim(basq_ctx* ctx, int64_t keep_bytes) {
 
 int64_t basq_ctx_launch_count(const basq_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int basq_ctx_set_seed(basq_ctx* ctx, uint64_t seed) {
+  BASQ_CHECK(ctx, BASQ_ERR_INVALID, "basq_ctx_set_seed: NULL context");
+  ctx->seed = seed;
+  ctx->draws = 0;
+  return BASQ_OK;
+}
+
 int basq_ctx_conditioning(basq_ctx* ctx, double kappa_max, double* last_kappa_host, int64_t* promotions_host) {
   BASQ_CHECK(ctx, BASQ_ERR_INVALID, "ctx is NULL");
   if (kappa_max >= 0.0) ctx->kappa_max = kappa_max;
@@ -1085,7 +1092,7 @@ int basq_gp_predict(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, 
 
 int basq_nystrom_basis(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, int64_t M, int q,
                        const double* Omega, int niter, double* U_out, double* S_out) {
-  BASQ_CHECK(ctx && desc && Z && Omega && U_out, BASQ_ERR_INVALID, "basq_nystrom_basis: NULL argument");
+  BASQ_CHECK(ctx && desc && Z && U_out, BASQ_ERR_INVALID, "basq_nystrom_basis: NULL argument");
   BASQ_CUDA(cudaSetDevice(ctx->device));
   const int rc = nystrom_basis(ctx, desc, Z, M, q, Omega, niter, U_out, S_out);
   basq_ctx_trim(ctx, -1);
@@ -1169,7 +1176,6 @@ static int recombine_host_impl(basq_ctx* ctx, const basq_kernel_desc* desc, cons
                                int* n_out_host) {
   BASQ_CHECK(ctx && desc && X_host && Z_host && idx_out_host && w_out_host && n_out_host, BASQ_ERR_INVALID,
              "basq_recombine_host: NULL argument");
-  BASQ_CHECK(U_host || Omega_host, BASQ_ERR_INVALID, "basq_recombine_host: need U_host or Omega_host");
   BASQ_CUDA(cudaSetDevice(ctx->device));
   const size_t esz = desc->dtype == BASQ_F64 ? 8 : 4;
   trace_point(ctx, "host: enter");
@@ -1199,7 +1205,7 @@ static int recombine_host_impl(basq_ctx* ctx, const basq_kernel_desc* desc, cons
     cudaError_t e2 = cudaMemcpyAsync(dZ.p, Z_host, esz * (size_t)M * desc->d, cudaMemcpyHostToDevice, ctx->stream);
     if (e2 == cudaSuccess && U_host)
       e2 = cudaMemcpyAsync(dU.p, U_host, sizeof(double) * (size_t)q * M, cudaMemcpyHostToDevice, ctx->stream);
-    if (e2 == cudaSuccess && !U_host) {
+    if (e2 == cudaSuccess && !U_host && Omega_host) {
       rc = dOm.alloc(ctx, sizeof(double) * (size_t)M * q);
       if (rc == BASQ_OK)
         e2 = cudaMemcpyAsync(dOm.p, Omega_host, sizeof(double) * (size_t)M * q, cudaMemcpyHostToDevice, ctx->stream);
@@ -1227,7 +1233,7 @@ static int recombine_host_impl(basq_ctx* ctx, const basq_kernel_desc* desc, cons
   }
   if (!U_host) {
     trace_point(ctx, "host: Z / Omega copies issued");
-    rc = nystrom_basis(ctx, desc, dZ.p, M, q, dOm.as<double>(), niter, dU.as<double>(), nullptr);
+    rc = nystrom_basis(ctx, desc, dZ.p, M, q, Omega_host ? dOm.as<double>() : nullptr, niter, dU.as<double>(), nullptr);
   }
   if (rc == BASQ_OK && cudaStreamWaitEvent(ctx->stream, x_ready, 0) != cudaSuccess) rc = BASQ_ERR_CUDA;
   if (rc != BASQ_OK) {

@@ -82,6 +82,30 @@ __global__ void sample_mvn_kernel(MvnDev p, uint64_t seed, int64_t offset, int64
   }
 }
 
+// out[rows, cols] fp64 standard normals, the stream of sample_mvn_kernel with mean 0 / L = I and no limit
+// on the number of columns: thread (row, blk) draws columns 4 blk .. 4 blk + 3.
+__global__ void standard_normals_kernel(uint64_t seed, int64_t offset, int64_t rows, int cols, double* __restrict__ out) {
+  const int nblk = (cols + 3) / 4;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * nblk) return;
+  const int64_t i = t / nblk;
+  const int blk = (int)(t % nblk);
+  const uint64_t g = (uint64_t)(offset + i);
+  uint32_t r[4];
+  philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)blk, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const double u0 = ((double)(r[2 * h] >> 8) + 0.5) * 5.9604644775390625e-08;      // 2^-24
+    const double u1 = ((double)(r[2 * h + 1] >> 8) + 0.5) * 5.9604644775390625e-08;
+    double sd, cd;
+    sincospi(2.0 * u1, &sd, &cd);
+    const double rad = sqrt(-2.0 * log(u0));
+    const int k = blk * 4 + 2 * h;
+    if (k < cols) out[i * cols + k] = rad * cd;
+    if (k + 1 < cols) out[i * cols + k + 1] = rad * sd;
+  }
+}
+
 // log N(x; mean, L L^T) = -1/2 |L^-1 (x - mean)|^2 - sum log L_ii - d/2 log 2 pi
 template <typename T>
 __global__ void mvn_logpdf_kernel(MvnDev p, double log_norm, const T* __restrict__ X, int64_t N,
@@ -219,11 +243,28 @@ int sum_device(basq_ctx* ctx, const double* w, int64_t N, double* total_dev) {
   return BASQ_OK;
 }
 
+int standard_normals(basq_ctx* ctx, uint64_t seed, int64_t offset, int64_t rows, int cols, double* out) {
+  if (rows == 0 || cols == 0) return BASQ_OK;
+  const int64_t threads = rows * ((cols + 3) / 4);
+  standard_normals_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, ctx->stream>>>(seed, offset, rows, cols, out);
+  ctx->launches++;
+  BASQ_CUDA(cudaGetLastError());
+  return BASQ_OK;
+}
+
 }  // namespace basq
 
 using namespace basq;
 
+
 extern "C" {
+
+int basq_standard_normals(basq_ctx* ctx, uint64_t seed, int64_t offset, int64_t rows, int cols, double* out) {
+  BASQ_CHECK(ctx && (out || rows == 0 || cols == 0), BASQ_ERR_INVALID, "basq_standard_normals: NULL argument");
+  BASQ_CHECK(rows >= 0 && cols >= 0 && offset >= 0, BASQ_ERR_INVALID, "basq_standard_normals: negative size or offset");
+  BASQ_CUDA(cudaSetDevice(ctx->device));
+  return standard_normals(ctx, seed, offset, rows, cols, out);
+}
 
 int basq_sample_mvn(basq_ctx* ctx, uint64_t seed, int64_t offset, int64_t N, int d, int dtype,
                     const double* mean_host, const double* chol_host, void* X_out) {

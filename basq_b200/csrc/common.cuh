@@ -66,6 +66,8 @@ struct basq_ctx {
   bool scalar_setsum = false;      // BASQ_SETSUM_SCALAR=1: CUDA-core set-sum kernel for fp32 too (A/B timing)
   bool no_tensor_nystrom = false;  // BASQ_NYSTROM_FP64=1: fp64 GEMMs in the Nystrom iteration for fp32 kernels too (A/B)
   bool no_gpvar = false;           // BASQ_GPVAR=0: chunked fp64-GEMM posterior variance for fp32 inputs too (A/B)
+  uint64_t seed = 0;               // basq_ctx_set_seed: key of the library's own Gaussian draws (Nystrom test matrix)
+  uint64_t draws = 0;              // test matrices drawn since the seed was set (each call uses key seed + draws)
   bool no_nlsum = false;           // BASQ_NLSUM=0: chunked fp64-GEMM path for the non-linear modes in fp32 too (A/B)
   // fp32 inputs are promoted to the fp64 path when max_m |(K_ZX W)_m|_1 exceeds kappa_max (api.cu:
   // session_create_impl); BASQ_F32_KAPPA_MAX overrides, 0 disables
@@ -440,6 +442,8 @@ int gram_matrix(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int6
                 double* out, bool tensor_correction);
 
 // nystrom.cu
+// out[rows, cols] fp64 N(0, 1) draws of the Philox stream `seed` (candidates.cu)
+int standard_normals(basq_ctx* ctx, uint64_t seed, int64_t offset, int64_t rows, int cols, double* out);
 int nystrom_basis(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, int64_t M, int q,
                   const double* Omega, int niter, double* U_out, double* S_out);
 

@@ -489,7 +489,15 @@ int nystrom_basis(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, in
   BASQ_CHECK(M <= 46000, BASQ_ERR_UNSUPPORTED, "nystrom: M=%lld landmarks need a %.1f GB Gram matrix", (long long)M,
              8.0 * M * M / 1e9);
   BASQ_CHECK(niter >= 0 && niter <= 16, BASQ_ERR_INVALID, "nystrom: niter out of range");
-  DevBuf K, Y, Y2;
+  DevBuf K, Y, Y2, drawn;
+  if (!Omega) {
+    // torch.svd_lowrank draws its own Gaussian test matrix (BASQ/_rchq.py:28-31); so does the library when
+    // the caller passes none: Philox stream of key seed + number of earlier draws (basq_ctx_set_seed)
+    BASQ_TRY(drawn.alloc(ctx, sizeof(double) * (size_t)M * q));
+    BASQ_TRY(standard_normals(ctx, ctx->seed + ctx->draws, 0, M, q, drawn.as<double>()));
+    ctx->draws++;
+    Omega = drawn.as<double>();
+  }
   BASQ_TRY(K.alloc(ctx, sizeof(double) * (size_t)M * M));
   BASQ_TRY(Y.alloc(ctx, sizeof(double) * (size_t)M * q));
   OrthWs ws;

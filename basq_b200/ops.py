@@ -53,18 +53,19 @@ def nystrom_basis(kernel, Z, q, omega=None, niter=2, device=None, want_S=True):
     """(S, U): U [q, M] is an orthonormal basis of the randomised range of K(Z, Z) (ker_svd_sparsify,
     BASQ/_rchq.py:28-31) - an arbitrary basis of that span, not the singular vectors (recombination
     only depends on the span); S [q] holds the Rayleigh quotients u_i^T K u_i of its rows, unordered.
-    omega [M, q] defaults to torch.randn on the device, consuming torch's global RNG exactly where
-    torch.svd_lowrank would.  want_S=False skips S (the reference discards it, BASQ/_rchq.py:36)."""
+    omega [M, q] = None lets the library draw the Gaussian test matrix on the device, as torch.svd_lowrank
+    does inside the reference (seed: ``manual_seed`` below / basq_ctx_set_seed).  want_S=False skips S
+    (the reference discards it, BASQ/_rchq.py:36)."""
     spec, ctx, device, dtype = _common(kernel, Z, device)
     Zd = _prep(Z, device, dtype)
     M = len(Zd)
-    if omega is None:
-        omega = torch.randn(M, q, dtype=torch.float64, device=device)
-    omega = _prep(omega, device, torch.float64)
+    if omega is not None:
+        omega = _prep(omega, device, torch.float64)
     desc, keep = spec.to_desc(Zd.shape[1], device, dtype)
     U = torch.empty(q, M, dtype=torch.float64, device=device)
     S = torch.empty(q, dtype=torch.float64, device=device) if want_S else None
-    _lib.check(_lib.lib.basq_nystrom_basis(ctx.handle, C.byref(desc), Zd.data_ptr(), M, int(q), omega.data_ptr(),
+    _lib.check(_lib.lib.basq_nystrom_basis(ctx.handle, C.byref(desc), Zd.data_ptr(), M, int(q),
+                                           omega.data_ptr() if omega is not None else None,
                                            int(niter), U.data_ptr(), S.data_ptr() if want_S else None))
     return S, U
 
@@ -151,7 +152,9 @@ def recombine(kernel, pts_rec, pts_nys, U, mu=None, device=None, obj=None):
 
 def recombine_host(kernel, X_host, Z_host, q, U_host=None, omega_host=None, mu_host=None, niter=2, device="cuda"):
     """The same through basq_recombine_host: HOST (ideally pinned) buffers in, host tensors out;
-    all host<->device copies happen inside the call (bench.py's end-to-end leg)."""
+    all host<->device copies happen inside the call (bench.py's end-to-end leg).  With neither U_host
+    nor omega_host the library draws the Nystrom test matrix on the device (the reference's call shape:
+    torch.svd_lowrank draws its own, BASQ/_rchq.py:28-31)."""
     spec = describe_kernel(kernel)
     device = torch.device(device)
     ctx = _lib.context_for(device)
@@ -165,8 +168,6 @@ def recombine_host(kernel, X_host, Z_host, q, U_host=None, omega_host=None, mu_h
     # the C call copies raw bytes with the descriptor's element size: every buffer must have it
     X_host, Z_host = X_host.contiguous(), Z_host.to(dtype).contiguous()
     N, M = len(X_host), len(Z_host)
-    if U_host is None and omega_host is None:
-        raise ValueError("recombine_host needs U_host [q, M] or omega_host [M, q]")
     if U_host is not None and tuple(U_host.shape) != (q, M):
         raise ValueError(f"U_host has shape {tuple(U_host.shape)}, expected {(q, M)}")
     if omega_host is not None and tuple(omega_host.shape) != (M, q):
@@ -313,6 +314,22 @@ class Session:
         k = C.c_int(0)
         _lib.check(_lib.lib.basq_session_result(self.handle, idx.data_ptr(), w.data_ptr(), self.n, C.byref(k)))
         return idx[: k.value], w[: k.value]
+
+
+def manual_seed(seed: int, device="cuda"):
+    """Seed of the library's own Gaussian draws on `device` (basq_ctx_set_seed): the Nystrom test matrix
+    of nystrom_basis / recombine_host when the caller passes none."""
+    _lib.context_for(torch.device(device)).set_seed(seed)
+
+
+def standard_normals(rows, cols, seed=0, offset=0, device="cuda") -> torch.Tensor:
+    """[rows, cols] fp64 N(0, 1) draws of the Philox stream `seed` (basq_standard_normals)."""
+    device = torch.device(device)
+    ctx = _lib.context_for(device)
+    out = torch.empty(int(rows), int(cols), dtype=torch.float64, device=device)
+    _lib.check(_lib.lib.basq_standard_normals(ctx.handle, int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset), int(rows),
+                                              int(cols), out.data_ptr()))
+    return out
 
 
 def release_memory(device=None, keep_bytes: int = 0):

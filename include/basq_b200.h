@@ -100,6 +100,9 @@ int basq_ctx_trim(basq_ctx* ctx, int64_t keep_bytes);
    (BASQ/_parameters.py:30) makes such GPs easy to produce in low dimension.  kappa_max < 0 leaves the
    threshold unchanged; the outputs (may be NULL) report the last kappa and the number of promotions. */
 int basq_ctx_conditioning(basq_ctx* ctx, double kappa_max, double* last_kappa_host, int64_t* promotions_host);
+/* Key of the library's own Gaussian draws (the Nystrom test matrix when the caller passes none); the
+   k-th draw after this call uses the Philox key seed + k.  Default 0. */
+int basq_ctx_set_seed(basq_ctx* ctx, uint64_t seed);
 /* number of kernels this library has launched on ctx so far (bench.py's gpu_launches) */
 int64_t basq_ctx_launch_count(const basq_ctx* ctx);
 /* kernel evaluations k(z, x) performed by the set-sum kernel on ctx so far (roofline accounting) */
@@ -124,7 +127,9 @@ int basq_gp_predict(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, 
 
 /* ---- Nystrom eigenbasis: ker_svd_sparsify, BASQ/_rchq.py:28-31 ------------------------------ */
 /* Randomised range finder (Halko alg. 4.4, niter subspace iterations, as torch.svd_lowrank) on
-   K(Z,Z) with the caller's Gaussian test matrix Omega[M,q] (fp64).  U_out[q,M] has orthonormal rows
+   K(Z,Z) with the Gaussian test matrix Omega[M,q] (fp64): the caller's, or - Omega NULL, what
+   torch.svd_lowrank does - drawn by the library on the device (basq_standard_normals with the key
+   set by basq_ctx_set_seed plus the number of earlier draws).  U_out[q,M] has orthonormal rows
    spanning the captured range - an arbitrary orthonormal basis of it, NOT the singular vectors: no
    final rotation is applied, because recombination only depends on span(U) (the reference discards
    the singular values, BASQ/_rchq.py:36).  S_out[q] (may be NULL) receives the Rayleigh quotients
@@ -161,7 +166,9 @@ int basq_recombine_objective(basq_ctx* ctx, const basq_kernel_desc* desc, const 
 int basq_car_objective(basq_ctx* ctx, double* A, int n, int C, int lda, double* omega_out);
 /* Same with HOST buffers for X, Z, U, mu and the outputs (the copies are part of the call);
    desc->Xobs / W / alpha stay device pointers (they belong to the GP model, not to the call).
-   If U_host is NULL the basis is built on the device from Omega_host[M,q] (basq_nystrom_basis). */
+   If U_host is NULL the basis is built on the device (basq_nystrom_basis) from Omega_host[M,q], or,
+   when that is NULL too, from a test matrix drawn on the device - the reference's own call shape
+   (recombination(pts_rec, pts_nys, ...) draws inside torch.svd_lowrank, BASQ/_rchq.py:28-31). */
 int basq_recombine_host(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X_host, int64_t N,
                         const void* Z_host, int64_t M, const double* U_host, int q,
                         const double* Omega_host, int niter, const double* mu_host,
@@ -231,6 +238,9 @@ int basq_session_apply_cells(basq_session* s, int64_t R_glob, int64_t off_glob, 
    by `seed` lands in X_out[i], so ranks sample disjoint shards by passing their first global row. */
 int basq_sample_mvn(basq_ctx* ctx, uint64_t seed, int64_t offset, int64_t N, int d, int dtype,
                     const double* mean_host, const double* chol_host, void* X_out);
+/* out[rows, cols] (fp64) ~ N(0, 1): the same stream with mean 0 and L = I, any number of columns (the
+   test matrix R of torch.svd_lowrank, BASQ/_rchq.py:28-31). */
+int basq_standard_normals(basq_ctx* ctx, uint64_t seed, int64_t offset, int64_t rows, int cols, double* out);
 /* out[N] (fp64) = log N(x_i; mean, L L^T): prior.log_prob (BASQ/_sampler.py:136, 204-212),
    Gaussian.pdf (SOBER/_prior.py:120-131). */
 int basq_mvn_logpdf(basq_ctx* ctx, const void* X, int64_t N, int d, int dtype, const double* mean_host,

@@ -38,6 +38,18 @@ def test_sample_matches_oracle_stream(bs, d, dtype):
     assert np.abs(X - ref).max() <= tol * (1.0 + np.abs(ref).max())
 
 
+@pytest.mark.parametrize("rows,cols", [(1000, 39), (257, 1), (64, 999)])
+def test_standard_normals_match_oracle_stream(rows, cols):
+    """basq_standard_normals (the library-drawn Nystrom test matrix): the sample_mvn stream with L = I and any
+    number of columns, against oracle.sampler.standard_normals."""
+    from basq_b200 import ops
+    seed, off = 0xABCDEF987, 77
+    out = ops.standard_normals(rows, cols, seed=seed, offset=off, device=DEV).cpu().numpy()
+    ref = osam.standard_normals(seed, off, rows, cols)
+    assert out.shape == ref.shape and np.abs(out - ref).max() < 1e-11
+    assert ops.standard_normals(0, cols, device=DEV).shape == (0, cols)
+
+
 def test_shards_are_slices_of_one_stream(bs):
     mean, cov, L = _prior(10, seed=1)
     full = bs.sample_mvn(mean, cov, 10_000, seed=7, device=DEV)

@@ -299,6 +299,35 @@ def test_host_buffer_entry(bq):
     assert orchq.moment_residual(Phi, mu, idx, w) < 1e-8
 
 
+def test_host_buffer_entry_draws_its_own_test_matrix(bq):
+    """The reference's call shape: recombination(pts_rec, pts_nys, ...) hands over points only and
+    torch.svd_lowrank draws the Gaussian test matrix itself (BASQ/_rchq.py:28-31).  With neither U_host
+    nor omega_host the library draws it on the device: key = seed + number of earlier draws."""
+    basq_b200, _lib, ops, _ = bq
+    g = torch.Generator().manual_seed(13)
+    N, d, M, n = 20011, 6, 120, 30
+    X = (math.sqrt(2.0) * torch.randn(N, d, generator=g)).pin_memory()
+    Z = X[:M].clone()
+    cov = _plain_model(0, 2.0)
+    mu = torch.full((N,), 1.0 / N, dtype=torch.float64)
+    ops.manual_seed(99, DEV)
+    idx, w = ops.recombine_host(cov.forward, X, Z, n - 1)
+    _check_rule(idx, w, N, n)
+    # the same draw, explicitly: first draw after manual_seed(99) has key 99
+    omega = ops.standard_normals(M, n - 1, seed=99, device=DEV)
+    _, U = ops.nystrom_basis(cov.forward, Z.to(DEV), n - 1, omega=omega)
+    Phi = ops.features(cov.forward, X.to(DEV), Z.to(DEV), U).cpu()
+    assert orchq.moment_residual(Phi, mu, idx, w) < 1e-8
+    # reseeding reproduces the basis (the rule preserves the same moments); the next draw (key 100) is another one
+    ops.manual_seed(99, DEV)
+    idx2, w2 = ops.recombine_host(cov.forward, X, Z, n - 1)
+    assert orchq.moment_residual(Phi, mu, idx2, w2) < 1e-8
+    _, U1 = ops.nystrom_basis(cov.forward, Z.to(DEV), n - 1)          # key 100
+    _, U100 = ops.nystrom_basis(cov.forward, Z.to(DEV), n - 1,
+                                omega=ops.standard_normals(M, n - 1, seed=100, device=DEV))
+    assert torch.allclose(U1, U100, rtol=0, atol=1e-12) and not torch.allclose(U1, U, rtol=0, atol=1e-6)
+
+
 def test_size_independent_properties_large(bq):
     """At a size the CPU oracle cannot finish quickly: N = 2e6, d = 10, n = 200.  Size-independent
     properties: mass, positivity, count, and moments for a random subset of test functions
