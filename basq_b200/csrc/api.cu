@@ -125,6 +125,11 @@ using namespace basq;
 // =============================================================================================
 // session
 // =============================================================================================
+struct Piece {   // a typed view of a slice of the context's host-call buffer (basq_recombine_host)
+  void* p = nullptr;
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
 struct basq_session {
   basq_ctx* ctx = nullptr;
   basq_kernel_desc desc;
@@ -164,37 +169,6 @@ struct basq_session {
   bool scale_wf = true;
   std::vector<double> omega_host;
   std::vector<int> rank_host;
-  // Pinned staging ring for the small per-level host arrays (node ids, parent positions, parent factors): the
-  // H2D copies read from a slot of this ring, so the level calls return without synchronising the stream and
-  // the caller may reuse its arrays at once; a slot is reused only after the event recorded behind its copies.
-  static constexpr int STAGE_SLOTS = 8;
-  unsigned char* stage = nullptr;
-  size_t stage_slot_bytes = 0;
-  cudaEvent_t stage_ev[STAGE_SLOTS] = {nullptr};
-  int stage_next = 0;
-  ~basq_session() {
-    if (stage) {
-      if (ctx) cudaStreamSynchronize(ctx->stream);
-      cudaFreeHost(stage);
-    }
-    for (cudaEvent_t e : stage_ev)
-      if (e) cudaEventDestroy(e);
-    (void)cudaGetLastError();
-  }
-  // a free slot (ints first, doubles behind them: [S ints][S ints][S doubles])
-  int stage_take(unsigned char** slot_out, int* slot_index) {
-    if (!stage) {
-      stage_slot_bytes = (size_t)S * 16;
-      BASQ_CUDA(cudaHostAlloc((void**)&stage, stage_slot_bytes * STAGE_SLOTS, cudaHostAllocDefault));
-      for (int i = 0; i < STAGE_SLOTS; ++i) BASQ_CUDA(cudaEventCreateWithFlags(&stage_ev[i], cudaEventDisableTiming));
-    }
-    const int i = stage_next;
-    stage_next = (stage_next + 1) % STAGE_SLOTS;
-    BASQ_CUDA(cudaEventSynchronize(stage_ev[i]));   // returns at once for a never-recorded / completed event
-    *slot_out = stage + (size_t)i * stage_slot_bytes;
-    *slot_index = i;
-    return BASQ_OK;
-  }
 };
 
 namespace basq {
@@ -445,6 +419,31 @@ int session_pass_begin(basq_session* s, int64_t R_glob, int64_t off, int F) {
 //   fold:    Gf_out[m, i] = sum_k G[m, node[i] + k (S << lvl)]   for m < Mtot, i < K   (ld = ld_gf)
 //   project: rows 1..q of the level's raw columns = U'[:, row0 .. row0 + nrows) Gf_rows[nrows, K];
 //            masses / objective rows from this rank's cells; high halves by linearity; A_out scaled.
+// Pinned staging ring of the context for the small per-level host arrays (node ids, parent positions, parent
+// factors): the H2D copies read from a slot of this ring, so the level calls return without synchronising the
+// stream and the caller may reuse its arrays at once; a slot is reused only after the event recorded behind
+// its copies.  Allocated once per context (cudaHostAlloc / cudaFreeHost synchronise the device).
+int stage_take(basq_ctx* ctx, size_t bytes, unsigned char** slot_out, int* slot_index) {
+  if (bytes > ctx->stage_slot_bytes) {
+    if (ctx->stage) {
+      BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+      BASQ_CUDA(cudaFreeHost(ctx->stage));
+      ctx->stage = nullptr;
+    }
+    const size_t slot = std::max<size_t>(bytes, 64 << 10);
+    BASQ_CUDA(cudaHostAlloc((void**)&ctx->stage, slot * basq_ctx::STAGE_SLOTS, cudaHostAllocDefault));
+    ctx->stage_slot_bytes = slot;
+    for (int i = 0; i < basq_ctx::STAGE_SLOTS; ++i)
+      if (!ctx->stage_ev[i]) BASQ_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+  }
+  const int i = ctx->stage_next;
+  ctx->stage_next = (ctx->stage_next + 1) % basq_ctx::STAGE_SLOTS;
+  BASQ_CUDA(cudaEventSynchronize(ctx->stage_ev[i]));   // returns at once for a never-recorded / completed event
+  *slot_out = ctx->stage + (size_t)i * ctx->stage_slot_bytes;
+  *slot_index = i;
+  return BASQ_OK;
+}
+
 int session_level_check(basq_session* s, int lvl, int K, const int* node_host, const int* ppos_host) {
   const int S = s->S, F = s->pass_F;
   BASQ_CHECK(F >= 1 && lvl >= 0 && (1 << lvl) <= F, BASQ_ERR_INVALID, "level %d outside the pass (F = %d)", lvl, F);
@@ -465,10 +464,10 @@ int session_level_fold(basq_session* s, int lvl, int K, const int* node_host, do
   const int stride = s->S << lvl, cnt = s->pass_F >> lvl;
   unsigned char* slot = nullptr;
   int si = 0;
-  BASQ_TRY(s->stage_take(&slot, &si));
+  BASQ_TRY(stage_take(ctx, (size_t)s->S * 16, &slot, &si));
   memcpy(slot, node_host, sizeof(int) * K);
   BASQ_CUDA(cudaMemcpyAsync(s->lnode.p, slot, sizeof(int) * K, cudaMemcpyHostToDevice, ctx->stream));
-  BASQ_CUDA(cudaEventRecord(s->stage_ev[si], ctx->stream));
+  BASQ_CUDA(cudaEventRecord(ctx->stage_ev[si], ctx->stream));
   fold_cols_kernel<<<(unsigned)ceil_div64((int64_t)s->Mtot * K, 256), 256, 0, ctx->stream>>>(
       s->G.as<double>(), s->ldg, s->Mtot, K, s->lnode.as<int>(), stride, cnt, Gf_out, ld_gf);
   ctx->launches++;
@@ -488,7 +487,7 @@ int session_level_project(basq_session* s, int lvl, int K, const int* node_host,
   {
     unsigned char* slot = nullptr;
     int si = 0;
-    BASQ_TRY(s->stage_take(&slot, &si));
+    BASQ_TRY(stage_take(ctx, (size_t)s->S * 16, &slot, &si));
     int* h_node = reinterpret_cast<int*>(slot);
     int* h_ppos = h_node + S;
     double* h_fpar = reinterpret_cast<double*>(slot + (size_t)S * 8);
@@ -498,7 +497,7 @@ int session_level_project(basq_session* s, int lvl, int K, const int* node_host,
     BASQ_CUDA(cudaMemcpyAsync(s->lnode.p, h_node, sizeof(int) * K, cudaMemcpyHostToDevice, ctx->stream));
     if (lvl > 0) BASQ_CUDA(cudaMemcpyAsync(s->lppos.p, h_ppos, sizeof(int) * K, cudaMemcpyHostToDevice, ctx->stream));
     BASQ_CUDA(cudaMemcpyAsync(s->lfpar.p, h_fpar, sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
-    BASQ_CUDA(cudaEventRecord(s->stage_ev[si], ctx->stream));
+    BASQ_CUDA(cudaEventRecord(ctx->stage_ev[si], ctx->stream));
   }
   BASQ_CUDA(cudaMemsetAsync(A_out, 0, sizeof(double) * (size_t)rows * S, ctx->stream));
   double* raw = s->raw[s->raw_cur].as<double>();
@@ -895,6 +894,17 @@ void basq_ctx_destroy(basq_ctx* ctx) {
   if (!ctx) return;
   ctx->resolve_spans();
   for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
+  if (ctx->stage || ctx->side) cudaStreamSynchronize(ctx->stream);
+  if (ctx->side) {
+    cudaStreamSynchronize(ctx->side);
+    cudaStreamDestroy(ctx->side);
+  }
+  for (cudaEvent_t e : ctx->side_ev)
+    if (e) cudaEventDestroy(e);
+  if (ctx->stage) cudaFreeHost(ctx->stage);
+  if (ctx->host_x) cudaFree(ctx->host_x);
+  for (cudaEvent_t e : ctx->stage_ev)
+    if (e) cudaEventDestroy(e);
   if (ctx->pool) {
     cudaStreamSynchronize(ctx->stream);
     cudaMemPoolDestroy(ctx->pool);
@@ -905,6 +915,12 @@ void basq_ctx_destroy(basq_ctx* ctx) {
 
 int basq_ctx_trim(basq_ctx* ctx, int64_t keep_bytes) {
   BASQ_CHECK(ctx, BASQ_ERR_INVALID, "ctx is NULL");
+  if (keep_bytes >= 0 && ctx->host_x) {   // an explicit request also drops the candidate buffer of basq_recombine_host
+    BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    BASQ_CUDA(cudaFree(ctx->host_x));
+    ctx->host_x = nullptr;
+    ctx->host_x_bytes = 0;
+  }
   if (!ctx->pool) return BASQ_OK;
   const uint64_t keep = keep_bytes < 0 ? ctx->pool_keep : (uint64_t)keep_bytes;
   if (keep == UINT64_MAX) return BASQ_OK;
@@ -1179,25 +1195,45 @@ static int recombine_host_impl(basq_ctx* ctx, const basq_kernel_desc* desc, cons
   BASQ_CUDA(cudaSetDevice(ctx->device));
   const size_t esz = desc->dtype == BASQ_F64 ? 8 : 4;
   trace_point(ctx, "host: enter");
-  DevBuf dX, dZ, dU, dOm, dmu, didx, dw;
-  BASQ_TRY(dX.alloc(ctx, esz * (size_t)N * desc->d));
-  BASQ_TRY(dZ.alloc(ctx, esz * (size_t)M * desc->d));
-  BASQ_TRY(dU.alloc(ctx, sizeof(double) * (size_t)q * M));
-  BASQ_TRY(didx.alloc(ctx, sizeof(int64_t) * (q + 1)));
-  BASQ_TRY(dw.alloc(ctx, sizeof(double) * (q + 1)));
+  // All call-lifetime device copies of the host arguments live in ONE buffer the context keeps between calls,
+  // outside the stream-ordered pool: the pool then sees exactly the requests of the device-resident path.
+  DevBuf dOm;
+  Piece dX, dZ, dU, didx, dw;
+  double* dmu_p = nullptr;
+  {
+    auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t bX = up(esz * (size_t)N * desc->d), bmu = mu_host ? up(sizeof(double) * (size_t)N) : 0;
+    const size_t bZ = up(esz * (size_t)M * desc->d), bU = up(sizeof(double) * (size_t)q * M);
+    const size_t bi = up(sizeof(int64_t) * (q + 1)), bw = up(sizeof(double) * (q + 1));
+    const size_t need = bX + bmu + bZ + bU + bi + bw;
+    if (need > ctx->host_x_bytes) {
+      if (ctx->host_x) {
+        BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+        BASQ_CUDA(cudaFree(ctx->host_x));
+        ctx->host_x = nullptr;
+        ctx->host_x_bytes = 0;
+      }
+      BASQ_CUDA(cudaMalloc(&ctx->host_x, need));
+      ctx->host_x_bytes = need;
+    }
+    unsigned char* base = static_cast<unsigned char*>(ctx->host_x);
+    dX.p = base;
+    if (mu_host) dmu_p = reinterpret_cast<double*>(base + bX);
+    dZ.p = base + bX + bmu;
+    dU.p = base + bX + bmu + bZ;
+    didx.p = base + bX + bmu + bZ + bU;
+    dw.p = base + bX + bmu + bZ + bU + bi;
+  }
   // The candidates (the bulk of the bytes) travel on a side stream while the basis is built from the
   // landmarks on the main stream: the Nystrom phase hides the host-to-device copy.
-  cudaStream_t side = nullptr;
-  cudaEvent_t x_ready = nullptr, buffers_ready = nullptr;
-  BASQ_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-  BASQ_CUDA(cudaEventCreateWithFlags(&x_ready, cudaEventDisableTiming));
-  BASQ_CUDA(cudaEventCreateWithFlags(&buffers_ready, cudaEventDisableTiming));
-  auto cleanup = [&]() {
-    cudaStreamSynchronize(side);
-    cudaEventDestroy(x_ready);
-    cudaEventDestroy(buffers_ready);
-    cudaStreamDestroy(side);
-  };
+  if (!ctx->side) {   // created once per context: stream / event creation and destruction take driver-wide locks
+    BASQ_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    BASQ_CUDA(cudaEventCreateWithFlags(&ctx->side_ev[0], cudaEventDisableTiming));
+    BASQ_CUDA(cudaEventCreateWithFlags(&ctx->side_ev[1], cudaEventDisableTiming));
+  }
+  cudaStream_t side = ctx->side;
+  cudaEvent_t x_ready = ctx->side_ev[0], buffers_ready = ctx->side_ev[1];
+  auto cleanup = [&]() { cudaStreamSynchronize(side); };   // the next call reuses the candidate buffer: the copy must be over
   // Landmarks and the test matrix go first (the copy engine serves requests in order, and the basis
   // cannot start without them); the candidates follow on the side stream.
   int rc = BASQ_OK;
@@ -1215,16 +1251,15 @@ static int recombine_host_impl(basq_ctx* ctx, const basq_kernel_desc* desc, cons
       rc = BASQ_ERR_CUDA;
     }
   }
-  if (rc == BASQ_OK && mu_host) rc = dmu.alloc(ctx, sizeof(double) * N);
   if (rc != BASQ_OK) {
     cleanup();
     return rc;
   }
-  BASQ_CUDA(cudaEventRecord(buffers_ready, ctx->stream));        // dX / dmu come from the stream-ordered pool
+  BASQ_CUDA(cudaEventRecord(buffers_ready, ctx->stream));        // earlier work on the main stream may still read the candidate buffer
   BASQ_CUDA(cudaStreamWaitEvent(side, buffers_ready, 0));
   cudaError_t ce = cudaMemcpyAsync(dX.p, X_host, esz * (size_t)N * desc->d, cudaMemcpyHostToDevice, side);
   if (ce == cudaSuccess && mu_host)
-    ce = cudaMemcpyAsync(dmu.p, mu_host, sizeof(double) * N, cudaMemcpyHostToDevice, side);
+    ce = cudaMemcpyAsync(dmu_p, mu_host, sizeof(double) * N, cudaMemcpyHostToDevice, side);
   if (ce == cudaSuccess) ce = cudaEventRecord(x_ready, side);
   if (ce != cudaSuccess) {
     cleanup();
@@ -1242,7 +1277,7 @@ static int recombine_host_impl(basq_ctx* ctx, const basq_kernel_desc* desc, cons
   }
   trace_point(ctx, "host: inputs + basis on device");
   int n_out = 0;
-  rc = recombine_impl(ctx, desc, dX.p, N, dZ.p, M, dU.as<double>(), q, mu_host ? dmu.as<double>() : nullptr,
+  rc = recombine_impl(ctx, desc, dX.p, N, dZ.p, M, dU.as<double>(), q, dmu_p,
                       didx.as<int64_t>(), dw.as<double>(), &n_out);
   cleanup();
   if (rc != BASQ_OK) return rc;

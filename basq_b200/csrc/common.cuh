@@ -66,6 +66,20 @@ struct basq_ctx {
   bool scalar_setsum = false;      // BASQ_SETSUM_SCALAR=1: CUDA-core set-sum kernel for fp32 too (A/B timing)
   bool no_tensor_nystrom = false;  // BASQ_NYSTROM_FP64=1: fp64 GEMMs in the Nystrom iteration for fp32 kernels too (A/B)
   bool no_gpvar = false;           // BASQ_GPVAR=0: chunked fp64-GEMM posterior variance for fp32 inputs too (A/B)
+  // per-context driver objects that are expensive to create per call (api.cu): pinned staging ring of the level
+  // calls, side stream + events of basq_recombine_host
+  static constexpr int STAGE_SLOTS = 8;
+  unsigned char* stage = nullptr;
+  size_t stage_slot_bytes = 0;
+  cudaEvent_t stage_ev[STAGE_SLOTS] = {nullptr};
+  int stage_next = 0;
+  cudaStream_t side = nullptr;
+  // candidate buffer of basq_recombine_host, kept between calls and outside the pool: carving 400 MB out of the
+  // pool's free blocks before every other request reshuffles them from call to call (observed: steps of
+  // 127-245 ms and an occasional second of re-growth where the device-resident path takes a steady 125 ms)
+  void* host_x = nullptr;
+  size_t host_x_bytes = 0;
+  cudaEvent_t side_ev[2] = {nullptr, nullptr};
   uint64_t seed = 0;               // basq_ctx_set_seed: key of the library's own Gaussian draws (Nystrom test matrix)
   uint64_t draws = 0;              // test matrices drawn since the seed was set (each call uses key seed + draws)
   bool no_nlsum = false;           // BASQ_NLSUM=0: chunked fp64-GEMM path for the non-linear modes in fp32 too (A/B)
@@ -430,9 +444,11 @@ int gp_variance_tc(basq_ctx* ctx, const basq_kernel_desc* desc, const KParams& k
 // dgemm.cu
 int dgemm(basq_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const double* A, int64_t lda,
           const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool b_lower_tri = false,
-          bool a_lower_tri = false);
+          bool a_lower_tri = false, bool c_symmetric = false);
 // b_lower_tri (with tb): B is lower triangular, C = A B^T only visits k <= column
 // a_lower_tri (without ta): A is lower triangular, C = A B only visits k <= row
+// c_symmetric (m == n, beta == 0; e.g. A^T A): only the tiles that touch the lower triangle are computed, the
+//   K range is split so that they still fill the SMs, and the upper triangle is the mirror image
 
 // car.cu
 int caratheodory(basq_ctx* ctx, double* A, int n, int S, int lda, double* omega_out);

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(WM* WN * 32) dgemm_pipe_kernel(int M, int N, i
                                                                 const double* __restrict__ A, int64_t lda,
                                                                 const double* __restrict__ B, int64_t ldb, double beta,
                                                                 double* __restrict__ C, int64_t ldc, int tri_k, int a16,
-                                                                int b16, int kchunk, double* __restrict__ part) {
+                                                                int b16, int kchunk, double* __restrict__ part, int sym) {
   constexpr int BM = WM * 8 * MF, BNN = WN * 8 * NF, NTHR = WM * WN * 32;
   constexpr int AS = TA ? BM + 4 : PK + 4, BS = TB ? PK + 4 : BNN + 4;
   constexpr int A_EL = TA ? PK * (BM + 4) : BM * (PK + 4);
@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(WM* WN * 32) dgemm_pipe_kernel(int M, int N, i
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp / WN, wn = warp % WN;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BNN;
+  if (sym && n0 >= m0 + BM) return;     // tile strictly above the diagonal: mirrored afterwards
   if (tri_k & 1) K = min(K, n0 + BNN);  // op(B)[k][n] = 0 for k > n
   if (tri_k & 2) K = min(K, m0 + BM);   // op(A)[m][k] = 0 for k > m
   // split-K (small outputs, long K): slice blockIdx.z covers k in [kb, K) with K clipped to the slice
@@ -179,19 +180,30 @@ __global__ void __launch_bounds__(WM* WN * 32) dgemm_pipe_kernel(int M, int N, i
 }
 
 // C = alpha * (sum of the slices, in slice order: deterministic) + beta * C
+// sym: entries above the diagonal take the sums of their mirror image (their own tiles were skipped)
 __global__ void splitk_reduce_kernel(const double* __restrict__ part, int splits, int M, int N, double alpha,
-                                     double beta, double* __restrict__ C, int64_t ldc) {
+                                     double beta, double* __restrict__ C, int64_t ldc, int sym) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (int64_t)M * N) return;
+  const int64_t r = t / N, cidx = t % N;
+  const int64_t src = (sym && cidx > r) ? cidx * N + r : t;
   double s = 0.0;
-  for (int z = 0; z < splits; ++z) s += part[(int64_t)z * M * N + t];
+  for (int z = 0; z < splits; ++z) s += part[(int64_t)z * M * N + src];
   double* c = C + (t / N) * ldc + (t % N);
   *c = (beta == 0.0) ? alpha * s : fma(alpha, s, beta * (*c));
 }
 
+// C[r][c] = C[c][r] for c > r (square, after a c_symmetric product without split-K)
+__global__ void mirror_lower_kernel(double* __restrict__ C, int N, int64_t ldc) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)N * N) return;
+  const int64_t r = t / N, c = t % N;
+  if (c > r) C[r * ldc + c] = C[c * ldc + r];
+}
+
 template <bool TA, bool TB, int WM, int WN, int MF, int NF>
 int launch_pipe(basq_ctx* ctx, int m, int n, int k, double alpha, const double* A, int64_t lda, const double* B,
-                int64_t ldb, double beta, double* C, int64_t ldc, int tri_k) {
+                int64_t ldb, double beta, double* C, int64_t ldc, int tri_k, int sym) {
   constexpr int BM = WM * 8 * MF, BNN = WN * 8 * NF;
   constexpr int A_EL = TA ? PK * (BM + 4) : BM * (PK + 4);
   constexpr int B_EL = TB ? BNN * (PK + 4) : PK * (BNN + 4);
@@ -202,13 +214,21 @@ int launch_pipe(basq_ctx* ctx, int m, int n, int k, double alpha, const double* 
   dim3 grid((unsigned)ceil_div(n, BNN), (unsigned)ceil_div(m, BM));
   // split-K when the output has far fewer tiles than the GPU has SMs and K is long (e.g. the 99 x 200
   // projection of a batch of 100 over 10^4 landmarks, the q x q Gram matrices of CholeskyQR)
-  const int64_t tiles = (int64_t)grid.x * grid.y;
+  int64_t tiles = (int64_t)grid.x * grid.y;
+  if (sym) {  // only the tiles with n0 < m0 + BM do any work
+    tiles = 0;
+    for (unsigned by = 0; by < grid.y; ++by) tiles += std::min<int64_t>(grid.x, ceil_div64((int64_t)(by + 1) * BM, BNN));
+  }
   int splits = 1;
   if (tri_k == 0 && tiles * 2 <= ctx->num_sms && k >= 16 * PK)
     splits = (int)std::min<int64_t>(ctx->num_sms / tiles, k / (8 * PK));
   if (splits <= 1) {
     kern<<<grid, WM * WN * 32, SMEM, ctx->stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k, a16, b16, 0,
-                                                    nullptr);
+                                                    nullptr, sym);
+    if (sym) {
+      mirror_lower_kernel<<<(unsigned)ceil_div64((int64_t)n * n, 256), 256, 0, ctx->stream>>>(C, n, ldc);
+      ctx->launches++;
+    }
     return BASQ_OK;
   }
   const int kchunk = ceil_div(ceil_div(k, splits), PK) * PK;
@@ -217,9 +237,9 @@ int launch_pipe(basq_ctx* ctx, int m, int n, int k, double alpha, const double* 
   BASQ_TRY(part.alloc(ctx, sizeof(double) * (size_t)splits * m * n));
   grid.z = (unsigned)splits;
   kern<<<grid, WM * WN * 32, SMEM, ctx->stream>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k, a16, b16, kchunk,
-                                                  part.as<double>());
+                                                  part.as<double>(), sym);
   splitk_reduce_kernel<<<(unsigned)ceil_div64((int64_t)m * n, 256), 256, 0, ctx->stream>>>(part.as<double>(), splits, m, n,
-                                                                                          alpha, beta, C, ldc);
+                                                                                          alpha, beta, C, ldc, sym);
   ctx->launches++;
   return BASQ_OK;  // `part` returns to the stream-ordered pool after the reduction
 }
@@ -227,29 +247,37 @@ int launch_pipe(basq_ctx* ctx, int m, int n, int k, double alpha, const double* 
 // tile shape that needs the fewest SM-waves of work for an m x n output
 template <bool TA, bool TB>
 int launch_best(basq_ctx* ctx, int m, int n, int k, double alpha, const double* A, int64_t lda, const double* B,
-                int64_t ldb, double beta, double* C, int64_t ldc, int tri_k) {
+                int64_t ldb, double beta, double* C, int64_t ldc, int tri_k, int sym) {
   auto cost = [&](int bm, int bn) {
     const int64_t tiles = (int64_t)ceil_div(m, bm) * ceil_div(n, bn);
     return (double)ceil_div64(tiles, ctx->num_sms) * bm * bn;
   };
+  // symmetric output: the smallest tile wastes the least work on the diagonal blocks and splits K most evenly
+  if (sym) return launch_pipe<TA, TB, 2, 4, 4, 4>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k, sym);
   const double c0 = cost(128, 128), c1 = cost(128, 112), c2 = cost(64, 128);
-  if (c1 < c0 && c1 <= c2) return launch_pipe<TA, TB, 4, 2, 4, 7>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k);
-  if (c2 < c0) return launch_pipe<TA, TB, 2, 4, 4, 4>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k);
-  return launch_pipe<TA, TB, 2, 4, 8, 4>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k);
+  if (c1 < c0 && c1 <= c2) return launch_pipe<TA, TB, 4, 2, 4, 7>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k, 0);
+  if (c2 < c0) return launch_pipe<TA, TB, 2, 4, 4, 4>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k, 0);
+  return launch_pipe<TA, TB, 2, 4, 8, 4>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k, 0);
 }
 
 }  // namespace
 
 int dgemm(basq_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, const double* A, int64_t lda,
-          const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool b_lower_tri, bool a_lower_tri) {
+          const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool b_lower_tri, bool a_lower_tri,
+          bool c_symmetric) {
+  BASQ_CHECK(!c_symmetric || (m == n && beta == 0.0 && !b_lower_tri && !a_lower_tri), BASQ_ERR_INVALID,
+             "dgemm: c_symmetric needs a square output, beta = 0 and dense operands");
+  // A^T A and A A^T are recognised without the flag
+  const bool gram = (ta != tb) && A == B && lda == ldb && m == n && beta == 0.0 && !b_lower_tri && !a_lower_tri;
+  const int sym = (c_symmetric || gram) ? 1 : 0;
   const int tri_k = ((b_lower_tri && tb) ? 1 : 0) | ((a_lower_tri && !ta) ? 2 : 0);
   if (m <= 0 || n <= 0) return BASQ_OK;
   BASQ_CHECK(k >= 0, BASQ_ERR_INVALID, "dgemm: negative k");
   BASQ_CHECK(ceil_div(m, 64) <= 65535, BASQ_ERR_UNSUPPORTED, "dgemm: m=%d too large for one launch", m);
-  if (!ta && !tb) BASQ_TRY((launch_best<false, false>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k)));
-  else if (ta && !tb) BASQ_TRY((launch_best<true, false>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k)));
-  else if (!ta && tb) BASQ_TRY((launch_best<false, true>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k)));
-  else BASQ_TRY((launch_best<true, true>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k)));
+  if (!ta && !tb) BASQ_TRY((launch_best<false, false>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k, sym)));
+  else if (ta && !tb) BASQ_TRY((launch_best<true, false>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k, sym)));
+  else if (!ta && tb) BASQ_TRY((launch_best<false, true>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k, sym)));
+  else BASQ_TRY((launch_best<true, true>(ctx, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri_k, sym)));
   ctx->launches++;
   BASQ_CUDA(cudaGetLastError());
   return BASQ_OK;

@@ -425,7 +425,8 @@ int orthonormalise(basq_ctx* ctx, OrthWs& ws, double* Y, int64_t M, int q, int p
   const bool adaptive = passes < 0;
   if (adaptive) passes = 4;
   for (int pass = 0; pass < passes; ++pass) {
-    BASQ_TRY(dgemm(ctx, true, false, q, q, (int)M, 1.0, Y, q, Y, q, 0.0, ws.gram.as<double>(), q));
+    BASQ_TRY(dgemm(ctx, true, false, q, q, (int)M, 1.0, Y, q, Y, q, 0.0, ws.gram.as<double>(), q, false, false,
+                   /*c_symmetric=*/true));
     BASQ_CUDA(cudaMemsetAsync(ws.scal.p, 0, 2 * sizeof(double), ctx->stream));
     trace_kernel<<<1, 256, 0, ctx->stream>>>(ws.gram.as<double>(), q, q, ws.scal.as<double>());
     ctx->launches++;

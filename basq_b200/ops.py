@@ -49,18 +49,29 @@ def gp_predict(kernel, X, space=0, want_var=True, device=None):
     return mean, var
 
 
-def nystrom_basis(kernel, Z, q, omega=None, niter=2, device=None, want_S=True):
+def _seed_context(ctx, seed):
+    """Key of the library's next Gaussian draw: the caller's, or - like every torch routine the reference
+    calls - the next value of torch's global generator, so that torch.manual_seed reproduces a run."""
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64))
+    ctx.set_seed(seed)
+
+
+def nystrom_basis(kernel, Z, q, omega=None, niter=2, device=None, want_S=True, seed=None):
     """(S, U): U [q, M] is an orthonormal basis of the randomised range of K(Z, Z) (ker_svd_sparsify,
     BASQ/_rchq.py:28-31) - an arbitrary basis of that span, not the singular vectors (recombination
     only depends on the span); S [q] holds the Rayleigh quotients u_i^T K u_i of its rows, unordered.
     omega [M, q] = None lets the library draw the Gaussian test matrix on the device, as torch.svd_lowrank
-    does inside the reference (seed: ``manual_seed`` below / basq_ctx_set_seed).  want_S=False skips S
-    (the reference discards it, BASQ/_rchq.py:36)."""
+    does inside the reference; its Philox key is `seed`, by default the next value of torch's global generator
+    (torch.manual_seed reproduces the basis, as it does in the reference).  want_S=False skips S (the
+    reference discards it, BASQ/_rchq.py:36)."""
     spec, ctx, device, dtype = _common(kernel, Z, device)
     Zd = _prep(Z, device, dtype)
     M = len(Zd)
     if omega is not None:
         omega = _prep(omega, device, torch.float64)
+    else:
+        _seed_context(ctx, seed)
     desc, keep = spec.to_desc(Zd.shape[1], device, dtype)
     U = torch.empty(q, M, dtype=torch.float64, device=device)
     S = torch.empty(q, dtype=torch.float64, device=device) if want_S else None
@@ -150,11 +161,12 @@ def recombine(kernel, pts_rec, pts_nys, U, mu=None, device=None, obj=None):
     return idx[: n_out.value], w[: n_out.value]
 
 
-def recombine_host(kernel, X_host, Z_host, q, U_host=None, omega_host=None, mu_host=None, niter=2, device="cuda"):
+def recombine_host(kernel, X_host, Z_host, q, U_host=None, omega_host=None, mu_host=None, niter=2, device="cuda",
+                   seed=None):
     """The same through basq_recombine_host: HOST (ideally pinned) buffers in, host tensors out;
     all host<->device copies happen inside the call (bench.py's end-to-end leg).  With neither U_host
     nor omega_host the library draws the Nystrom test matrix on the device (the reference's call shape:
-    torch.svd_lowrank draws its own, BASQ/_rchq.py:28-31)."""
+    torch.svd_lowrank draws its own, BASQ/_rchq.py:28-31) with the Philox key `seed` (see nystrom_basis)."""
     spec = describe_kernel(kernel)
     device = torch.device(device)
     ctx = _lib.context_for(device)
@@ -188,6 +200,8 @@ def recombine_host(kernel, X_host, Z_host, q, U_host=None, omega_host=None, mu_h
         omega_host = omega_host.to(torch.float64).contiguous()
     if mu_host is not None:
         mu_host = mu_host.to(torch.float64).contiguous()
+    if U_host is None and omega_host is None:
+        _seed_context(ctx, seed)
     _lib.check(_lib.lib.basq_recombine_host(ctx.handle, C.byref(desc), X_host.data_ptr(), len(X_host),
                                             Z_host.data_ptr(), len(Z_host), ptr(U_host), int(q), ptr(omega_host),
                                             int(niter), ptr(mu_host), idx.data_ptr(), w.data_ptr(),
@@ -314,12 +328,6 @@ class Session:
         k = C.c_int(0)
         _lib.check(_lib.lib.basq_session_result(self.handle, idx.data_ptr(), w.data_ptr(), self.n, C.byref(k)))
         return idx[: k.value], w[: k.value]
-
-
-def manual_seed(seed: int, device="cuda"):
-    """Seed of the library's own Gaussian draws on `device` (basq_ctx_set_seed): the Nystrom test matrix
-    of nystrom_basis / recombine_host when the caller passes none."""
-    _lib.context_for(torch.device(device)).set_seed(seed)
 
 
 def standard_normals(rows, cols, seed=0, offset=0, device="cuda") -> torch.Tensor:

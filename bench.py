@@ -439,11 +439,10 @@ def run_ours(a, rank, world, local_rank):
         X_host.copy_(X)
         Z_host = Z.cpu().pin_memory()
         # no test matrix travels: like torch.svd_lowrank inside the reference, the library draws it on the device
-        ops.manual_seed(7, dev)
 
     def step_e2e():
         if world == 1:
-            return ops.recombine_host(kern, X_host, Z_host, q, device=dev)
+            return ops.recombine_host(kern, X_host, Z_host, q, device=dev, seed=7)
         # landmarks first (the copy engine is FIFO), candidates on a side stream underneath
         # the Nystrom phase - what basq_recombine_host does inside the C call at N = 1
         main = torch.cuda.current_stream(dev)
@@ -451,7 +450,7 @@ def run_ours(a, rank, world, local_rank):
         with torch.cuda.stream(side_stream):
             Xd = X_host.to(dev, non_blocking=True)
         x_ready = side_stream.record_event()
-        _, U = ops.nystrom_basis(kern, Zd, q, want_S=False)     # every rank draws the same matrix (same seed, same count)
+        _, U = ops.nystrom_basis(kern, Zd, q, want_S=False, seed=7)     # every rank draws the same matrix
         main.wait_event(x_ready)
         Xd.record_stream(main)
         idx, w = sharded.recombination_sharded(Xd, Zd, a.n, kern, N_glob, base, U)

@@ -12,7 +12,7 @@ N = int(os.environ.get("N", 10_000_000))
 M, n, d, n_obs = 10_000, 1000, 10, 1002
 q = n - 1
 Xo, yo = bench.make_observations(d, n_obs)
-model = bgp.FixedGP(Xo.to(dev, torch.float32), yo.to(dev), bgp.ScaleKernel(bgp.RBFKernel(bench.LENGTHSCALE), 1.0), noise=bench.NOISE)
+model = bgp.FixedGP(Xo.to(dev, torch.float32), yo.to(dev), bgp.ScaleKernel(bgp.RBFKernel(2.5), 1.0), noise=1e-10)
 kern = spec_from_model(model, _lib.PRED_COV)
 g = torch.Generator(device=dev).manual_seed(1000)
 X = math.sqrt(2.0) * torch.randn(N, d, generator=g, device=dev, dtype=torch.float32)

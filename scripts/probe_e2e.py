@@ -10,7 +10,7 @@ dev = torch.device("cuda:0")
 N = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10_000_000
 d, M, q, n_obs = 10, 10000, 999, 1002
 Xo, yo = bench.make_observations(d, n_obs)
-model = bgp.FixedGP(Xo.to(dev, torch.float32), yo.to(dev), bgp.ScaleKernel(bgp.RBFKernel(bench.LENGTHSCALE), 1.0), noise=bench.NOISE)
+model = bgp.FixedGP(Xo.to(dev, torch.float32), yo.to(dev), bgp.ScaleKernel(bgp.RBFKernel(2.5), 1.0), noise=1e-10)
 kern = spec_from_model(model, _lib.PRED_COV)
 g = torch.Generator(device=dev).manual_seed(1)
 X = math.sqrt(2.0) * torch.randn(N, d, generator=g, device=dev)
@@ -18,16 +18,20 @@ Z = X[:M].clone()
 Om = torch.randn(M, q, generator=g, device=dev, dtype=torch.float64)
 Xh = torch.empty(N, d).pin_memory(); Xh.copy_(X)
 Zh = Z.cpu().pin_memory(); Oh = Om.cpu().pin_memory()
-def t(fn, reps=3):
+def t(fn, reps=5):
     fn(); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(reps): fn()
-    torch.cuda.synchronize()
-    return (time.perf_counter() - t0) / reps * 1e3
+    each = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        each.append((time.perf_counter() - t0) * 1e3)
+    if os.environ.get("PROBE_EACH"): print("   per call:", " ".join(f"{x:.1f}" for x in each), file=sys.stderr)
+    return min(each)
 def dev_path():
     _, U = ops.nystrom_basis(kern, Z, q, omega=Om, want_S=False)
     return ops.recombine(kern, X, Z, U)
-print(f"N={N}: device path {t(dev_path):.2f} ms | host call {t(lambda: ops.recombine_host(kern, Xh, Zh, q, omega_host=Oh, device=dev)):.2f} ms | "
+print(f"N={N}: device path {t(dev_path):.2f} ms | host call {t(lambda: ops.recombine_host(kern, Xh, Zh, q, device=dev, seed=3)):.2f} ms | "
       f"bare H2D X {t(lambda: Xh.to(dev, non_blocking=True)):.2f} ms, Omega {t(lambda: Oh.to(dev, non_blocking=True)):.2f} ms")
 s2 = torch.cuda.Stream()
 def overlapped():

@@ -33,7 +33,7 @@ if "nys" in sys.argv:
     import bench
     d, M, q, n_obs = 10, 10000, 999, 1002
     Xo, yo = bench.make_observations(d, n_obs)
-    model = bgp.FixedGP(Xo.to(dev, torch.float32), yo.to(dev), bgp.ScaleKernel(bgp.RBFKernel(bench.LENGTHSCALE), 1.0), noise=bench.NOISE)
+    model = bgp.FixedGP(Xo.to(dev, torch.float32), yo.to(dev), bgp.ScaleKernel(bgp.RBFKernel(2.5), 1.0), noise=1e-10)
     kern = spec_from_model(model, _lib.PRED_COV)
     X = math.sqrt(2.0) * torch.randn(M, d, generator=g, device=dev)
     Om = torch.randn(M, q, generator=g, device=dev, dtype=torch.float64)

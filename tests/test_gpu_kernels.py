@@ -42,6 +42,20 @@ def test_dgemm(bq, ta, tb, m, n, k):
     assert rel(C, ref) < 1e-13
 
 
+@pytest.mark.parametrize("n,k,ta", [(1, 5, True), (64, 40, True), (65, 3000, True), (130, 517, False),
+                                    (999, 10000, True), (400, 9000, False)])
+def test_dgemm_gram_is_symmetric(bq, n, k, ta):
+    """A^T A / A A^T (the CholeskyQR Gram matrix): only the tiles touching the lower triangle are computed,
+    with the K range split, and the rest is mirrored - exactly symmetric, same values as the full product."""
+    _, _, ops = bq
+    g = torch.Generator().manual_seed(n + k)
+    A = torch.randn((k, n) if ta else (n, k), generator=g, dtype=torch.float64).to(DEV)
+    C = ops.dgemm(A, A, ta, not ta)
+    ref = A.T @ A if ta else A @ A.T
+    assert C.shape == (n, n) and torch.equal(C, C.T)
+    assert rel(C, ref) < 1e-13
+
+
 @pytest.mark.parametrize("m,n,k", [(1, 1, 1), (65, 33, 17), (128, 256, 32), (129, 257, 33), (300, 700, 1001),
                                    (999, 640, 2048)])
 def test_tgemm_3xtf32(bq, m, n, k):

@@ -302,7 +302,7 @@ def test_host_buffer_entry(bq):
 def test_host_buffer_entry_draws_its_own_test_matrix(bq):
     """The reference's call shape: recombination(pts_rec, pts_nys, ...) hands over points only and
     torch.svd_lowrank draws the Gaussian test matrix itself (BASQ/_rchq.py:28-31).  With neither U_host
-    nor omega_host the library draws it on the device: key = seed + number of earlier draws."""
+    nor omega_host the library draws it on the device, keyed by `seed` or by torch's global generator."""
     basq_b200, _lib, ops, _ = bq
     g = torch.Generator().manual_seed(13)
     N, d, M, n = 20011, 6, 120, 30
@@ -310,22 +310,24 @@ def test_host_buffer_entry_draws_its_own_test_matrix(bq):
     Z = X[:M].clone()
     cov = _plain_model(0, 2.0)
     mu = torch.full((N,), 1.0 / N, dtype=torch.float64)
-    ops.manual_seed(99, DEV)
-    idx, w = ops.recombine_host(cov.forward, X, Z, n - 1)
+    idx, w = ops.recombine_host(cov.forward, X, Z, n - 1, seed=99)
     _check_rule(idx, w, N, n)
-    # the same draw, explicitly: first draw after manual_seed(99) has key 99
+    # the same draw, explicitly
     omega = ops.standard_normals(M, n - 1, seed=99, device=DEV)
     _, U = ops.nystrom_basis(cov.forward, Z.to(DEV), n - 1, omega=omega)
     Phi = ops.features(cov.forward, X.to(DEV), Z.to(DEV), U).cpu()
     assert orchq.moment_residual(Phi, mu, idx, w) < 1e-8
-    # reseeding reproduces the basis (the rule preserves the same moments); the next draw (key 100) is another one
-    ops.manual_seed(99, DEV)
-    idx2, w2 = ops.recombine_host(cov.forward, X, Z, n - 1)
-    assert orchq.moment_residual(Phi, mu, idx2, w2) < 1e-8
-    _, U1 = ops.nystrom_basis(cov.forward, Z.to(DEV), n - 1)          # key 100
-    _, U100 = ops.nystrom_basis(cov.forward, Z.to(DEV), n - 1,
-                                omega=ops.standard_normals(M, n - 1, seed=100, device=DEV))
-    assert torch.allclose(U1, U100, rtol=0, atol=1e-12) and not torch.allclose(U1, U, rtol=0, atol=1e-6)
+    # without a seed the key comes from torch's global generator: torch.manual_seed reproduces the basis (the
+    # rule then preserves the same moments), consecutive calls draw different matrices
+    torch.manual_seed(4)
+    ia, wa = ops.recombine_host(cov.forward, X, Z, n - 1)
+    _, U1 = ops.nystrom_basis(cov.forward, Z.to(DEV), n - 1)
+    torch.manual_seed(4)
+    _, U0 = ops.nystrom_basis(cov.forward, Z.to(DEV), n - 1)
+    _, U1b = ops.nystrom_basis(cov.forward, Z.to(DEV), n - 1)
+    Phi0 = ops.features(cov.forward, X.to(DEV), Z.to(DEV), U0).cpu()
+    assert orchq.moment_residual(Phi0, mu, ia, wa) < 1e-8
+    assert torch.allclose(U1, U1b, rtol=0, atol=1e-12) and not torch.allclose(U1, U0, rtol=0, atol=1e-6)
 
 
 def test_size_independent_properties_large(bq):
