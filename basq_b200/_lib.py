@@ -81,6 +81,7 @@ def _load():
         "basq_sample_mvn": (I, [P, C.c_uint64, L, L, I, I, P, P, P]),
         "basq_standard_normals": (I, [P, C.c_uint64, L, L, I, P]),
         "basq_ctx_set_seed": (I, [P, C.c_uint64]),
+        "basq_ctx_allow_f32_eval": (I, [P, I, C.POINTER(L)]),
         "basq_mvn_logpdf": (I, [P, P, L, I, I, P, P, P]),
         "basq_candidate_weights": (I, [P, I, D, I, P, P, L, I, P]),
         "basq_cleanse_weights": (I, [P, P, L, D]),
@@ -129,6 +130,13 @@ class Context:
     def trim(self, keep_bytes: int = 0):
         """Hand the context's cached scratch memory back to the driver (down to keep_bytes)."""
         check(lib.basq_ctx_trim(self.handle, int(keep_bytes)))
+
+    def allow_f32_eval(self, on=None) -> int:
+        """fp64 inputs may be evaluated on the fp32 tensor-core path (basq_ctx_allow_f32_eval); returns the
+        number of sessions demoted so far.  on=None only reads the counter."""
+        n = C.c_int64(0)
+        check(lib.basq_ctx_allow_f32_eval(self.handle, -1 if on is None else int(bool(on)), C.byref(n)))
+        return int(n.value)
 
     def set_seed(self, seed: int):
         """Key of the library's own Gaussian draws (basq_ctx_set_seed)."""

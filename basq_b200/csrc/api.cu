@@ -96,6 +96,11 @@ __global__ void f32_to_f64_kernel(const float* __restrict__ in, int64_t n, doubl
   if (t < n) out[t] = (double)in[t];
 }
 
+__global__ void f64_to_f32_kernel(const double* __restrict__ in, int64_t n, float* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = (float)in[t];
+}
+
 // kappa = max over rows m of sum_o |A[m, o]|  (non-negative doubles order like their bit patterns)
 __global__ void row_l1_max_kernel(const double* __restrict__ A, int rows, int cols, unsigned long long* __restrict__ out) {
   __shared__ double sh[256];
@@ -169,6 +174,11 @@ struct basq_session {
   bool scale_wf = true;
   std::vector<double> omega_host;
   std::vector<int> rank_host;
+  // fp64 inputs evaluated in fp32 at the caller's request (basq_ctx_allow_f32_eval): narrowed copies, and the
+  // original fp64 arrays in case the conditioning guard sends the session back to the fp64 path
+  DevBuf X32, Z32, Xobs32;
+  bool demoted = false;
+  const void *origX = nullptr, *origZ = nullptr, *origXobs = nullptr;
 };
 
 namespace basq {
@@ -226,6 +236,35 @@ int session_create_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
   BASQ_CHECK(q >= 1 && M >= q, BASQ_ERR_INVALID, "session: need 1 <= q <= M (q=%d, M=%lld)", q, (long long)M);
   BASQ_CHECK(M <= 1000000, BASQ_ERR_UNSUPPORTED, "session: more than 1e6 landmarks");
   s->ctx = ctx;
+  if (desc->dtype == BASQ_F64 && ctx->eval_f32 && !s->promoted && !s->demoted) {
+    // opt-in: evaluate the kernel in fp32 (tensor-core set sums) although the caller's arrays are fp64 - SOBER
+    // runs everything in torch.double (SOBER/_settings.py:4-11); accumulation, projection and Caratheodory stay
+    // fp64 as on the fp32 path, and the conditioning guard below may still send the session back to fp64
+    const int d = desc->d;
+    auto narrow = [&](const void* src, int64_t rows, DevBuf* dst) -> int {
+      BASQ_TRY(dst->alloc(ctx, sizeof(float) * (size_t)std::max<int64_t>(rows, 1) * d));
+      if (rows > 0) {
+        f64_to_f32_kernel<<<(unsigned)ceil_div64(rows * d, 256), 256, 0, ctx->stream>>>((const double*)src, rows * d,
+                                                                                         dst->as<float>());
+        ctx->launches++;
+        BASQ_CUDA(cudaGetLastError());
+      }
+      return BASQ_OK;
+    };
+    BASQ_TRY(narrow(X, N_loc, &s->X32));
+    BASQ_TRY(narrow(Z, M, &s->Z32));
+    basq_kernel_desc d32 = *desc;
+    d32.dtype = BASQ_F32;
+    if (desc->mode != BASQ_PLAIN) {
+      BASQ_TRY(narrow(desc->Xobs, desc->n_obs, &s->Xobs32));
+      d32.Xobs = s->Xobs32.p;
+      d32.Xobs_f64 = static_cast<const double*>(desc->Xobs);
+    }
+    s->demoted = true;
+    s->origX = X; s->origZ = Z; s->origXobs = desc->Xobs;
+    ctx->demotions++;
+    return session_create_impl(ctx, &d32, s->X32.p, N_loc, N_glob, idx_base, s->Z32.p, M, U, q, mu, S_override, s);
+  }
   s->desc = *desc;
   BASQ_TRY(make_kparams(desc, &s->kp));
   BASQ_TRY(compute_center(ctx, desc, Z, M, &s->kp));
@@ -282,6 +321,19 @@ int session_create_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
         }
         return BASQ_OK;
       };
+      if (s->demoted) {   // the caller's arrays were fp64 to begin with: go back to them
+        s->lm.zz.release(); s->lm.b.release(); s->lm.lmA.release();
+        s->lmobs.zz.release(); s->lmobs.b.release(); s->lmobs.lmA.release();
+        s->Az.release();
+        s->X32.release(); s->Z32.release(); s->Xobs32.release();
+        basq_kernel_desc d64 = *desc;
+        d64.dtype = BASQ_F64;
+        d64.Xobs = s->origXobs;
+        d64.Xobs_f64 = nullptr;
+        s->promoted = true;
+        ctx->promotions++;
+        return session_create_impl(ctx, &d64, s->origX, N_loc, N_glob, idx_base, s->origZ, M, U, q, mu, S_override, s);
+      }
       BASQ_TRY(widen(X, N_loc, &s->X64));
       BASQ_TRY(widen(Z, M, &s->Z64));
       if (desc->Xobs_f64) {
@@ -886,6 +938,7 @@ int basq_ctx_create(int device, void* stream, basq_ctx** out) {
   { const char* t = getenv("BASQ_NYSTROM_FP64"); c->no_tensor_nystrom = t && t[0] == '1'; }
   { const char* t = getenv("BASQ_SETSUM_SCALAR"); c->scalar_setsum = t && t[0] == '1'; }
   { const char* t = getenv("BASQ_F32_KAPPA_MAX"); if (t) c->kappa_max = atof(t); }
+  { const char* t = getenv("BASQ_F64_EVAL_F32"); c->eval_f32 = t && t[0] == '1'; }
   *out = c;
   return BASQ_OK;
 }
@@ -934,6 +987,13 @@ int basq_ctx_trim(basq_ctx* ctx, int64_t keep_bytes) {
 }
 
 int64_t basq_ctx_launch_count(const basq_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int basq_ctx_allow_f32_eval(basq_ctx* ctx, int on, int64_t* demotions_host) {
+  BASQ_CHECK(ctx, BASQ_ERR_INVALID, "basq_ctx_allow_f32_eval: NULL context");
+  if (on >= 0) ctx->eval_f32 = on != 0;
+  if (demotions_host) *demotions_host = ctx->demotions;
+  return BASQ_OK;
+}
 
 int basq_ctx_set_seed(basq_ctx* ctx, uint64_t seed) {
   BASQ_CHECK(ctx, BASQ_ERR_INVALID, "basq_ctx_set_seed: NULL context");

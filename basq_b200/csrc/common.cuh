@@ -80,6 +80,8 @@ struct basq_ctx {
   void* host_x = nullptr;
   size_t host_x_bytes = 0;
   cudaEvent_t side_ev[2] = {nullptr, nullptr};
+  bool eval_f32 = false;           // basq_ctx_allow_f32_eval: fp64 inputs may be evaluated on the fp32 tensor-core path
+  int64_t demotions = 0;
   uint64_t seed = 0;               // basq_ctx_set_seed: key of the library's own Gaussian draws (Nystrom test matrix)
   uint64_t draws = 0;              // test matrices drawn since the seed was set (each call uses key seed + draws)
   bool no_nlsum = false;           // BASQ_NLSUM=0: chunked fp64-GEMM path for the non-linear modes in fp32 too (A/B)

@@ -1,16 +1,19 @@
-// Tensor-core GEMM with fp32 accuracy (3xTF32) on blocked + split operands - see tgemm.cu.
+// Tensor-core GEMM with fp32 accuracy (fp16 hi / lo split, three products) on blocked operands - see tgemm.cu.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace basq {
 
-// Matrix X [rows, kdim] stored as two fp32 arrays (x = hi + lo, both tf32-representable) in the
-// layout [row tile of 128][K chunk of 4 (kdim padded to 32)][128 rows][4]; padding is zero.
+// Matrix X [rows, kdim] stored as two fp16 arrays of the row-scaled matrix (x * rscale = hi + lo; rscale a power
+// of two that brings the row's largest magnitude into [2^13, 2^14)) in the layout
+// [row tile of 128][K chunk of 8 (kdim padded to 64)][128 rows][8]; padding is zero.  rinv[row] = 1 / rscale.
 struct BlkOperand {
-  DevBuf hi, lo;
+  DevBuf hi, lo, rinv;
   int rows = 0, kdim = 0;
   int RT = 0;  // row tiles
-  int KC = 0;  // K chunks of 4 elements (multiple of 8)
+  int KC = 0;  // K chunks of 8 elements (multiple of 8: one 16 KB piece per row tile and 64-wide K block)
   int alloc(basq_ctx* ctx, int rows, int kdim);
 };
 

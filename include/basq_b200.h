@@ -100,6 +100,14 @@ int basq_ctx_trim(basq_ctx* ctx, int64_t keep_bytes);
    (BASQ/_parameters.py:30) makes such GPs easy to produce in low dimension.  kappa_max < 0 leaves the
    threshold unchanged; the outputs (may be NULL) report the last kappa and the number of promotions. */
 int basq_ctx_conditioning(basq_ctx* ctx, double kappa_max, double* last_kappa_host, int64_t* promotions_host);
+/* Opt-in for callers that hold fp64 arrays but accept fp32 kernel evaluation (SOBER runs in torch.double,
+   SOBER/_settings.py:4-11): with on != 0, sessions created from fp64 inputs (basq_recombine*, basq_session_create)
+   evaluate the kernel on the fp32 tensor-core path - narrowed copies of X, Z, Xobs; set sums, projection and
+   Caratheodory stay fp64 exactly as for fp32 inputs - unless the conditioning guard above sends them back to
+   fp64.  Kernel values then carry ~2e-7 relative error instead of 1e-16.  Default off (environment
+   BASQ_F64_EVAL_F32=1).  on < 0 leaves the setting unchanged; demotions_host (may be NULL) receives the
+   number of sessions demoted so far. */
+int basq_ctx_allow_f32_eval(basq_ctx* ctx, int on, int64_t* demotions_host);
 /* Key of the library's own Gaussian draws (the Nystrom test matrix when the caller passes none); the
    k-th draw after this call uses the Philox key seed + k.  Default 0. */
 int basq_ctx_set_seed(basq_ctx* ctx, uint64_t seed);

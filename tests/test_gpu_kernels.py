@@ -58,15 +58,16 @@ def test_dgemm_gram_is_symmetric(bq, n, k, ta):
 
 @pytest.mark.parametrize("m,n,k", [(1, 1, 1), (65, 33, 17), (128, 256, 32), (129, 257, 33), (300, 700, 1001),
                                    (999, 640, 2048)])
-def test_tgemm_3xtf32(bq, m, n, k):
-    """Tensor-core GEMM (tcgen05, 3xTF32 split): fp32-level accuracy against an fp64 product."""
+def test_tgemm_split_fp16(bq, m, n, k):
+    """Tensor-core GEMM (tcgen05, row-scaled fp16 hi / lo split, three products): fp32-level accuracy against
+    an fp64 product."""
     _, _, ops = bq
     g = torch.Generator().manual_seed(m * 11 + n)
     A = torch.randn(m, k, generator=g, dtype=torch.float64).to(DEV)
     B = torch.randn(n, k, generator=g, dtype=torch.float64).to(DEV)
     C = ops.tgemm(A, B)
     ref = A @ B.T
-    # error relative to the magnitude of the sum's terms: 3xTF32 drops the lo*lo product (2^-22) and
+    # error relative to the magnitude of the sum's terms: the split drops the lo*lo product (2^-22) and
     # the accumulator in TMEM is fp32 (growth with k like an fp32 GEMM)
     scale = float((A.abs() @ B.abs().T).max())
     assert float((C - ref).abs().max()) / scale < 2e-6 * max(1.0, k / 512)
@@ -74,6 +75,25 @@ def test_tgemm_3xtf32(bq, m, n, k):
     Ai = torch.randint(-8, 9, (m, k), generator=g).double().to(DEV)
     Bi = torch.randint(-8, 9, (n, k), generator=g).double().to(DEV)
     assert torch.equal(ops.tgemm(Ai, Bi), Ai @ Bi.T)
+
+
+@pytest.mark.parametrize("m,n,k", [(999, 10000, 2000), (640, 2100, 700), (1000, 4000, 64)])
+def test_tgemm_ksplit_and_row_ranges(bq, m, n, k):
+    """More tiles than SMs and not a multiple of them: every tile is computed as two K parts that are added onto
+    the zero-filled output (two addends: order-independent).  Rows and columns with very different magnitudes
+    exercise the per-row power-of-two scales."""
+    _, _, ops = bq
+    g = torch.Generator().manual_seed(m + n + k)
+    A = torch.randn(m, k, generator=g, dtype=torch.float64) * torch.logspace(-6, 6, m, dtype=torch.float64).unsqueeze(1)
+    B = torch.randn(n, k, generator=g, dtype=torch.float64) * torch.logspace(3, -9, n, dtype=torch.float64).unsqueeze(1)
+    A[5] = 0.0                                   # an all-zero row keeps scale 1
+    A, B = A.to(DEV), B.to(DEV)
+    C = ops.tgemm(A, B)
+    ref = A @ B.T
+    scale = A.abs() @ B.abs().T
+    err = ((C - ref).abs() / scale.clamp_min(1e-300)).max()
+    assert float(err) < 2e-6 * max(1.0, k / 512)
+    assert torch.equal(C, ops.tgemm(A, B))       # run-to-run identical
 
 
 # ------------------------------------------------------------------------------------------- base kernels

@@ -226,3 +226,52 @@ def test_warped_gram_diagonal_noise_before_jitter_after(lib, name):
     X = torch.randn(30, 4, generator=g, dtype=torch.float64)
     K = ops.gram(kern, X.to(DEV), X[:20].to(DEV))
     assert rel(K, kern(X, X[:20])) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------- fp64 arrays, fp32 evaluation
+@pytest.mark.parametrize("mode", ["pred_cov", "wsabim"])
+def test_opt_in_f32_evaluation_of_f64_inputs(lib, mode):
+    """basq_ctx_allow_f32_eval: a caller holding torch.double arrays (SOBER's dtype, SOBER/_settings.py:4-11) may ask
+    for the fp32 tensor-core path.  Default off: fp64 inputs are evaluated in fp64 (residual ~1e-12 against the
+    oracle's fp64 features); on: the rule preserves the moments of the fp32-evaluated kernel to 1e-8 and those of
+    the fp64 oracle kernel to fp32 evaluation accuracy; a stiff GP goes back to fp64 through the conditioning guard."""
+    basq_b200, _lib, gp, ops, sampler, KernelSpec, spec_from_model = lib
+    g = torch.Generator().manual_seed(77)
+    d, N, M, n = 4, 60_000, 300, 40
+    X = math.sqrt(2.0) * torch.randn(N, d, generator=g, dtype=torch.float64)
+    Z = X[:M].clone()
+    model = ogp.make_gp(d, 30, lengthscale=1.6, outputscale=1.1, noise=1e-2, seed=3, mean_const=0.1)
+    obj = ogp.VanillaGP(model) if mode == "pred_cov" else ogp.WsabiGP(model, alpha=0.05)
+    kern = obj.predictive_kernel if mode == "pred_cov" else obj.wsabim_kernel
+    _, U = orchq.nystrom_basis(Z, n - 1, kern)
+    Phi = orchq.features(X, U, Z, kern)
+    mu = torch.full((N,), 1.0 / N, dtype=torch.float64)
+    ctx = _lib.context_for(DEV)
+    base = ctx.allow_f32_eval()
+    idx, w = ops.recombine(kern, X.to(DEV), Z.to(DEV), U.to(DEV))
+    assert ctx.allow_f32_eval() == base                       # default: untouched
+    assert orchq.moment_residual(Phi, mu, idx.cpu(), w.cpu()) < 1e-10
+    try:
+        ctx.allow_f32_eval(True)
+        idx32, w32 = ops.recombine(kern, X.to(DEV), Z.to(DEV), U.to(DEV))
+        assert ctx.allow_f32_eval() == base + 1
+        assert len(idx32) <= n and abs(float(w32.sum()) - 1.0) < 1e-12 and bool((w32 > 0).all())
+        res64 = orchq.moment_residual(Phi, mu, idx32.cpu(), w32.cpu())
+        assert 1e-10 < res64 < 2e-5, res64                    # fp32 kernel values against fp64 features
+        Phi32 = ops.features(kern, X.float().to(DEV), Z.float().to(DEV), U.to(DEV)).cpu()
+        assert orchq.moment_residual(Phi32, mu, idx32.cpu(), w32.cpu()) < 1e-8
+        # a stiff GP: the guard promotes the demoted session back to the caller's fp64 arrays
+        stiff = ogp.make_gp(2, 60, lengthscale=1.0, outputscale=1.0, noise=1e-10, seed=5)
+        k2 = ogp.VanillaGP(stiff).predictive_kernel
+        X2 = math.sqrt(2.0) * torch.randn(20_000, 2, generator=g, dtype=torch.float64)
+        Z2 = X2[:200].clone()
+        _, U2 = orchq.nystrom_basis(Z2, 19, k2)
+        _, promoted0 = ctx.conditioning()
+        i2, w2 = ops.recombine(k2, X2.to(DEV), Z2.to(DEV), U2.to(DEV))
+        kappa, promoted1 = ctx.conditioning()
+        assert kappa > 64 and promoted1 == promoted0 + 1
+        Phi2 = orchq.features(X2, U2, Z2, k2)
+        mu2 = torch.full((len(X2),), 1.0 / len(X2), dtype=torch.float64)
+        assert orchq.moment_residual(Phi2, mu2, i2.cpu(), w2.cpu()) < 1e-9
+    finally:
+        ctx.allow_f32_eval(False)
