@@ -910,29 +910,10 @@ int basq_ctx_create(int device, void* stream, basq_ctx** out) {
     set_error("basq_b200 is built for sm_100a (Blackwell B200); device %d is sm_%d%d", device, prop.major, prop.minor);
     return BASQ_ERR_CUDA;
   }
-  {
-    // Private stream-ordered pool (the device's default pool is left untouched: it is shared with
-    // whatever else lives in the process).  Freed scratch stays cached in it across the pass loop and
-    // across calls; basq_ctx_trim hands it back on request.  Automatic trimming at the end of every
-    // top-level call is opt-in (BASQ_POOL_KEEP_MB): with a 24 GiB keep size the 2-GPU bench showed
-    // sporadic 150-800 ms stalls per step, because legs with different buffer sizes fragment the pool past
-    // the threshold and every trim is followed by a re-growth at driver speed.
-    cudaMemPoolProps props;
-    memset(&props, 0, sizeof(props));
-    props.allocType = cudaMemAllocationTypePinned;
-    props.handleTypes = cudaMemHandleTypeNone;
-    props.location.type = cudaMemLocationTypeDevice;
-    props.location.id = device;
-    if (cudaMemPoolCreate(&c->pool, &props) != cudaSuccess) {
-      delete c;
-      set_error("cudaMemPoolCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
-      return BASQ_ERR_CUDA;
-    }
-    uint64_t hold = UINT64_MAX;  // inside a call nothing goes back to the driver
-    cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &hold);
-    c->pool_keep = UINT64_MAX;   // no automatic trim
-    if (const char* t = getenv("BASQ_POOL_KEEP_MB")) c->pool_keep = (uint64_t)strtoull(t, nullptr, 10) << 20;
-  }
+  // Scratch memory comes from the context's own block cache (common.cuh).  Automatic trimming at the end of every
+  // top-level call is opt-in (BASQ_POOL_KEEP_MB): a trim is followed by re-allocation at driver speed.
+  c->pool_keep = UINT64_MAX;
+  if (const char* t = getenv("BASQ_POOL_KEEP_MB")) c->pool_keep = (uint64_t)strtoull(t, nullptr, 10) << 20;
   { const char* t = getenv("BASQ_TRACE"); c->trace = t && t[0] == '1'; }
   { const char* t = getenv("BASQ_CAR_GENERAL"); c->force_general_car = t && t[0] == '1'; }
   { const char* t = getenv("BASQ_NYSTROM_FP64"); c->no_tensor_nystrom = t && t[0] == '1'; }
@@ -958,10 +939,7 @@ void basq_ctx_destroy(basq_ctx* ctx) {
   if (ctx->host_x) cudaFree(ctx->host_x);
   for (cudaEvent_t e : ctx->stage_ev)
     if (e) cudaEventDestroy(e);
-  if (ctx->pool) {
-    cudaStreamSynchronize(ctx->stream);
-    cudaMemPoolDestroy(ctx->pool);
-  }
+  ctx->block_trim(0);
   (void)cudaGetLastError();
   delete ctx;
 }
@@ -974,15 +952,9 @@ int basq_ctx_trim(basq_ctx* ctx, int64_t keep_bytes) {
     ctx->host_x = nullptr;
     ctx->host_x_bytes = 0;
   }
-  if (!ctx->pool) return BASQ_OK;
   const uint64_t keep = keep_bytes < 0 ? ctx->pool_keep : (uint64_t)keep_bytes;
   if (keep == UINT64_MAX) return BASQ_OK;
-  uint64_t reserved = 0;
-  cudaMemPoolGetAttribute(ctx->pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
-  if (reserved > keep) {
-    BASQ_CUDA(cudaStreamSynchronize(ctx->stream));  // pending stream-ordered frees become releasable
-    BASQ_CUDA(cudaMemPoolTrimTo(ctx->pool, (size_t)keep));
-  }
+  ctx->block_trim((size_t)keep);
   return BASQ_OK;
 }
 

@@ -51,11 +51,77 @@ enum Phase { PH_PREP = 0, PH_SETSUM = 1, PH_PROJ = 2, PH_CAR = 3, PH_APPLY = 4, 
 struct basq_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  // Private stream-ordered pool: scratch freed by the library stays cached here (no driver calls in the
-  // pass loop) without touching the device's default pool, which other code in the process may share.
-  // basq_ctx_trim / the end of every top-level call release everything above pool_keep bytes.
-  cudaMemPool_t pool = nullptr;
+  // Private block cache for the library's scratch (DevBuf below): a freed block goes onto a free list and is
+  // handed out again to the next request of the same size class, whole - blocks are never split or merged.
+  // Everything the library launches runs on `stream`, so a block may be reused without a fence.  In steady
+  // state no allocation reaches the driver.  (Round 2 first used a cudaMemPool_t here: its best-fit carving
+  // of free blocks made the layout depend on the order of requests, and a call sequence that differed from
+  // the warmed-up one - the host-buffer entry after device-resident calls, the next leg of the bench - ran
+  // into re-mapping stalls of 0.15-1.65 s per call.)  basq_ctx_trim / the end of every top-level call
+  // release everything above pool_keep bytes (default: keep all).
+  struct Block { void* p; size_t bytes; };
+  std::vector<Block> free_blocks;
+  size_t cached_bytes = 0;          // on the free list
+  size_t live_bytes = 0;            // handed out
+  int64_t driver_allocs = 0;
   uint64_t pool_keep = 0;
+  static size_t size_class(size_t n) {
+    if (n < 4096) n = 4096;
+    size_t p2 = 4096;
+    while (p2 * 2 <= n) p2 *= 2;
+    const size_t gran = p2 / 8 < 4096 ? 4096 : p2 / 8;       // at most 12.5 % above the request
+    return (n + gran - 1) / gran * gran;
+  }
+  // returns nullptr when the device is out of memory even after the cache was emptied
+  void* block_alloc(size_t n, size_t* got) {
+    const size_t cls = size_class(n);
+    int best = -1;
+    for (int i = 0; i < (int)free_blocks.size(); ++i)
+      if (free_blocks[i].bytes >= cls && free_blocks[i].bytes <= cls + cls / 4 &&
+          (best < 0 || free_blocks[i].bytes < free_blocks[best].bytes))
+        best = i;
+    void* p = nullptr;
+    if (best >= 0) {
+      p = free_blocks[best].p;
+      *got = free_blocks[best].bytes;
+      cached_bytes -= *got;
+      free_blocks[best] = free_blocks.back();
+      free_blocks.pop_back();
+    } else {
+      if (cudaMalloc(&p, cls) != cudaSuccess) {
+        (void)cudaGetLastError();
+        block_trim(0);
+        if (cudaMalloc(&p, cls) != cudaSuccess) {
+          (void)cudaGetLastError();
+          return nullptr;
+        }
+      }
+      ++driver_allocs;
+      *got = cls;
+    }
+    live_bytes += *got;
+    return p;
+  }
+  void block_free(void* p, size_t bytes) {
+    free_blocks.push_back({p, bytes});
+    cached_bytes += bytes;
+    live_bytes -= bytes;
+  }
+  // hand cached blocks back to the driver, largest first, until at most `keep` bytes stay cached
+  void block_trim(size_t keep) {
+    if (cached_bytes <= keep) return;
+    cudaStreamSynchronize(stream);   // queued work may still use a block that is already on the free list
+    while (cached_bytes > keep && !free_blocks.empty()) {
+      int big = 0;
+      for (int i = 1; i < (int)free_blocks.size(); ++i)
+        if (free_blocks[i].bytes > free_blocks[big].bytes) big = i;
+      cudaFree(free_blocks[big].p);
+      cached_bytes -= free_blocks[big].bytes;
+      free_blocks[big] = free_blocks.back();
+      free_blocks.pop_back();
+    }
+    (void)cudaGetLastError();
+  }
   int num_sms = 0;
   size_t smem_optin = 0;
   int64_t launches = 0;
@@ -159,36 +225,33 @@ struct PhaseTimer {
   }
 };
 
-// Device buffer with RAII, carved from the context's private stream-ordered memory pool on the
-// context's stream (cudaMallocFromPoolAsync / cudaFreeAsync; the pool keeps freed blocks, so in
-// steady state neither call reaches the driver or synchronises the device - the round loop
-// allocates and frees scratch every round).  Everything the library launches runs on
-// that one stream, so a freed block may be handed to the next allocation without a fence.
+// Device buffer with RAII from the context's block cache (basq_ctx::block_alloc): in steady state neither
+// alloc nor release reaches the driver or synchronises the device - the round loop allocates and frees scratch
+// every round.  Everything the library launches runs on the context's one stream, so a released block may be
+// handed to the next allocation without a fence.
 struct DevBuf {
   void* p = nullptr;
-  size_t bytes = 0;
-  cudaStream_t stream = nullptr;
+  size_t bytes = 0;      // size of the cache block behind p (>= the request)
+  basq_ctx* owner = nullptr;
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFreeAsync(p, stream);
+    if (p && owner) owner->block_free(p, bytes);
     p = nullptr;
     bytes = 0;
   }
   int alloc(basq_ctx* ctx, size_t n) {
     release();
     if (n == 0) n = 16;
-    stream = ctx->stream;
-    cudaError_t e = ctx->pool ? cudaMallocFromPoolAsync(&p, n, ctx->pool, stream) : cudaMallocAsync(&p, n, stream);
-    if (e != cudaSuccess) {
-      set_error("stream-ordered allocation of %zu bytes failed: %s", n, cudaGetErrorString(e));
-      p = nullptr;
-      (void)cudaGetLastError();
+    owner = ctx;
+    p = ctx->block_alloc(n, &bytes);
+    if (!p) {
+      set_error("device allocation of %zu bytes failed (%zu bytes live in this context)", n, ctx->live_bytes);
+      bytes = 0;
       return BASQ_ERR_CUDA;
     }
-    bytes = n;
     return BASQ_OK;
   }
   template <typename T>

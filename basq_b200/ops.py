@@ -117,7 +117,7 @@ def dgemm(A, B, transA=False, transB=False):
 
 
 def tgemm(A, B):
-    """A @ B.T on the tensor cores with fp32 accuracy (3xTF32); fp64 tensors in and out."""
+    """A @ B.T on the tensor cores with fp32 accuracy (fp16 hi/lo split, three products); fp64 tensors in and out."""
     ctx = _lib.context_for(A.device)
     A = A.to(torch.float64).contiguous(); B = B.to(torch.float64).contiguous()
     m, k = A.shape

@@ -612,7 +612,7 @@ def run_ours(a, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": "points/s",
             "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
-            "dtype": "f32 kernel evaluation (3xTF32 distance contraction), f64 accumulation/projection/Caratheodory",
+            "dtype": "f32 kernel evaluation (fp16 hi/lo split distance contraction, 3 products), f64 accumulation/projection/Caratheodory",
             "data": "synthetic", "config": config_of(a, world),
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
             "iteration": {"ms": ms_iter, "unit": "ms per BASQ iteration",
@@ -621,7 +621,7 @@ def run_ours(a, rank, world, local_rank):
             "phases_ms": {k: round(v[0] / a.steps, 3) for k, v in prof.items()}, "rounds": n_rounds,
             "roofline": {
                 "bound": "mufu",
-                "kernel": "setsum_mma_kernel<RBF, 10> (tcgen05 kind::tf32 distance contraction, ex2 + fp64 set-sum epilogue)",
+                "kernel": "setsum_mma_kernel<RBF, 10> (tcgen05 kind::f16 distance contraction on fp16 hi/lo split operands, ex2 + fp64 set-sum epilogue)",
                 "achieved": pair_rate / 1e9 if pair_rate else None, "peak": mufu_peak / 1e9,
                 "unit": "G kernel evaluations/s", "frac": (pair_rate / mufu_peak) if pair_rate else None,
                 "traffic": traffic,
@@ -632,8 +632,8 @@ def run_ours(a, rank, world, local_rank):
                 "pairs_per_step": pairs_step, "set_sum_ms_per_step": ss_ms, "set_sum_launches_per_step": n_rounds,
                 "tensor_pipe": {"algorithmic_flop_per_pair": flop_per_pair,
                                 "achieved_tflops": (pair_rate * flop_per_pair / 1e12) if pair_rate else None,
-                                "note": "the distance contraction issues 80 tf32 MMA flop per pair (K = 3d+6 -> 40, "
-                                        "3xTF32); far from the tensor peak by design"},
+                                "note": "the distance contraction issues 96 fp16 MMA flop per pair (K = 48: lo hi, hi lo, hi hi "
+                                        "of the split operands); far from the tensor peak by design"},
                 "hbm": {"algorithmic_bytes_per_step": None if not pairs_step else int(2 * 64 * N_loc * 1.04),
                         "note": "records are re-read per 256-landmark group from L2 (DESIGN.md 4)"},
             },

@@ -277,9 +277,10 @@ int basq_sir_resample(basq_ctx* ctx, const double* w, int64_t N, int64_t n_out, 
 int basq_dgemm(basq_ctx* ctx, int transA, int transB, int m, int n, int k, double alpha,
                const double* A, int lda, const double* B, int ldb, double beta, double* C, int ldc);
 
-/* C[m,n] = A[m,k] B[n,k]^T on the tensor cores with fp32 accuracy (3xTF32 split operands, fp32
-   accumulation in TMEM; inputs rounded to fp32 first).  fp64 row-major in and out.  This is the GEMM
-   behind the Nystrom subspace iteration and the posterior-variance contraction for fp32 kernels. */
+/* C[m,n] = A[m,k] B[n,k]^T on the tensor cores with fp32 accuracy (rows scaled by powers of two and split
+   into fp16 hi + lo, three products, fp32 accumulation in TMEM: ~2^-21 relative to sum |a||b|).  fp64
+   row-major in and out.  This is the GEMM behind the Nystrom subspace iteration and the posterior-covariance
+   Gram correction for fp32 kernels. */
 int basq_tgemm(basq_ctx* ctx, int m, int n, int k, const double* A, int lda, const double* B, int ldb,
                double* C, int ldc);
 
