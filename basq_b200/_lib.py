@@ -81,6 +81,7 @@ def _load():
         "basq_sample_mvn": (I, [P, C.c_uint64, L, L, I, I, P, P, P]),
         "basq_standard_normals": (I, [P, C.c_uint64, L, L, I, P]),
         "basq_ctx_set_seed": (I, [P, C.c_uint64]),
+        "basq_ctx_memory": (I, [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(L)]),
         "basq_ctx_allow_f32_eval": (I, [P, I, C.POINTER(L)]),
         "basq_mvn_logpdf": (I, [P, P, L, I, I, P, P, P]),
         "basq_candidate_weights": (I, [P, I, D, I, P, P, L, I, P]),
@@ -126,6 +127,12 @@ class Context:
     @property
     def pair_evals(self) -> int:
         return int(lib.basq_ctx_pair_evals(self.handle))
+
+    def memory(self):
+        """(bytes cached for reuse, bytes handed out to live sessions, driver allocations so far)."""
+        c, l, n = C.c_uint64(0), C.c_uint64(0), C.c_int64(0)
+        check(lib.basq_ctx_memory(self.handle, C.byref(c), C.byref(l), C.byref(n)))
+        return int(c.value), int(l.value), int(n.value)
 
     def trim(self, keep_bytes: int = 0):
         """Hand the context's cached scratch memory back to the driver (down to keep_bytes)."""

@@ -958,6 +958,15 @@ int basq_ctx_trim(basq_ctx* ctx, int64_t keep_bytes) {
   return BASQ_OK;
 }
 
+int basq_ctx_memory(const basq_ctx* ctx, uint64_t* cached_bytes_host, uint64_t* live_bytes_host,
+                    int64_t* driver_allocs_host) {
+  BASQ_CHECK(ctx, BASQ_ERR_INVALID, "ctx is NULL");
+  if (cached_bytes_host) *cached_bytes_host = ctx->cached_bytes + ctx->host_x_bytes;
+  if (live_bytes_host) *live_bytes_host = ctx->live_bytes;
+  if (driver_allocs_host) *driver_allocs_host = ctx->driver_allocs;
+  return BASQ_OK;
+}
+
 int64_t basq_ctx_launch_count(const basq_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int basq_ctx_allow_f32_eval(basq_ctx* ctx, int on, int64_t* demotions_host) {

@@ -341,7 +341,7 @@ def standard_normals(rows, cols, seed=0, offset=0, device="cuda") -> torch.Tenso
 
 
 def release_memory(device=None, keep_bytes: int = 0):
-    """Hand the scratch memory cached by the library's private CUDA pools back to the driver (all
+    """Hand the scratch memory cached by the library (block cache, host-call buffer) back to the driver (all
     contexts of `device`, or of every device)."""
     for (index, _stream), ctx in list(_lib._contexts.items()):
         if device is None or torch.device(device).index in (None, index):

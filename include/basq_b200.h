@@ -82,15 +82,21 @@ const char* basq_last_error(void);
 /* stream: a cudaStream_t (0 = the legacy default stream). */
 int basq_ctx_create(int device, void* stream, basq_ctx** out);
 void basq_ctx_destroy(basq_ctx* ctx);
-/* Scratch memory: every ctx owns a private stream-ordered CUDA memory pool (the device's default pool
-   is never touched), which caches freed blocks so that neither the pass loop nor the next call reaches
-   the driver (a 1e7-candidate call holds 7-10 GB).  basq_ctx_trim(ctx, keep_bytes) hands the cache back
-   to the driver down to keep_bytes (0: everything) - call it when other CUDA code in the process needs
-   the memory, e.g. between the BASQ iteration and the GP refit.  keep_bytes < 0 applies the context's
-   automatic keep size, which every top-level call also applies before it returns; it is unlimited (no
-   automatic trim) unless the environment sets BASQ_POOL_KEEP_MB - trimming after every call was measured
-   to cost sporadic 150-800 ms re-growth stalls per step.  basq_ctx_destroy releases the pool. */
+/* Scratch memory: every ctx owns a private cache of device blocks (plain cudaMalloc blocks, reused whole per
+   size class on the context's stream; no CUDA memory pool is involved), so that neither the pass loop nor
+   the next call reaches the driver (a 1e7-candidate call holds 7-10 GB).  basq_ctx_trim(ctx, keep_bytes)
+   hands the cache back to the driver down to keep_bytes (0: everything, including the candidate buffer of
+   basq_recombine_host) - call it when other CUDA code in the process needs the memory, e.g. between the
+   BASQ iteration and the GP refit.  keep_bytes < 0 applies the context's automatic keep size, which every
+   top-level call also applies before it returns; it is unlimited (no automatic trim) unless the environment
+   sets BASQ_POOL_KEEP_MB - a trim is followed by re-allocation at driver speed.  basq_ctx_destroy releases
+   everything. */
 int basq_ctx_trim(basq_ctx* ctx, int64_t keep_bytes);
+/* Scratch memory of the context: bytes cached for reuse (free list of the block cache plus the candidate
+   buffer of basq_recombine_host), bytes currently handed out (live sessions), and how many times the cache
+   had to go to the driver (cudaMalloc) so far - constant in steady state.  Outputs may be NULL. */
+int basq_ctx_memory(const basq_ctx* ctx, uint64_t* cached_bytes_host, uint64_t* live_bytes_host,
+                    int64_t* driver_allocs_host);
 /* Conditioning guard of the fp32 path.  A posterior-covariance kernel evaluates
    C(z, x) = k(z, x) - (K_ZX W) k(Xobs, x): an evaluation error eps of the kernel values (fp32: ~2e-7
    relative) reaches C as eps * |(K_ZX W)_m|_1 * outputscale.  kappa = max_m |(K_ZX W)_m|_1 is computed

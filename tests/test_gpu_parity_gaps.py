@@ -275,3 +275,38 @@ def test_opt_in_f32_evaluation_of_f64_inputs(lib, mode):
         assert orchq.moment_residual(Phi2, mu2, i2.cpu(), w2.cpu()) < 1e-9
     finally:
         ctx.allow_f32_eval(False)
+
+
+# ------------------------------------------------------------------------------------------- scratch memory
+def test_block_cache_steady_state_and_trim(lib):
+    """The context's block cache: repeated identical calls allocate nothing new from the driver, alternating call
+    shapes settle after one round each, basq_ctx_trim hands the memory back (visible to the rest of the
+    process) and the next call simply re-allocates."""
+    basq_b200, _lib, gp, ops, sampler, KernelSpec, spec_from_model = lib
+    g = torch.Generator().manual_seed(8)
+    spec = KernelSpec(_lib.RBF, _lib.PLAIN, torch.tensor([2.0]), 1.0)
+    Xa = math.sqrt(2.0) * torch.randn(200_000, 6, generator=g)
+    Xb = math.sqrt(2.0) * torch.randn(77_777, 6, generator=g)
+    ctx = _lib.context_for(DEV)
+
+    def call(X, n):
+        Xd = X.to(DEV)
+        _, U = ops.nystrom_basis(spec, Xd[:400], n - 1, want_S=False, seed=1)
+        return ops.recombine(spec, Xd, Xd[:400], U)
+
+    for _ in range(2):
+        call(Xa, 50); call(Xb, 30)
+        ops.recombine_host(spec, Xb.pin_memory(), Xb[:400].clone(), 29, seed=2)
+    n0 = ctx.memory()[2]
+    for _ in range(3):
+        ia, wa = call(Xa, 50); ib, wb = call(Xb, 30)
+        ops.recombine_host(spec, Xb.pin_memory(), Xb[:400].clone(), 29, seed=2)
+    cached, live, n1 = ctx.memory()
+    assert n1 == n0, (n0, n1)                      # steady state: no driver allocation
+    assert live == 0 and cached > 0
+    free_before = torch.cuda.mem_get_info(DEV)[0]
+    ops.release_memory(DEV)
+    assert ctx.memory()[0] == 0
+    assert torch.cuda.mem_get_info(DEV)[0] >= free_before + cached // 2
+    ia2, wa2 = call(Xa, 50)                        # works again after the trim
+    assert len(ia2) <= 50 and abs(float(wa2.sum()) - 1.0) < 1e-12
