@@ -28,15 +28,15 @@ __global__ void scale_columns_kernel(double* __restrict__ U, int rows, int cols,
 // noise enters the covariance BEFORE the warping (predictive_covariance adds it, BASQ/_gp.py:275-276,
 // and wsabi*_kernel warp its result, BASQ/_wsabi.py:216-224), the jitter after it.
 __global__ void warp_gram_kernel(double* __restrict__ C, int64_t a, int64_t b, int mode, const double* __restrict__ fx,
-                                 const double* __restrict__ fy, double pre_add, double diag_add) {
+                                 const double* __restrict__ fy, double pre_add, double diag_add, int64_t diag_col0) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a * b) return;
-  const int64_t i = t / b, j = t % b;
+  const int64_t i = t / b, j = t % b - diag_col0;   // row i of this block is row diag_col0 + i of the square matrix
   double c = C[t];
   if (i == j) c += pre_add;
-  if (mode == BASQ_WSABI_L) c = fx[i] * c * fy[j];
-  else if (mode == BASQ_WSABI_M) c = fx[i] * c * fy[j] + 0.5 * c * c;
-  else if (mode == BASQ_MMLT_G) c = fx[i] * fy[j] * expm1(c);
+  if (mode == BASQ_WSABI_L) c = fx[i] * c * fy[j + diag_col0];
+  else if (mode == BASQ_WSABI_M) c = fx[i] * c * fy[j + diag_col0] + 0.5 * c * c;
+  else if (mode == BASQ_MMLT_G) c = fx[i] * fy[j + diag_col0] * expm1(c);
   if (i == j) c += diag_add;
   C[t] = c;
 }
@@ -1052,7 +1052,7 @@ int basq_gram(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_
 // (tgemm.cu).  Only the Nystrom range finder asks for that: its products with this matrix are
 // 3xTF32 as well, and only the span of the resulting basis matters.
 int basq::gram_matrix(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t a, const void* Y, int64_t b,
-                      double* out, bool tensor_correction) {
+                      double* out, bool tensor_correction, int64_t diag_col0) {
   KParams kp;
   BASQ_TRY(make_kparams(desc, &kp));
   BASQ_TRY(compute_center(ctx, desc, X, a, &kp));
@@ -1096,7 +1096,7 @@ int basq::gram_matrix(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X
     if (warped || desc->diag_add != 0.0 || pre_add != 0.0) {
       const int64_t tot = a * b;
       warp_gram_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, ctx->stream>>>(
-          out, a, b, warped ? mode : BASQ_PRED_COV, fx.as<double>(), fy.as<double>(), pre_add, desc->diag_add);
+          out, a, b, warped ? mode : BASQ_PRED_COV, fx.as<double>(), fy.as<double>(), pre_add, desc->diag_add, diag_col0);
       ctx->launches++;
       BASQ_CUDA(cudaGetLastError());
     }
@@ -1104,7 +1104,7 @@ int basq::gram_matrix(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X
   } else if (desc->diag_add != 0.0) {
     const int64_t tot = a * b;
     warp_gram_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, ctx->stream>>>(out, a, b, BASQ_PLAIN, nullptr, nullptr,
-                                                                             0.0, desc->diag_add);
+                                                                             0.0, desc->diag_add, diag_col0);
     ctx->launches++;
     BASQ_CUDA(cudaGetLastError());
   }
@@ -1152,6 +1152,18 @@ int basq_nystrom_basis(basq_ctx* ctx, const basq_kernel_desc* desc, const void* 
   BASQ_CHECK(ctx && desc && Z && U_out, BASQ_ERR_INVALID, "basq_nystrom_basis: NULL argument");
   BASQ_CUDA(cudaSetDevice(ctx->device));
   const int rc = nystrom_basis(ctx, desc, Z, M, q, Omega, niter, U_out, S_out);
+  basq_ctx_trim(ctx, -1);
+  return rc;
+}
+
+int basq_nystrom_basis_sharded(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, int64_t M, int q,
+                               const double* Omega, int niter, int rank, int world, double* gram_buf,
+                               double* rows_buf, basq_exchange_fn exchange, void* user, double* U_out) {
+  BASQ_CHECK(ctx && desc && Z && U_out && gram_buf && rows_buf && exchange, BASQ_ERR_INVALID,
+             "basq_nystrom_basis_sharded: NULL argument");
+  BASQ_CUDA(cudaSetDevice(ctx->device));
+  const int rc = nystrom_basis_sharded(ctx, desc, Z, M, q, Omega, niter, rank, world, gram_buf, rows_buf, exchange, user,
+                                       U_out);
   basq_ctx_trim(ctx, -1);
   return rc;
 }

@@ -519,12 +519,17 @@ int dgemm(basq_ctx* ctx, bool ta, bool tb, int m, int n, int k, double alpha, co
 int caratheodory(basq_ctx* ctx, double* A, int n, int S, int lda, double* omega_out);
 
 // api.cu: kernel(X, Y) [a, b] in fp64 (the body of basq_gram)
+// diag_col0: X is rows [diag_col0, diag_col0 + a) of the square matrix kernel(Y, Y) - the diagonal terms
+// (noise, jitter) then sit at (i, diag_col0 + i)
 int gram_matrix(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t a, const void* Y, int64_t b,
-                double* out, bool tensor_correction);
+                double* out, bool tensor_correction, int64_t diag_col0 = 0);
 
 // nystrom.cu
 // out[rows, cols] fp64 N(0, 1) draws of the Philox stream `seed` (candidates.cu)
 int standard_normals(basq_ctx* ctx, uint64_t seed, int64_t offset, int64_t rows, int cols, double* out);
+int nystrom_basis_sharded(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, int64_t M, int q,
+                          const double* Omega, int niter, int rank, int world, double* gram_buf, double* rows_buf,
+                          basq_exchange_fn fn, void* user, double* U_out);
 int nystrom_basis(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, int64_t M, int q,
                   const double* Omega, int niter, double* U_out, double* S_out);
 

@@ -419,14 +419,35 @@ int chol_inverse(basq_ctx* ctx, OrthWs& ws, int q, double floor_val) {
 // Y [M, q] (ld = q) <- basis of span(Y) by shifted CholeskyQR: `passes` = 3 gives an orthonormal
 // basis to machine precision (sCholQR3); 2 is enough between subspace iterations, where only the
 // conditioning of the basis matters
-int orthonormalise(basq_ctx* ctx, OrthWs& ws, double* Y, int64_t M, int q, int passes) {
+// `sh` (row-sharded basis): Y holds this rank's rows only; the Gram matrix is summed over the ranks through the
+// caller's exchange function, everything after it (trace, shift, Cholesky + inverse) is replicated and the
+// factor is applied to the local rows.  M_glob = rows of the whole matrix (the shift depends on it).
+struct ShardXchg {
+  basq_exchange_fn fn = nullptr;
+  void* user = nullptr;
+  double* gram_buf = nullptr;   // [q, q], the buffer the exchange function reduces
+};
+
+int orthonormalise(basq_ctx* ctx, OrthWs& ws, double* Y, int64_t M, int q, int passes, const ShardXchg* sh = nullptr,
+                   int64_t M_glob = 0) {
+  if (!sh) M_glob = M;
   // passes < 0: "until orthonormal to fp64" - a pass whose input Gram matrix is within 0.1 of the
   // identity is the last one (CholeskyQR squares the distance to orthonormality); at most 4.
   const bool adaptive = passes < 0;
   if (adaptive) passes = 4;
   for (int pass = 0; pass < passes; ++pass) {
-    BASQ_TRY(dgemm(ctx, true, false, q, q, (int)M, 1.0, Y, q, Y, q, 0.0, ws.gram.as<double>(), q, false, false,
-                   /*c_symmetric=*/true));
+    if (M > 0) {
+      BASQ_TRY(dgemm(ctx, true, false, q, q, (int)M, 1.0, Y, q, Y, q, 0.0, ws.gram.as<double>(), q, false, false,
+                     /*c_symmetric=*/true));
+    } else {
+      BASQ_CUDA(cudaMemsetAsync(ws.gram.p, 0, sizeof(double) * (size_t)q * q, ctx->stream));
+    }
+    if (sh) {   // sum of the ranks' partial Gram matrices (identical bits on every rank afterwards)
+      BASQ_CUDA(cudaMemcpyAsync(sh->gram_buf, ws.gram.p, sizeof(double) * (size_t)q * q, cudaMemcpyDeviceToDevice, ctx->stream));
+      BASQ_CHECK(sh->fn(sh->user, BASQ_XCHG_ALLREDUCE_GRAM, (int64_t)q * q) == 0, BASQ_ERR_INVALID,
+                 "nystrom: the exchange function failed (all-reduce of the Gram matrix)");
+      BASQ_CUDA(cudaMemcpyAsync(ws.gram.p, sh->gram_buf, sizeof(double) * (size_t)q * q, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     BASQ_CUDA(cudaMemsetAsync(ws.scal.p, 0, 2 * sizeof(double), ctx->stream));
     trace_kernel<<<1, 256, 0, ctx->stream>>>(ws.gram.as<double>(), q, q, ws.scal.as<double>());
     ctx->launches++;
@@ -442,16 +463,18 @@ int orthonormalise(basq_ctx* ctx, OrthWs& ws, double* Y, int64_t M, int q, int p
     if (adaptive && pass > 0 && trdev[1] < 0.1) passes = pass + 1;  // this pass finishes the job
     const double eps = 2.220446049250313e-16;
     // shift of Fukaya et al. (shifted CholeskyQR3): 11 (M q + q (q+1)) u |Y|_2^2 ; |Y|_2^2 <= trace
-    const double shift = (pass == 0) ? 11.0 * ((double)M * q + (double)q * (q + 1)) * eps * tr : 0.0;
+    const double shift = (pass == 0) ? 11.0 * ((double)M_glob * q + (double)q * (q + 1)) * eps * tr : 0.0;
     if (shift > 0.0) {
       add_diag_kernel<<<ceil_div(q, 256), 256, 0, ctx->stream>>>(ws.gram.as<double>(), q, q, shift);
       ctx->launches++;
     }
     BASQ_TRY(chol_inverse(ctx, ws, q, tr * 1e-30));
     // Y <- Y L^-T
-    BASQ_TRY(dgemm(ctx, false, true, (int)M, q, q, 1.0, Y, q, ws.linv.as<double>(), q, 0.0, ws.tmp.as<double>(), q,
-                   /*b_lower_tri=*/true));
-    BASQ_CUDA(cudaMemcpyAsync(Y, ws.tmp.p, sizeof(double) * (size_t)M * q, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (M > 0) {
+      BASQ_TRY(dgemm(ctx, false, true, (int)M, q, q, 1.0, Y, q, ws.linv.as<double>(), q, 0.0, ws.tmp.as<double>(), q,
+                     /*b_lower_tri=*/true));
+      BASQ_CUDA(cudaMemcpyAsync(Y, ws.tmp.p, sizeof(double) * (size_t)M * q, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
   }
   int status = 0;
   BASQ_CUDA(cudaMemcpyAsync(&status, ws.flags.as<int>() + 64, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -573,6 +596,106 @@ int nystrom_basis(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, in
     BASQ_TRY(dgemm(ctx, false, false, Mi, q, Mi, 1.0, K.as<double>(), M, Y.as<double>(), q, 0.0, Y2.as<double>(), q));
     BASQ_TRY(dgemm(ctx, true, false, q, q, Mi, 1.0, Y.as<double>(), q, Y2.as<double>(), q, 0.0, ws.gram.as<double>(), q));
     diag_kernel<<<ceil_div(q, 256), 256, 0, ctx->stream>>>(ws.gram.as<double>(), q, q, S_out);
+    ctx->launches++;
+  }
+  BASQ_CUDA(cudaGetLastError());
+  BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+  return BASQ_OK;
+}
+
+// Row-sharded variant (multi-GPU): rank r of `world` owns rows [r chunk, min(M, (r + 1) chunk)), chunk = ceil(M / world),
+// of K(Z, Z) - it evaluates, converts and multiplies only those - and the ranks meet twice per product: a sum
+// of the q x q Gram matrices (CholeskyQR) and an all-gather of the orthonormalised rows, both done by the
+// caller's exchange function on buffers the caller owns (the library stays free of any communication
+// dependency; basq_b200/sharded.py passes torch.distributed collectives).  rows_buf [world * chunk, q] is the
+// full basis in global row order (rank r's rows at r * chunk).  The Cholesky factorisations are replicated.
+int nystrom_basis_sharded(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, int64_t M, int q,
+                          const double* Omega, int niter, int rank, int world, double* gram_buf, double* rows_buf,
+                          basq_exchange_fn fn, void* user, double* U_out) {
+  PhaseTimer timer(ctx, PH_NYS);
+  BASQ_CHECK(q >= 1 && q <= M, BASQ_ERR_INVALID, "nystrom: need 1 <= q <= M (q=%d M=%lld)", q, (long long)M);
+  BASQ_CHECK(world >= 1 && rank >= 0 && rank < world && fn && gram_buf && rows_buf, BASQ_ERR_INVALID,
+             "nystrom (sharded): bad rank / world / buffers");
+  BASQ_CHECK(M <= 46000 * (int64_t)world, BASQ_ERR_UNSUPPORTED, "nystrom: M=%lld landmarks too many", (long long)M);
+  BASQ_CHECK(niter >= 0 && niter <= 16, BASQ_ERR_INVALID, "nystrom: niter out of range");
+  const int64_t chunk = (M + world - 1) / world;
+  const int64_t row0 = std::min<int64_t>(M, (int64_t)rank * chunk);
+  const int nr = (int)(std::min<int64_t>(M, row0 + chunk) - row0);
+  const int Mi = (int)M;
+  const size_t esz = desc->dtype == BASQ_F64 ? 8 : 4;
+  ShardXchg sh;
+  sh.fn = fn; sh.user = user; sh.gram_buf = gram_buf;
+
+  DevBuf K, Yr, drawn;
+  if (!Omega) {
+    BASQ_TRY(drawn.alloc(ctx, sizeof(double) * (size_t)M * q));
+    BASQ_TRY(standard_normals(ctx, ctx->seed + ctx->draws, 0, M, q, drawn.as<double>()));   // the same on every rank
+    ctx->draws++;
+    Omega = drawn.as<double>();
+  }
+  BASQ_TRY(K.alloc(ctx, sizeof(double) * (size_t)std::max(nr, 1) * M));
+  BASQ_TRY(Yr.alloc(ctx, sizeof(double) * (size_t)std::max(nr, 1) * q));
+  OrthWs ws;
+  BASQ_TRY(ws.gram.alloc(ctx, sizeof(double) * (size_t)q * q));
+  BASQ_TRY(ws.linv.alloc(ctx, sizeof(double) * (size_t)q * q));
+  BASQ_TRY(ws.tmp.alloc(ctx, sizeof(double) * (size_t)std::max(nr, 1) * q));
+  BASQ_TRY(ws.prow.alloc(ctx, sizeof(double) * 4 * q));
+  BASQ_TRY(ws.prow2.alloc(ctx, sizeof(double) * 2 * (size_t)q * q));
+  BASQ_TRY(ws.flags.alloc(ctx, 512));
+  BASQ_CUDA(cudaMemsetAsync(ws.flags.p, 0, 512, ctx->stream));
+  BASQ_TRY(ws.scal.alloc(ctx, 64));
+  const bool tensor = (desc->dtype == BASQ_F32) && !ctx->no_tensor_nystrom;
+  BlkOperand Kb, Yb;
+  if (nr > 0) {
+    const unsigned char* Zr = static_cast<const unsigned char*>(Z) + (size_t)row0 * desc->d * esz;
+    BASQ_TRY(gram_matrix(ctx, desc, Zr, nr, Z, M, K.as<double>(), tensor, /*diag_col0=*/row0));
+    if (tensor) {
+      BASQ_TRY(Kb.alloc(ctx, nr, Mi));
+      BASQ_TRY(blk_from_f64(ctx, K.as<double>(), M, false, &Kb));
+      BASQ_TRY(Yb.alloc(ctx, q, Mi));
+    }
+  }
+  // Yr [nr, q] = K[rows, :] Yin  (Yin: the full [M, q] matrix)
+  auto multiply = [&](const double* Yin) -> int {
+    if (nr == 0) return BASQ_OK;
+    if (!tensor) return dgemm(ctx, false, false, nr, q, Mi, 1.0, K.as<double>(), M, Yin, q, 0.0, Yr.as<double>(), q);
+    BASQ_TRY(blk_from_f64(ctx, Yin, q, true, &Yb));
+    return tgemm(ctx, Yb, Kb, 1.0, Yr.as<double>(), q, true);
+  };
+  // this rank's rows into the shared layout, then every rank's
+  auto gather = [&]() -> int {
+    if (nr > 0)
+      BASQ_CUDA(cudaMemcpyAsync(rows_buf + (size_t)row0 * q, Yr.p, sizeof(double) * (size_t)nr * q, cudaMemcpyDeviceToDevice,
+                                ctx->stream));
+    BASQ_CHECK(fn(user, BASQ_XCHG_ALLGATHER_ROWS, chunk * q) == 0, BASQ_ERR_INVALID,
+               "nystrom: the exchange function failed (all-gather of the basis rows)");
+    return BASQ_OK;
+  };
+  static const int final_passes = [] { const char* e = getenv("BASQ_NYS_FINAL_PASSES"); return e ? atoi(e) : -1; }();
+  BASQ_TRY(multiply(Omega));
+  BASQ_TRY(orthonormalise(ctx, ws, Yr.as<double>(), nr, q, niter > 0 ? 1 : final_passes, &sh, M));
+  BASQ_TRY(gather());
+  const bool force_mid = [] { const char* e = getenv("BASQ_NYS_ORTH_MID"); return e && e[0] == '1'; }();
+  bool skip_mid = false;
+  if (!force_mid && niter > 0) {   // the factor is replicated: every rank takes the same decision
+    diag_spread_kernel<<<1, 256, 0, ctx->stream>>>(ws.linv.as<double>(), q, q, ws.scal.as<double>());
+    ctx->launches++;
+    double spread = 0.0;
+    BASQ_CUDA(cudaMemcpyAsync(&spread, ws.scal.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    skip_mid = spread > 1e-2;
+  }
+  for (int it = 0; it < niter; ++it) {
+    BASQ_TRY(multiply(rows_buf));
+    if (!skip_mid) BASQ_TRY(orthonormalise(ctx, ws, Yr.as<double>(), nr, q, 1, &sh, M));
+    BASQ_TRY(gather());
+    BASQ_TRY(multiply(rows_buf));
+    BASQ_TRY(orthonormalise(ctx, ws, Yr.as<double>(), nr, q, it + 1 == niter ? final_passes : 1, &sh, M));
+    BASQ_TRY(gather());
+  }
+  {
+    dim3 grid((unsigned)ceil_div(q, 32), (unsigned)ceil_div(Mi, 32));
+    transpose_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(rows_buf, Mi, q, U_out);
     ctx->launches++;
   }
   BASQ_CUDA(cudaGetLastError());

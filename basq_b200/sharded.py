@@ -188,3 +188,87 @@ def recombination_sharded(pts_rec_local, pts_nys, num_pts, kernel, N_glob, idx_b
         return gather_result(idx, w, sess.n, group=group)
     finally:
         sess.close()
+
+
+_XCHG_BUFFERS = {}
+
+
+def nystrom_basis_sharded(kernel, Z, q, omega=None, niter=2, group=None, seed=None, device=None):
+    """U [q, M], the Nystrom basis of ops.nystrom_basis, with the rows of K(Z, Z) sharded over the ranks
+    (basq_nystrom_basis_sharded): every rank evaluates and multiplies M / world rows; per product the ranks
+    all-reduce a q x q Gram matrix and all-gather the orthonormalised rows.  Z (and omega, or the seed) must
+    be the same on every rank; every rank returns the same U.  The collectives are torch.distributed's on the
+    current stream (NCCL); with a gloo group they are staged through the host (tests).  Without a process
+    group the call degenerates to one shard."""
+    import ctypes as C
+
+    from . import _lib, ops
+
+    spec, ctx, device, dtype = ops._common(kernel, Z, device)
+    Zd = ops._prep(Z, device, dtype)
+    M = len(Zd)
+    on = dist.is_initialized() and dist.get_world_size(group) > 1
+    world = dist.get_world_size(group) if on else 1
+    rank = dist.get_rank(group) if on else 0
+    chunk = -(-M // world)
+    # exchange buffers live across calls: allocating 130 MB of them per call made torch's caching allocator
+    # re-carve its blocks every few steps (sporadic 40-130 ms stalls in the 2-GPU bench)
+    key = (device.index, world, chunk, q)
+    bufs = _XCHG_BUFFERS.get(key)
+    if bufs is None:
+        _XCHG_BUFFERS.clear()       # one shape at a time is enough; do not hoard memory for old ones
+        bufs = _XCHG_BUFFERS[key] = (torch.empty(q * q, dtype=torch.float64, device=device),
+                                     torch.zeros(world * chunk * q, dtype=torch.float64, device=device),
+                                     torch.empty(chunk * q, dtype=torch.float64, device=device))
+    gram_buf, rows_buf, mine = bufs
+    staged = on and dist.get_backend(group) != "nccl"
+    failure = []
+
+    def exchange(_user, op, count):
+        try:
+            if not on:
+                return 0
+            if op == 0:
+                if staged:
+                    h = gram_buf.cpu()
+                    dist.all_reduce(h, group=group)
+                    gram_buf.copy_(h)
+                else:
+                    dist.all_reduce(gram_buf, group=group)
+            else:
+                mine.copy_(rows_buf[rank * count:(rank + 1) * count])
+                if staged:
+                    parts = [torch.empty(count, dtype=torch.float64) for _ in range(world)]
+                    dist.all_gather(parts, mine.cpu(), group=group)
+                    rows_buf.copy_(torch.cat(parts))
+                else:
+                    dist.all_gather_into_tensor(rows_buf, mine, group=group)
+            return 0
+        except Exception as e:      # never let an exception cross the C frame
+            failure.append(e)
+            return 1
+
+    cb = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int64)(exchange)
+    if omega is not None:
+        omega = ops._prep(omega, device, torch.float64)
+    else:
+        ops._seed_context(ctx, seed if seed is not None else _shared_seed(group, on, device))
+    desc, keep = spec.to_desc(Zd.shape[1], device, dtype)
+    U = torch.empty(q, M, dtype=torch.float64, device=device)
+    rc = _lib.lib.basq_nystrom_basis_sharded(ctx.handle, C.byref(desc), Zd.data_ptr(), M, int(q),
+                                             omega.data_ptr() if omega is not None else None, int(niter), rank, world,
+                                             gram_buf.data_ptr(), rows_buf.data_ptr(), C.cast(cb, C.c_void_p), None, U.data_ptr())
+    if failure:
+        raise failure[0]
+    _lib.check(rc)
+    return U
+
+
+def _shared_seed(group, on, device):
+    """One draw of rank 0's torch generator, shared with the other ranks: the test matrix must be the same
+    everywhere (torch.manual_seed on rank 0 reproduces the run)."""
+    s = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64)
+    if on:
+        s = s.to(device) if dist.get_backend(group) == "nccl" else s
+        dist.broadcast(s, dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return int(s.item())

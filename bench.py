@@ -426,8 +426,16 @@ def run_ours(a, rank, world, local_rank):
     gO = torch.Generator(device=dev).manual_seed(7)
     Omega = torch.randn(a.M, q, generator=gO, device=dev, dtype=torch.float64)
 
+    shard_basis = world > 1 and os.environ.get("BASQ_BENCH_SHARD_NYSTROM", "1") != "0"
+
+    def basis(k, Zb, omega=None, seed=None):
+        """Nystrom basis: at N > 1 the rows of K(Z, Z) are sharded over the ranks (basq_nystrom_basis_sharded)."""
+        if shard_basis:
+            return sharded.nystrom_basis_sharded(k, Zb, q, omega=omega, seed=seed)
+        return ops.nystrom_basis(k, Zb, q, omega=omega, want_S=False, seed=seed)[1]
+
     def step_device():
-        _, U = ops.nystrom_basis(kern, Z, q, omega=Omega, want_S=False)
+        U = basis(kern, Z, omega=Omega)
         if world == 1:
             return ops.recombine(kern, X, Z, U)
         return sharded.recombination_sharded(X, Z, a.n, kern, N_glob, base, U)
@@ -450,7 +458,7 @@ def run_ours(a, rank, world, local_rank):
         with torch.cuda.stream(side_stream):
             Xd = X_host.to(dev, non_blocking=True)
         x_ready = side_stream.record_event()
-        _, U = ops.nystrom_basis(kern, Zd, q, want_S=False, seed=7)     # every rank draws the same matrix
+        U = basis(kern, Zd, seed=7)     # every rank draws the same matrix
         main.wait_event(x_ready)
         Xd.record_stream(main)
         idx, w = sharded.recombination_sharded(Xd, Zd, a.n, kern, N_glob, base, U)
@@ -470,7 +478,7 @@ def run_ours(a, rank, world, local_rank):
         Xs = bsampler.sample_mvn(prior_mean, None, N_loc, seed=seed, offset=base, device=dev, scale_tril=prior_tril)
         Zs = Xs[: a.M] if world == 1 else bsampler.sample_mvn(prior_mean, None, a.M, seed=seed, offset=0, device=dev,
                                                               scale_tril=prior_tril)
-        _, U = ops.nystrom_basis(kern, Zs, q, omega=Omega, want_S=False)
+        U = basis(kern, Zs, omega=Omega)
         if world == 1:
             return ops.recombine(kern, Xs, Zs, U)
         return sharded.recombination_sharded(Xs, Zs, a.n, kern, N_glob, base, U)
@@ -557,7 +565,7 @@ def run_ours(a, rank, world, local_rank):
         Xs_ = X[: hi - lo]
 
         def step_strong():
-            _, U = ops.nystrom_basis(kern, Z, q, omega=Omega, want_S=False)
+            U = basis(kern, Z, omega=Omega)
             return sharded.recombination_sharded(Xs_, Z, a.n, kern, a.N, lo, U)
         step_strong()
         ctx.profile(True)
@@ -585,7 +593,7 @@ def run_ours(a, rank, world, local_rank):
             k5 = spec_from_model(m5, mode)
 
             def step5():
-                _, U = ops.nystrom_basis(k5, Z, q, omega=Omega, want_S=False)
+                U = basis(k5, Z, omega=Omega)
                 return sharded.recombination_sharded(Xs5, Z, a.n, k5, a.N, lo, U)
             step5()
             ms5, out5 = timed(step5, 2)

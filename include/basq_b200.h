@@ -162,6 +162,25 @@ int basq_features(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, in
    sets, each mass rescaled by omega_j).  A is destroyed.  n_kept_host may be NULL. */
 int basq_car(basq_ctx* ctx, double* A, int n, int S, int lda, double* omega_out, int* n_kept_host);
 
+/* Row-sharded variant for one process per GPU: rank `rank` of `world` evaluates, converts and multiplies only rows
+   [rank * chunk, min(M, (rank + 1) * chunk)), chunk = ceil(M / world), of K(Z, Z); Z, Omega (or the seed, when
+   Omega is NULL) must be the same on every rank.  The ranks meet through `exchange`, a function of the caller
+   that the library calls on the host while its kernels are queued on the context's stream:
+     op BASQ_XCHG_ALLREDUCE_GRAM: sum gram_buf[count] (fp64, count = q * q) over the ranks, in place;
+     op BASQ_XCHG_ALLGATHER_ROWS: rows_buf is [world][count] (count = chunk * q); this rank's part is filled
+                                  in, fetch the others'.
+   Both must be ordered after the work already queued on the context's stream and before the work queued after
+   they return (torch.distributed collectives on the current stream do this), and must return 0.  gram_buf
+   [q * q] and rows_buf [world * chunk * q] are device buffers of the caller.  U_out [q, M] is the same basis
+   on every rank.  The library itself links no communication library.  Same algorithm as basq_nystrom_basis;
+   the Cholesky factorisations are replicated. */
+#define BASQ_XCHG_ALLREDUCE_GRAM 0
+#define BASQ_XCHG_ALLGATHER_ROWS 1
+typedef int (*basq_exchange_fn)(void* user, int op, int64_t count);
+int basq_nystrom_basis_sharded(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, int64_t M, int q,
+                               const double* Omega, int niter, int rank, int world, double* gram_buf,
+                               double* rows_buf, basq_exchange_fn exchange, void* user, double* U_out);
+
 /* ---- recombination: recombination / rc_kernel_svd / Mod_Tchernychova_Lyons, BASQ/_rchq.py:4-130 */
 /* X[N,d] candidates, Z[M,d] landmarks, U[q,M] basis (fp64), mu[N] fp64 weights or NULL (uniform).
    Writes at most q+1 ascending indices and positive weights summing to sum(mu). */
