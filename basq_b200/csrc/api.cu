@@ -1239,6 +1239,31 @@ int basq_session_set_objective(basq_session* s, const double* obj) {
   return BASQ_OK;
 }
 
+// the context's device buffer for host-buffer calls and the side stream their copies travel on
+static int ensure_host_buffer(basq_ctx* ctx, size_t need) {
+  if (need > ctx->host_x_bytes) {
+    if (ctx->host_x) {
+      BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (ctx->side) BASQ_CUDA(cudaStreamSynchronize(ctx->side));
+      BASQ_CUDA(cudaFree(ctx->host_x));
+      ctx->host_x = nullptr;
+      ctx->host_x_bytes = 0;
+    }
+    BASQ_CUDA(cudaMalloc(&ctx->host_x, need));
+    ctx->host_x_bytes = need;
+  }
+  return BASQ_OK;
+}
+
+static int ensure_side_stream(basq_ctx* ctx) {
+  if (!ctx->side) {   // created once per context: stream / event creation and destruction take driver-wide locks
+    BASQ_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    BASQ_CUDA(cudaEventCreateWithFlags(&ctx->side_ev[0], cudaEventDisableTiming));
+    BASQ_CUDA(cudaEventCreateWithFlags(&ctx->side_ev[1], cudaEventDisableTiming));
+  }
+  return BASQ_OK;
+}
+
 static int recombine_host_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X_host, int64_t N,
                                const void* Z_host, int64_t M, const double* U_host, int q, const double* Omega_host,
                                int niter, const double* mu_host, int64_t* idx_out_host, double* w_out_host,
@@ -1259,16 +1284,8 @@ static int recombine_host_impl(basq_ctx* ctx, const basq_kernel_desc* desc, cons
     const size_t bZ = up(esz * (size_t)M * desc->d), bU = up(sizeof(double) * (size_t)q * M);
     const size_t bi = up(sizeof(int64_t) * (q + 1)), bw = up(sizeof(double) * (q + 1));
     const size_t need = bX + bmu + bZ + bU + bi + bw;
-    if (need > ctx->host_x_bytes) {
-      if (ctx->host_x) {
-        BASQ_CUDA(cudaStreamSynchronize(ctx->stream));
-        BASQ_CUDA(cudaFree(ctx->host_x));
-        ctx->host_x = nullptr;
-        ctx->host_x_bytes = 0;
-      }
-      BASQ_CUDA(cudaMalloc(&ctx->host_x, need));
-      ctx->host_x_bytes = need;
-    }
+    ctx->staged_N = -1;   // the buffer is about to be overwritten
+    BASQ_TRY(ensure_host_buffer(ctx, need));
     unsigned char* base = static_cast<unsigned char*>(ctx->host_x);
     dX.p = base;
     if (mu_host) dmu_p = reinterpret_cast<double*>(base + bX);
@@ -1279,11 +1296,7 @@ static int recombine_host_impl(basq_ctx* ctx, const basq_kernel_desc* desc, cons
   }
   // The candidates (the bulk of the bytes) travel on a side stream while the basis is built from the
   // landmarks on the main stream: the Nystrom phase hides the host-to-device copy.
-  if (!ctx->side) {   // created once per context: stream / event creation and destruction take driver-wide locks
-    BASQ_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
-    BASQ_CUDA(cudaEventCreateWithFlags(&ctx->side_ev[0], cudaEventDisableTiming));
-    BASQ_CUDA(cudaEventCreateWithFlags(&ctx->side_ev[1], cudaEventDisableTiming));
-  }
+  BASQ_TRY(ensure_side_stream(ctx));
   cudaStream_t side = ctx->side;
   cudaEvent_t x_ready = ctx->side_ev[0], buffers_ready = ctx->side_ev[1];
   auto cleanup = [&]() { cudaStreamSynchronize(side); };   // the next call reuses the candidate buffer: the copy must be over
@@ -1350,6 +1363,52 @@ int basq_recombine_host(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
                                      idx_out_host, w_out_host, n_out_host);
   if (ctx) basq_ctx_trim(ctx, -1);
   return rc;
+}
+
+// ---- host buffers for the sharded path -------------------------------------------------------------------
+int basq_ctx_stage_candidates(basq_ctx* ctx, const void* X_host, int64_t N_loc, int d, int dtype, const double* mu_host) {
+  BASQ_CHECK(ctx && (X_host || N_loc == 0) && N_loc >= 0 && d >= 1 && d <= BASQ_MAX_DIM &&
+                 (dtype == BASQ_F32 || dtype == BASQ_F64),
+             BASQ_ERR_INVALID, "basq_ctx_stage_candidates: bad argument");
+  BASQ_CUDA(cudaSetDevice(ctx->device));
+  const size_t esz = dtype == BASQ_F64 ? 8 : 4;
+  auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t bX = up(esz * (size_t)N_loc * d), bmu = mu_host ? up(sizeof(double) * (size_t)N_loc) : 0;
+  ctx->staged_N = -1;
+  BASQ_TRY(ensure_host_buffer(ctx, std::max<size_t>(bX + bmu, 256)));
+  BASQ_TRY(ensure_side_stream(ctx));
+  // earlier work on the main stream may still read the buffer (a session under construction)
+  BASQ_CUDA(cudaEventRecord(ctx->side_ev[1], ctx->stream));
+  BASQ_CUDA(cudaStreamWaitEvent(ctx->side, ctx->side_ev[1], 0));
+  unsigned char* base = static_cast<unsigned char*>(ctx->host_x);
+  if (N_loc > 0) BASQ_CUDA(cudaMemcpyAsync(base, X_host, esz * (size_t)N_loc * d, cudaMemcpyHostToDevice, ctx->side));
+  ctx->staged_mu = nullptr;
+  if (mu_host && N_loc > 0) {
+    ctx->staged_mu = reinterpret_cast<double*>(base + bX);
+    BASQ_CUDA(cudaMemcpyAsync(ctx->staged_mu, mu_host, sizeof(double) * (size_t)N_loc, cudaMemcpyHostToDevice, ctx->side));
+  }
+  BASQ_CUDA(cudaEventRecord(ctx->side_ev[0], ctx->side));
+  ctx->staged_N = N_loc;
+  ctx->staged_d = d;
+  ctx->staged_dtype = dtype;
+  return BASQ_OK;
+}
+
+int basq_session_create_staged(basq_ctx* ctx, const basq_kernel_desc* desc, int64_t N_loc, int64_t N_glob, int64_t idx_base,
+                               const void* Z, int64_t M, const double* U, int q, basq_session** out) {
+  BASQ_CHECK(ctx && desc && out, BASQ_ERR_INVALID, "basq_session_create_staged: NULL argument");
+  *out = nullptr;
+  BASQ_CHECK(ctx->staged_N == N_loc && ctx->staged_d == desc->d && ctx->staged_dtype == desc->dtype, BASQ_ERR_INVALID,
+             "basq_session_create_staged: the staged candidates (%lld x %d, dtype %d) do not match the call (%lld x %d, dtype %d)",
+             (long long)ctx->staged_N, ctx->staged_d, ctx->staged_dtype, (long long)N_loc, desc->d, desc->dtype);
+  BASQ_CUDA(cudaSetDevice(ctx->device));
+  BASQ_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->side_ev[0], 0));
+  std::unique_ptr<basq_session> s(new (std::nothrow) basq_session());
+  BASQ_CHECK(s, BASQ_ERR_INVALID, "out of host memory");
+  BASQ_TRY(session_create_impl(ctx, desc, N_loc > 0 ? ctx->host_x : nullptr, N_loc, N_glob, idx_base, Z, M, U, q,
+                               ctx->staged_mu, 0, s.get()));
+  *out = s.release();
+  return BASQ_OK;
 }
 
 int basq_session_create(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t N_loc, int64_t N_glob,

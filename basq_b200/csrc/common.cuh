@@ -145,6 +145,10 @@ struct basq_ctx {
   // 127-245 ms and an occasional second of re-growth where the device-resident path takes a steady 125 ms)
   void* host_x = nullptr;
   size_t host_x_bytes = 0;
+  // basq_ctx_stage_candidates: what currently travels / sits in host_x for basq_session_create_staged
+  int64_t staged_N = -1;
+  int staged_d = 0, staged_dtype = 0;
+  double* staged_mu = nullptr;
   cudaEvent_t side_ev[2] = {nullptr, nullptr};
   bool eval_f32 = false;           // basq_ctx_allow_f32_eval: fp64 inputs may be evaluated on the fp32 tensor-core path
   int64_t demotions = 0;

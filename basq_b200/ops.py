@@ -209,30 +209,66 @@ def recombine_host(kernel, X_host, Z_host, q, U_host=None, omega_host=None, mu_h
     return idx[: n_out.value], w[: n_out.value]
 
 
+_F = {torch.float32: _lib.F32, torch.float64: _lib.F64}
+
+
+def stage_candidates(X_host, mu_host=None, device="cuda"):
+    """Start copying a rank's shard of candidates (and weights) from HOST (ideally pinned) memory into the
+    context's device buffer (basq_ctx_stage_candidates); returns (N_loc, dtype) for Session(staged=...).
+    The copy runs on a side stream: build the basis meanwhile."""
+    if X_host.device.type != "cpu" or X_host.dim() != 2 or X_host.dtype not in _F:
+        raise ValueError("stage_candidates takes a host tensor [N_loc, d] in float32 or float64")
+    X_host = X_host.contiguous()
+    if mu_host is not None:
+        if mu_host.device.type != "cpu" or tuple(mu_host.shape) != (len(X_host),):
+            raise ValueError(f"mu_host must be a host tensor of shape {(len(X_host),)}")
+        mu_host = mu_host.to(torch.float64).contiguous()
+    ctx = _lib.context_for(torch.device(device))
+    _lib.check(_lib.lib.basq_ctx_stage_candidates(ctx.handle, X_host.data_ptr(), len(X_host), X_host.shape[1],
+                                                  _F[X_host.dtype], mu_host.data_ptr() if mu_host is not None else None))
+    ctx._staged_keep = (X_host, mu_host)      # the host buffers must outlive the copy
+    return len(X_host), X_host.dtype
+
+
 class Session:
     """Staged recombination over a rank-local shard (basq_session_* in the C ABI)."""
 
-    def __init__(self, kernel, X_loc, Z, U, N_glob, idx_base, mu_loc=None, device=None, obj_loc=None):
-        spec, ctx, device, dtype = _common(kernel, X_loc, device)
+    def __init__(self, kernel, X_loc, Z, U, N_glob, idx_base, mu_loc=None, device=None, obj_loc=None, staged=None):
+        """staged = (N_loc, dtype): the shard was handed over with stage_candidates (host buffers); X_loc and
+        mu_loc are then ignored."""
+        if staged is not None:
+            n_loc, dtype = int(staged[0]), staged[1]
+            spec = describe_kernel(kernel)
+            device = torch.device(device if device is not None else Z.device)
+            ctx = _lib.context_for(device)
+        else:
+            spec, ctx, device, dtype = _common(kernel, X_loc, device)
         self.ctx, self.device = ctx, device
-        Xd, Zd = _prep(X_loc, device, dtype), _prep(Z, device, dtype)
+        Zd = _prep(Z, device, dtype)
         Ud = _prep(U, device, torch.float64)
         self.q = Ud.shape[0]
         self.n = self.q + 1
         self.S = 2 * self.n
-        mud = _prep(mu_loc, device, torch.float64) if mu_loc is not None else None
         desc, keep = spec.to_desc(Zd.shape[1], device, dtype)
-        self._keep = keep + [Xd, Zd, Ud, mud]
         h = C.c_void_p()
-        _lib.check(_lib.lib.basq_session_create(ctx.handle, C.byref(desc), Xd.data_ptr() if len(Xd) else None,
-                                                len(Xd), int(N_glob), int(idx_base), Zd.data_ptr(), len(Zd),
-                                                Ud.data_ptr(), self.q,
-                                                mud.data_ptr() if mud is not None else None, C.byref(h)))
+        if staged is not None:
+            self._keep = keep + [Zd, Ud]
+            _lib.check(_lib.lib.basq_session_create_staged(ctx.handle, C.byref(desc), n_loc, int(N_glob), int(idx_base),
+                                                           Zd.data_ptr(), len(Zd), Ud.data_ptr(), self.q, C.byref(h)))
+        else:
+            Xd = _prep(X_loc, device, dtype)
+            n_loc = len(Xd)
+            mud = _prep(mu_loc, device, torch.float64) if mu_loc is not None else None
+            self._keep = keep + [Xd, Zd, Ud, mud]
+            _lib.check(_lib.lib.basq_session_create(ctx.handle, C.byref(desc), Xd.data_ptr() if len(Xd) else None,
+                                                    len(Xd), int(N_glob), int(idx_base), Zd.data_ptr(), len(Zd),
+                                                    Ud.data_ptr(), self.q,
+                                                    mud.data_ptr() if mud is not None else None, C.byref(h)))
         self.handle = h
         self.rows = self.n
         if obj_loc is not None:
             objd = _prep(obj_loc, device, torch.float64)
-            assert objd.shape == (len(Xd),)
+            assert objd.shape == (n_loc,)
             self._keep.append(objd)
             _lib.check(_lib.lib.basq_session_set_objective(h, objd.data_ptr()))
             self.rows = self.n + 1

@@ -175,14 +175,15 @@ def gather_result(idx, w, n, group=None):
 
 
 def recombination_sharded(pts_rec_local, pts_nys, num_pts, kernel, N_glob, idx_base, U, init_weights_local=None,
-                          group=None, obj_local=None):
+                          group=None, obj_local=None, staged=None):
     """Sharded counterpart of recombination(): this rank holds pts_rec_local = rows
     [idx_base, idx_base + len) of the global candidate set; pts_nys, U and the GP caches are
-    replicated.  Returns the full (idx, w) on every rank."""
+    replicated.  Returns the full (idx, w) on every rank.  staged = ops.stage_candidates(X_host_local, ...):
+    the shard comes from host memory through the C ABI (pts_rec_local / init_weights_local are ignored)."""
     from . import ops
 
     sess = ops.Session(kernel, pts_rec_local, pts_nys, U, N_glob, idx_base, mu_loc=init_weights_local,
-                       obj_loc=obj_local)
+                       obj_loc=obj_local, staged=staged, device=pts_nys.device if staged is not None else None)
     try:
         idx, w = recombine_sharded(sess, sess.n, sess.S, group=group, device=sess.device)
         return gather_result(idx, w, sess.n, group=group)

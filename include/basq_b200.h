@@ -213,6 +213,17 @@ int basq_recombine_host(basq_ctx* ctx, const basq_kernel_desc* desc, const void*
 int basq_session_create(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t N_loc,
                         int64_t N_glob, int64_t idx_base, const void* Z, int64_t M,
                         const double* U, int q, const double* mu, basq_session** out);
+/* The same from HOST candidates, for one process per GPU: basq_ctx_stage_candidates starts copying this rank's
+   shard X_host[N_loc, d] (dtype) and, if not NULL, its weights mu_host[N_loc] from (pinned) host memory into a
+   device buffer the context owns, on a side stream, and returns at once - call it first, build the basis
+   (basq_nystrom_basis / _sharded) while the bytes travel, then basq_session_create_staged creates the
+   session from the staged shard (it waits for the copy on the context's stream).  One staged shard per
+   context at a time; basq_recombine_host uses the same buffer. */
+int basq_ctx_stage_candidates(basq_ctx* ctx, const void* X_host, int64_t N_loc, int d, int dtype,
+                              const double* mu_host);
+int basq_session_create_staged(basq_ctx* ctx, const basq_kernel_desc* desc, int64_t N_loc, int64_t N_glob,
+                               int64_t idx_base, const void* Z, int64_t M, const double* U, int q,
+                               basq_session** out);
 void basq_session_destroy(basq_session* s);
 /* Objective-aware mode for a staged session: obj[N_loc] (device, fp64, -calc_obj per local row, kept
    by the caller) or NULL to switch it off.  Level systems then have n + 1 rows (basq_session_level

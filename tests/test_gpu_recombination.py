@@ -330,6 +330,31 @@ def test_host_buffer_entry_draws_its_own_test_matrix(bq):
     assert torch.allclose(U1, U1b, rtol=0, atol=1e-12) and not torch.allclose(U1, U0, rtol=0, atol=1e-6)
 
 
+def test_staged_host_shards_match_device_shards(bq):
+    """basq_ctx_stage_candidates + basq_session_create_staged: a rank hands its shard over from host memory
+    (the copy runs on a side stream while the basis is built) - same rule as with device tensors, with and
+    without weights; a mismatching stage is refused."""
+    basq_b200, _lib, ops, sharded = bq
+    g = torch.Generator().manual_seed(21)
+    N, d, M, n = 40_003, 5, 200, 24
+    X = (math.sqrt(2.0) * torch.randn(N, d, generator=g)).pin_memory()
+    Z = X[:M].clone().to(DEV)
+    cov = _plain_model(0, 1.7)
+    _, U = ops.nystrom_basis(cov.forward, Z, n - 1, want_S=False, seed=3)
+    mu = torch.rand(N, generator=g, dtype=torch.float64)
+    mu[torch.rand(N, generator=g) < 0.2] = 0.0
+    mu = (mu / mu.sum()).pin_memory()
+    for weights in (None, mu):
+        ref_i, ref_w = sharded.recombination_sharded(X.to(DEV), Z, n, cov.forward, N, 0, U,
+                                                     init_weights_local=None if weights is None else weights.to(DEV))
+        staged = ops.stage_candidates(X, weights, device=DEV)
+        got_i, got_w = sharded.recombination_sharded(None, Z, n, cov.forward, N, 0, U, staged=staged)
+        assert torch.equal(ref_i, got_i) and torch.equal(ref_w, got_w)
+    ops.stage_candidates(X[:100], device=DEV)
+    with pytest.raises(RuntimeError, match="do not match"):
+        ops.Session(cov.forward, None, Z, U, N, 0, staged=(N, torch.float32), device=DEV)
+
+
 def test_size_independent_properties_large(bq):
     """At a size the CPU oracle cannot finish quickly: N = 2e6, d = 10, n = 200.  Size-independent
     properties: mass, positivity, count, and moments for a random subset of test functions
