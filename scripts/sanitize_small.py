@@ -14,7 +14,7 @@ from basq_b200 import _lib, ops, sampler
 from oracle import gp_kernels as ogp
 
 dev = torch.device("cuda:0")
-which = set(sys.argv[1:]) or {"linear", "nonlinear", "fp64", "nystrom", "gp", "candidates", "gemm"}
+which = set(sys.argv[1:]) or {"linear", "nonlinear", "fp64", "nystrom", "gp", "candidates", "gemm", "host"}
 g = torch.Generator().manual_seed(0)
 d, N, M, n = 6, 6000, 256, 24
 X = (math.sqrt(2.0) * torch.randn(N, d, generator=g)).float().to(dev)
@@ -69,4 +69,25 @@ if "gemm" in which:
     torch.cuda.synchronize()
     assert float((C1 - A @ B).abs().max()) < 1e-10 and float((C2 - A @ B).abs().max()) < 1e-2
     print("[sanitize] gemm: ok", flush=True)
+    # symmetric Gram product (lower tiles + mirror, split K) and the two-K-part tgemm (more tiles than SMs)
+    Y = torch.randn(3000, 200, generator=g, dtype=torch.float64).to(dev)
+    G1 = ops.dgemm(Y, Y, True, False)
+    A2 = torch.randn(1300, 512, generator=g, dtype=torch.float64).to(dev)
+    B2 = torch.randn(7000, 512, generator=g, dtype=torch.float64).to(dev)
+    C3 = ops.tgemm(A2, B2)
+    torch.cuda.synchronize()
+    assert torch.equal(G1, G1.T) and float((G1 - Y.T @ Y).abs().max()) < 1e-9
+    assert float((C3 - A2 @ B2.T).abs().max()) < 5e-3
+    print("[sanitize] gram dgemm / k-split tgemm: ok", flush=True)
+if "host" in which:
+    # host-buffer entries: library-drawn test matrix, staged shard, row-sharded basis (one shard), block-cache trim
+    from basq_b200 import sharded
+    Xh, Zh = X.cpu().pin_memory(), Z.cpu()
+    kern = model.covar_module.forward
+    check("recombine_host (device-drawn test matrix)", *ops.recombine_host(kern, Xh, Zh, n - 1, seed=5))
+    Ush = sharded.nystrom_basis_sharded(kern, Z, n - 1, seed=5)
+    staged = ops.stage_candidates(Xh, device=dev)
+    check("staged shard + sharded basis", *sharded.recombination_sharded(None, Z, n, kern, N, 0, Ush, staged=staged))
+    ops.release_memory(dev)
+    check("after trim", *ops.recombine(kern, X, Z, U))
 print("[sanitize] done", flush=True)
