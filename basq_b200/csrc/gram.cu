@@ -253,6 +253,54 @@ int landmark_dot(basq_ctx* ctx, const KParams& kp, const LmView& lm, const doubl
   return launch_lp<1, false>(ctx, kp, lm, P, N, out, 0, coef, c0, 0);
 }
 
+// mean[p] = c0 + sum_j G[p, j]  (the per-set partial sums of landmark_dot_tc)
+__global__ void rowsum_cols_kernel(const double* __restrict__ G, int64_t n, int cols, double c0, double* __restrict__ out) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  double s = 0.0;
+  for (int j = 0; j < cols; ++j) s += G[p * cols + j];
+  out[p] = c0 + s;
+}
+
+// The same sum on the tensor-core set-sum kernel (setsum_mma.cuh) with the roles swapped: the N points are the
+// "landmarks" (128 per tile row), the n_obs observations are the "records" carrying coef as their weight, spread
+// over 8 sets so that the 256-column tiles are full; the 8 partial sums per point are added afterwards.
+// 1e10 kernel evaluations (1e7 candidates x 1002 observations) take ~5 ms this way against ~12 ms on the
+// CUDA-core kernel above - the per-candidate factors m(x) of the WSABI kernels (BASQ/_wsabi.py:216-224).
+int landmark_dot_tc(basq_ctx* ctx, const KParams& kp, const void* Xobs, int n_obs, const double* coef, double c0,
+                    const void* P, int64_t N, double* out) {
+  constexpr int SETS = 8;
+  constexpr int64_t CHUNK = 1 << 20;
+  RecPool obs;
+  BASQ_TRY(build_records(ctx, kp, BASQ_F32, Xobs, n_obs, 1.0, nullptr, coef, true, &obs));   // record weight = coef
+  DevBuf G;
+  BASQ_TRY(G.alloc(ctx, sizeof(double) * (size_t)std::min(CHUNK, N) * SETS));
+  for (int64_t p0 = 0; p0 < N; p0 += CHUNK) {
+    const int64_t cnt = std::min(CHUNK, N - p0);
+    Landmarks lmx;
+    BASQ_TRY(prep_landmarks(ctx, kp, BASQ_F32, static_cast<const float*>(P) + p0 * kp.d, cnt, nullptr, 0, &lmx));
+    SetSumArgs a;
+    a.pool = &obs;
+    a.lm = lmx.view();
+    a.off_glob = 0;
+    a.S = SETS;
+    a.p_lo = 0;
+    a.p_hi = obs.count;
+    a.nl = NL_LIN;
+    a.corrT = nullptr;
+    a.ld_corr = 0;
+    a.sz = nullptr;
+    a.G = G.as<double>();
+    a.ldg = SETS;
+    a.accumulate = false;
+    BASQ_TRY(set_sums(ctx, kp, a));
+    rowsum_cols_kernel<<<(unsigned)ceil_div64(cnt, 256), 256, 0, ctx->stream>>>(G.as<double>(), cnt, SETS, c0, out + p0);
+    ctx->launches++;
+    BASQ_CUDA(cudaGetLastError());
+  }
+  return BASQ_OK;
+}
+
 // Exact GP posterior mean / variance (likelihood noise included), BASQ/_gp.py:213-230.
 int gp_predict_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const KParams& kp, const LmView& lmobs,
                     const void* X, int64_t N, double* mean_out, double* var_out) {
@@ -265,7 +313,15 @@ int gp_predict_impl(basq_ctx* ctx, const basq_kernel_desc* desc, const KParams& 
     if (mean_out && !mean_done) BASQ_TRY(landmark_dot(ctx, kp, lmobs, desc->alpha, desc->mean_const, X, N, mean_out));
     return BASQ_OK;
   }
-  if (mean_out) BASQ_TRY(landmark_dot(ctx, kp, lmobs, desc->alpha, desc->mean_const, X, N, mean_out));
+  if (mean_out) {
+    static const bool mean_tc = [] { const char* e = getenv("BASQ_GPMEAN_TC"); return !(e && e[0] == '0'); }();
+    // the choice depends on the GP only, never on N: the per-point factors of the warped kernels must come out
+    // bit-identical for the 1e7 candidates of a session and for the handful of points of a feature / Gram call
+    if (mean_tc && desc->dtype == BASQ_F32 && N > 0 && desc->n_obs >= 64 && !ctx->scalar_setsum)
+      BASQ_TRY(landmark_dot_tc(ctx, kp, desc->Xobs, desc->n_obs, desc->alpha, desc->mean_const, X, N, mean_out));
+    else
+      BASQ_TRY(landmark_dot(ctx, kp, lmobs, desc->alpha, desc->mean_const, X, N, mean_out));
+  }
   if (!var_out || N == 0) return BASQ_OK;
   const int n_obs = desc->n_obs;
   // chunk so that V and Y (n_obs x P fp64 each) stay around 512 MB (large GEMMs: fewer, fuller waves)

@@ -53,6 +53,12 @@ if "gp" in which:
     torch.cuda.synchronize()
     assert bool(torch.isfinite(mean).all()) and bool((var > 0).all()) and bool(torch.isfinite(Phi).all())
     print("[sanitize] gp predict / features / gram: ok", flush=True)
+    # mean on the tensor-core set-sum kernel with the roles swapped (n_obs >= 64)
+    model80 = ogp.make_gp(d, 80, lengthscale=2.0, noise=1e-3, seed=2)
+    m80, _ = ops.gp_predict(ogp.VanillaGP(model80).predictive_kernel, X[:3000], want_var=False)
+    check("wsabi-l fp32, n_obs = 80", *ops.recombine(ogp.WsabiGP(model80).wsabil_kernel, X, Z, U))
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(m80).all())
 if "candidates" in which:
     Xs = sampler.sample_mvn(torch.zeros(d), 2.0 * torch.eye(d), 5000, seed=3, device=dev)
     w = sampler.calc_weights(ogp.VanillaGP(model).predictive_kernel, Xs, ratio=0.5)
