@@ -432,6 +432,8 @@ def run_ours(a, rank, world, local_rank):
         """Nystrom basis: at N > 1 the rows of K(Z, Z) are sharded over the ranks (basq_nystrom_basis_sharded)."""
         if shard_basis:
             return sharded.nystrom_basis_sharded(k, Zb, q, omega=omega, seed=seed)
+        if world > 1 and omega is None and seed is None:
+            seed = sharded._shared_seed(None, True, dev)      # every rank must draw the same test matrix
         return ops.nystrom_basis(k, Zb, q, omega=omega, want_S=False, seed=seed)[1]
 
     def step_device():
@@ -473,7 +475,7 @@ def run_ours(a, rank, world, local_rank):
         Xs = bsampler.sample_mvn(prior_mean, None, N_loc, seed=seed, offset=base, device=dev, scale_tril=prior_tril)
         Zs = Xs[: a.M] if world == 1 else bsampler.sample_mvn(prior_mean, None, a.M, seed=seed, offset=0, device=dev,
                                                               scale_tril=prior_tril)
-        U = basis(kern, Zs, omega=Omega)
+        U = basis(kern, Zs)      # the library draws the test matrix (rank 0's torch generator seeds every rank)
         if world == 1:
             return ops.recombine(kern, Xs, Zs, U)
         return sharded.recombination_sharded(Xs, Zs, a.n, kern, N_glob, base, U)
