@@ -672,6 +672,12 @@ def run_ours(a, rank, world, local_rank):
         except Exception as exc:
             line["extra"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if rank == 0:
+        try:    # scratch memory the library holds at the end of the run (block cache + host-call buffer)
+            cached, live, n_alloc = ctx.memory()
+            line["scratch_memory"] = {"cached_GB": round(cached / 1e9, 2), "live_GB": round(live / 1e9, 2),
+                                      "driver_allocations": n_alloc}
+        except Exception:
+            pass
         print(json.dumps(line), flush=True)
 
 
