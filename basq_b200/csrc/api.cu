@@ -1050,7 +1050,7 @@ int basq_gram(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_
 // kernel(X, Y) [a, b] in fp64.  tensor_correction: the posterior-covariance correction
 // (K_xX W) K_Xy - an [a, n_obs] x [n_obs, b] product - runs on the tensor cores with fp32 accuracy
 // (tgemm.cu).  Only the Nystrom range finder asks for that: its products with this matrix are
-// 3xTF32 as well, and only the span of the resulting basis matters.
+// fp32-accurate split products as well, and only the span of the resulting basis matters.
 int basq::gram_matrix(basq_ctx* ctx, const basq_kernel_desc* desc, const void* X, int64_t a, const void* Y, int64_t b,
                       double* out, bool tensor_correction, int64_t diag_col0) {
   KParams kp;
@@ -1274,7 +1274,7 @@ static int recombine_host_impl(basq_ctx* ctx, const basq_kernel_desc* desc, cons
   const size_t esz = desc->dtype == BASQ_F64 ? 8 : 4;
   trace_point(ctx, "host: enter");
   // All call-lifetime device copies of the host arguments live in ONE buffer the context keeps between calls,
-  // outside the stream-ordered pool: the pool then sees exactly the requests of the device-resident path.
+  // outside the block cache: the cache then sees exactly the requests of the device-resident path.
   DevBuf dOm;
   Piece dX, dZ, dU, didx, dw;
   double* dmu_p = nullptr;

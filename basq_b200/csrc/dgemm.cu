@@ -241,7 +241,7 @@ int launch_pipe(basq_ctx* ctx, int m, int n, int k, double alpha, const double* 
   splitk_reduce_kernel<<<(unsigned)ceil_div64((int64_t)m * n, 256), 256, 0, ctx->stream>>>(part.as<double>(), splits, m, n,
                                                                                           alpha, beta, C, ldc, sym);
   ctx->launches++;
-  return BASQ_OK;  // `part` returns to the stream-ordered pool after the reduction
+  return BASQ_OK;  // `part` returns to the context's block cache; stream order keeps it intact until the reduction has run
 }
 
 // tile shape that needs the fewest SM-waves of work for an m x n output

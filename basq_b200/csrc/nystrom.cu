@@ -534,7 +534,7 @@ int nystrom_basis(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, in
   BASQ_CUDA(cudaMemsetAsync(ws.flags.p, 0, 512, ctx->stream));
   BASQ_TRY(ws.scal.alloc(ctx, 64));
   const int Mi = (int)M;
-  // Y_out [M, q] = K Y_in.  fp32 kernels: on the tensor cores (3xTF32, tgemm.cu) - the Gram matrix itself
+  // Y_out [M, q] = K Y_in.  fp32 kernels: on the tensor cores (fp16 hi/lo split products, tgemm.cu) - the Gram matrix itself
   // is only fp32-accurate, and the subspace iteration re-orthonormalises in fp64 after every product;
   // fp64 kernels: fp64 GEMM.  K is symmetric, so K^T Y = K Y.
   const bool tensor = (desc->dtype == BASQ_F32) && !ctx->no_tensor_nystrom;
@@ -561,7 +561,7 @@ int nystrom_basis(basq_ctx* ctx, const basq_kernel_desc* desc, const void* Z, in
   BASQ_TRY(Y2.alloc(ctx, sizeof(double) * (size_t)M * q));
   // Within a power iteration (K^T then K) the intermediate basis need not be re-orthonormalised when
   // the spectrum behind the basis is flat enough: two products damp the weakest captured direction by
-  // (sigma_q / sigma_1)^2 relative to the strongest, which must stay well above the 3xTF32 rounding
+  // (sigma_q / sigma_1)^2 relative to the strongest, which must stay well above the split product's rounding
   // (1e-7) of the second product.  sigma_q / sigma_1 is read off the diagonal of the Cholesky factor
   // of the first CholeskyQR pass (L^-1 is at hand).  Measured at M = 1e4, q = 999, d = 10 (spread 0.38):
   // the captured trace tr(U K U^T) agrees to 9 digits with the fully re-orthonormalised run

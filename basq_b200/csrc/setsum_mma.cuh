@@ -4,11 +4,13 @@
 //
 // The exponent argument of every kernel family is bilinear in prepared operands,
 //   arg(m, p) = a_p + b_m + sum_i x'_{p,i} zz_{m,i}        (see common.cuh: KParams),
-// so a 128-landmark x NT-point tile of arguments is ONE small GEMM with K = 3 DP + 6:
-//   * x' and zz are split into tf32 "hi + lo" parts and the three significant cross products
-//     (hi hi, lo hi, hi lo) occupy three K columns per dimension (3xTF32: ~2^-21 relative);
-//   * a_p and b_m ride along as three tf32 pieces each against constant-one columns.
-// tcgen05.mma (kind::tf32, M = 128, N = NT, operands K-major in shared memory, no swizzle) writes the
+// so a 128-landmark x NT-point tile of arguments is ONE small GEMM with K = 3 DP + 6 (padded to the MMA's K step):
+//   * x' and zz are split into "hi + lo" parts with 11 significant bits each - fp16 by default
+//     (BASQ_SETSUM_F16, kind::f16: K = 48 at d = 10, three MMAs per tile), tf32 in round 1 (kind::tf32, K = 40,
+//     five MMAs) - and the three significant cross products (hi hi, lo hi, hi lo) occupy three K columns per
+//     dimension (~2^-21 relative);
+//   * a_p and b_m ride along as three pieces each against constant-one columns.
+// tcgen05.mma (M = 128, N = NT, operands K-major in shared memory, no swizzle) writes the
 // argument tile into TMEM; the epilogue warps read it back with tcgen05.ld, apply exp2 / the Matern
 // polynomial on the MUFU/FMA pipes and accumulate w_p * k in fp64 - one accumulator per (landmark,
 // set).  What remains on the CUDA cores per pair is 1 MUFU + 2 integer ops + 1 DFMA; the DP-long

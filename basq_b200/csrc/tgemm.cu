@@ -355,7 +355,7 @@ int blk_from_f64(basq_ctx* ctx, const double* src, int64_t ld, bool transposed, 
                                                            op->hi.as<__half>(), op->lo.as<__half>());
   ctx->launches += 2;
   BASQ_CUDA(cudaGetLastError());
-  return BASQ_OK;   // `rscale` returns to the stream-ordered pool behind the split kernel
+  return BASQ_OK;   // `rscale` returns to the context's block cache; stream order keeps it intact until the split kernel has run
 }
 
 int tgemm(basq_ctx* ctx, const BlkOperand& A, const BlkOperand& B, double alpha, double* out, int64_t ldo,
